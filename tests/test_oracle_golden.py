@@ -174,14 +174,13 @@ def test_window_indexing_goldens(golden_dir):
 
 
 def test_wta_and_step_goldens_from_reference_tests():
-  """test/attention_decoder_test.py:111-150 style sequences."""
-  r1 = np.array([1, 2, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1], dtype=float)
-  r2 = np.array([2, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 0], dtype=float)
-  np.testing.assert_array_equal(ora.wta_attention(r1, r2),
-                                [False, True, True] + [False] * 8 + [True])
-  step = ora.step_attention(np.ones(6), np.zeros(6))
-  np.testing.assert_array_equal(step, [True] * 6)
-  step = ora.step_attention(np.r_[np.ones(5), np.zeros(5)], np.r_[np.zeros(5), np.ones(5)])
-  # 0.6 .7 .8 .9 .9 | .8 .7 .6 .5 .4
-  np.testing.assert_array_equal(step, [True] * 8 + [False, False])
+  """test/attention_decoder_test.py:111-150 literal sequences (the step decoder's
+  0.5000000000000001 > 0.5 floating-point quirk included)."""
+  cor2 = np.ones(13)
+  cor1 = np.array([2] * 7 + [0] * 6, dtype=float)
+  np.testing.assert_array_equal(ora.wta_attention(cor1, cor2), [1] * 7 + [0] * 6)
+  np.testing.assert_array_equal(ora.step_attention(cor1, cor2), [1] * 11 + [0] * 2)
+  cor1 = np.array([2] * 2 + [0] * 11, dtype=float)
+  np.testing.assert_array_equal(ora.step_attention(cor1, cor2), [1] * 3 + [0] * 10)
+  assert ora.wta_attention(0.6, 0.4) and not ora.wta_attention(0.4, 0.6)
   assert ora.aad_accuracy([True, False, True], [0, 1, 0]) == 1.0
