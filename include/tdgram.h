@@ -1,0 +1,185 @@
+/*
+ * tdgram.h -- C ABI of libtdgram.so, the B200 (sm_100a) implementation of the dense
+ * decoding hot path of google/telluride_decoding.
+ *
+ * The reference has no FFI seam: its hot path is numpy called from Python
+ * (telluride_decoding/brain_model.py:429-481, cca.py:311-369, infer_decoder.py:288-328,
+ * result_store.py:253-338).  Each entry point below names the reference code it replaces.
+ * The Python package telluride_decoding_b200 binds these with ctypes
+ * (telluride_decoding_b200/_lib.py); INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative td_status; td_last_error() gives a
+ *     thread-local message.  Nothing throws, nothing allocates caller-visible memory.
+ *   - Pointers named *_dev are CUDA device pointers (they come from torch tensors that crossed
+ *     by DLPack); `segments` tables and lambda lists are small HOST arrays.
+ *   - All work is enqueued on `cuda_stream` (a cudaStream_t cast to void*, NULL = default
+ *     stream).  Functions do not synchronise unless documented.
+ *   - Matrices are row-major float32 unless stated.
+ *
+ * Lag (temporal context) semantics -- brain_data.py:425-483.  A *stream* is a raw
+ * [rows, channels] array cut into *segments* (one per trial file and per
+ * `initial_batch_size` chunk).  Design row t of segment s is
+ *     X_s[t, k*C + c] = x_s[t - pre + k, c]   for k in [0, pre+1+post),  0 outside [0, len_s)
+ * and only the first keep[s] rows of each segment are used (`drop_remainder`,
+ * brain_data.py:369-370).  The lagged design is never written to memory.
+ */
+#ifndef TDGRAM_H_
+#define TDGRAM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TD_VERSION 100
+
+typedef enum td_status {
+  TD_OK = 0,
+  TD_ERR_INVALID = -1,      /* bad argument (message says which) */
+  TD_ERR_WORKSPACE = -2,    /* workspace too small */
+  TD_ERR_CUDA = -3,         /* CUDA runtime / driver error */
+  TD_ERR_SOLVER = -4,       /* cuSOLVER / cuBLAS failure or singular system */
+  TD_ERR_UNSUPPORTED = -5   /* shape outside what the kernels handle */
+} td_status;
+
+/* One raw input stream with its lag spec.  seg_start/seg_len are HOST arrays of n_seg entries. */
+typedef struct td_stream {
+  const float* data_dev;     /* [rows, channels], row stride ld elements */
+  int64_t ld;
+  int32_t channels;
+  int32_t pre;               /* pre_context  (brain_data.py:104) */
+  int32_t post;              /* post_context (brain_data.py:105) */
+  const int64_t* seg_start;  /* first raw row of segment i in data_dev */
+  const int64_t* seg_len;    /* raw rows in segment i: zero padding begins at seg_len[i] */
+} td_stream;
+
+const char* td_last_error(void);
+int td_version(void);
+/* Number of SMs / compute capability of the current device (for the bench's roofline). */
+int td_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------
+ * Lagged Gram.  Replaces the minibatch loop `sum_xtx += np.matmul(x.T, x)`
+ * (brain_model.py:437) and the three products cov_xx/cov_yy/cov_xy of cca.py:325-327.
+ *
+ * The design is Z = [X_0 | X_1 | ...] over n_streams (1 or 2) lagged streams sharing the
+ * segment table; G = Z'Z, [Dz, Dz] with Dz = sum_q channels_q * (pre_q+1+post_q), full
+ * symmetric, row stride ldg.  method 0: tcgen05 3xTF32 implicit-Hankel kernel (TMA-staged,
+ * TMEM fp32 accumulation flushed every `chunk_rows` frames into fp32 registers);
+ * method 1: fp32 CUDA-core kernel kept as an on-device cross-check.
+ * Workspace: td_lagged_gram_workspace_bytes bytes of device memory.
+ * ------------------------------------------------------------------------------------- */
+typedef struct td_gram_options {
+  int32_t method;        /* 0 = tcgen05 3xTF32 (default), 1 = fp32 SIMT cross-check */
+  int32_t cta_group;     /* 0 = auto, 1 = 128x128 tiles per CTA, 2 = CTA-pair 256x256 tiles */
+  int32_t chunk_rows;    /* TMEM flush period in frames (0 = default 512) */
+  int32_t superchunk_rows; /* L2 working-set period in frames (0 = auto) */
+  int32_t max_ctas;      /* 0 = all SMs */
+  int32_t reserved[3];
+} td_gram_options;
+
+int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_streams,
+                                   const int64_t* seg_keep, int n_seg,
+                                   const td_gram_options* opt, size_t* bytes);
+int td_lagged_gram_f32(const td_stream* streams, int n_streams,
+                       const int64_t* seg_keep, int n_seg,
+                       float* G_dev, int64_t ldg, const td_gram_options* opt,
+                       void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Thin products against the un-lagged targets and the ones column.  Replaces
+ * `sum_xty += x.T @ y`, `sum_x += sum(x)` and the hstack'ed ones column
+ * (brain_model.py:436-439), `sum_x`/`sum_y` of cca.py:328-329.
+ *   V = [v_0 .. v_{Q-2}, 1]  (v = thin stream without lags, may be NULL: then V = [1])
+ *   xtv_dev [Dx, Q] double  = X'V        vtv_dev [Q, Q] double = V'V   (V'V[Q-1,Q-1] = row count)
+ * Both are zeroed by the call.  Q = (v ? v->channels : 0) + 1 <= 16.
+ * ------------------------------------------------------------------------------------- */
+int td_lagged_thin_f64(const td_stream* x, const td_stream* v,
+                       const int64_t* seg_keep, int n_seg,
+                       double* xtv_dev, double* vtv_dev, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Forward pass.  Replaces Keras Dense on the lagged batch (brain_model.py:340-341) and one half
+ * of BrainCcaLayer.call (cca.py:157-158):
+ *   out[out_row[s] + t, :] = (X_s[t, :] - mean) W + bias      t < keep[s]
+ * W [Dx, Dy] row-major, bias [Dy] or NULL, mean [Dx] or NULL, out row stride ldo, Dy <= 64.
+ * out_row is a HOST array.
+ * ------------------------------------------------------------------------------------- */
+int td_lagged_predict_f32(const td_stream* x, const int64_t* seg_keep, const int64_t* out_row,
+                          int n_seg, const float* W_dev, const float* bias_dev,
+                          const float* mean_dev, int Dy, float* out_dev, int64_t ldo,
+                          void* cuda_stream);
+
+/* The lagged rows themselves (compatibility iterator / tests only; brain_data.py:453-455). */
+int td_lagged_rows_f32(const td_stream* x, const int64_t* seg_keep, const int64_t* out_row,
+                       int n_seg, float* out_dev, int64_t ldo, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Solves (cuSOLVER/cuBLAS inside, float64 internally -- stated non-hot-path dependency).
+ *
+ * td_ridge_solve: brain_model.py:447-454, :477-479.  A = G_aug / n + lambda I over ALL rows
+ * (bias row included), B = C_aug / n, solution = A^-1 B for every lambda.
+ *   G_aug_dev [Da, Da] double (Da = D+1 with the ones column last, or D when no offset)
+ *   C_aug_dev [Da, Dy] double;  W_out_dev [n_lambda, Da, Dy] float32.
+ *   method 0: Cholesky per lambda (LU if not positive definite); 1: one eigendecomposition
+ *   reused for the whole sweep.  Synchronises the stream.
+ * ------------------------------------------------------------------------------------- */
+int td_ridge_solve(const double* G_aug_dev, const double* C_aug_dev, int Da, int Dy, double n,
+                   const double* lambdas, int n_lambda, int method, float* W_out_dev,
+                   void* cuda_stream);
+
+/* td_cca_solve: cca.py:337-367.  Inputs are raw sums (double): Gxx [D1,D1], Gyy [D2,D2],
+ * Gxy [D1,D2], sum_x [D1], sum_y [D2]; n_frames = total rows, n_norm = n_batches*n_row - 1.
+ * Outputs float32: rot_x [D1,dim], rot_y [D2,dim], mean_x [D1], mean_y [D2], e [dim].
+ * Signs: each (rot_x[:,i], rot_y[:,i]) pair is normalised so that the entry of rot_x[:,i] with
+ * the largest magnitude is positive.  Synchronises the stream. */
+int td_cca_solve(const double* Gxx_dev, const double* Gyy_dev, const double* Gxy_dev,
+                 const double* sum_x_dev, const double* sum_y_dev, int D1, int D2,
+                 double n_frames, double n_norm, double reg, double eps_eig, int dim,
+                 float* rot_x_dev, float* rot_y_dev, float* mean_x_dev, float* mean_y_dev,
+                 float* e_dev, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Correlation / windows / decision.
+ *
+ * td_column_moments_f64: the Decoder's streaming statistics, infer_decoder.py:299-303.
+ *   sums_dev [4, dims] double += [sum a, sum b, sum a^2, sum b^2] over n rows (NOT zeroed).
+ * ------------------------------------------------------------------------------------- */
+int td_column_moments_f64(const float* a_dev, int64_t lda, const float* b_dev, int64_t ldb,
+                          int64_t n, int dims, double* sums_dev, void* cuda_stream);
+
+/* td_windowed_corr_f32: sliding windows [i*S, i*S+W) per segment while W frames remain
+ * (result_store.py:262-271; count (n-W)//S + 1).
+ *   mode 0  plain:   value = float64 mean over the window of a[t, 0]           (infer.py:264-265)
+ *   mode 1  global:  c[t,d] = (a-mu_a)(b-mu_b)/power in float32 (infer_decoder.py:327-328),
+ *                    reduced over d by `reduction` (0 first, 1 second, 2 mean, 3 mean-squared;
+ *                    infer_decoder.py:441-450), then float64 window mean
+ *   mode 2  local:   Pearson r per window and column from the five sums
+ *                    (brain_model.py:62-79); out has `dims` columns, and a window whose
+ *                    product of powers over columns is <= 0 yields zeros
+ * seg_start/seg_len HOST arrays (rows of a/b); n_sizes window shapes (W[j], S[j]) are evaluated
+ * in ONE pass over the data.  out_dev is double [total_windows, out_cols]; windows are ordered
+ * size-major, then segment, then window index; out_offset (HOST, n_sizes+1 entries, may be
+ * NULL) receives the first window row of each size. */
+int td_windowed_corr_f32(const float* a_dev, int64_t lda, const float* b_dev, int64_t ldb,
+                         int dims, const int64_t* seg_start, const int64_t* seg_len, int n_seg,
+                         const int64_t* W, const int64_t* S, int n_sizes, int mode, int reduction,
+                         const float* mu_a_dev, const float* mu_b_dev, const float* power_dev,
+                         double* out_dev, int64_t* out_offset, void* cuda_stream);
+int64_t td_window_count(int64_t n_frames, int64_t W, int64_t S);
+
+/* Winner-take-all: out[i] = r1[i] > r2[i] (attention_decoder.py:134). */
+int td_wta_decide_u8(const double* r1_dev, const double* r2_dev, int64_t n, uint8_t* out_dev,
+                     void* cuda_stream);
+
+/* Utility: out[j, i] = out[i, j] for j > i (mirror the computed triangle). */
+int td_symmetrize_f32(float* G_dev, int64_t n, int64_t ldg, int from_upper, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* TDGRAM_H_ */

@@ -1,0 +1,540 @@
+"""Data layer: the reference's BrainData surface, without ever building the lagged design.
+
+Mirrors telluride_decoding/brain_data.py (constructor arguments :99-118, create_dataset
+:219-243, TestBrainData.preserve_test_data :588-642, filter_file_names :253-323,
+create_brain_dataset :959-1049).  What changes is the object create_dataset returns: a
+`LaggedDataset` holding the RAW per-trial [frames, channels] tensors on the GPU, the lag spec
+and the row plan (segments, kept rows, batch size).  The models' fit / evaluate / predict hand
+that straight to the CUDA kernels; iterating it yields the same `(dict, y)` minibatches the
+reference's tf.data pipeline produces (built by td_lagged_rows_f32) for tests and compatibility.
+
+Row-set semantics reproduced exactly:
+  * context and input_offset are applied per file and per `initial_batch_size` chunk
+    (brain_data.py:485-502): each chunk is a *segment* with zero padding at both ends;
+  * files are interleaved round-robin, one row at a time (brain_data.py:725-728);
+  * `batch(final_batch_size, drop_remainder=True)` drops the tail of that stream
+    (brain_data.py:369-370), which is a per-file prefix of kept rows.
+Shuffling (shuffle_buffer_size > 0) cannot be reproduced bit-for-bit (tf.data's RNG); the
+batches are then shuffled with a torch generator and the dropped remainder is taken from the
+un-shuffled tail.  The reference's regression presets run with shuffle_buffer_size = 0
+(regression.py:459, :479).
+"""
+
+import random
+import re
+
+import numpy as np
+import torch
+
+from telluride_decoding_b200 import _lib
+from telluride_decoding_b200 import ops
+
+
+class TensorSpec(object):
+  """Stand-in for tf.TensorSpec: `.shape[-1]` is what the models read (brain_model.py:329-330)."""
+
+  def __init__(self, shape, dtype=torch.float32):
+    self.shape = tuple(shape)
+    self.dtype = dtype
+
+  def __repr__(self):
+    return 'TensorSpec(shape=%s)' % (self.shape,)
+
+
+class FixedLenFeature(object):
+  """Stand-in for tf.io.FixedLenFeature (brain_data.py:616-619): shape + dtype."""
+
+  def __init__(self, shape, dtype='float32'):
+    self.shape = list(shape)
+    self.dtype = dtype
+
+
+def interleave_kept_prefix(lengths, kept_total):
+  """Rows each file keeps when the round-robin stream is cut after `kept_total` elements.
+
+  Stream order: round r emits row r of every file with more than r rows, in file order
+  (tf.data interleave, cycle_length = n_files, block_length = 1; brain_data.py:725-728).
+  """
+  lengths = [int(n) for n in lengths]
+  kept = [0] * len(lengths)
+  remaining = int(kept_total)
+  if remaining <= 0:
+    return kept
+  # Largest round count R such that sum_f min(n_f, R) <= kept_total.
+  lo, hi = 0, max(lengths + [0])
+  while lo < hi:
+    mid = (lo + hi + 1) // 2
+    if sum(min(n, mid) for n in lengths) <= remaining:
+      lo = mid
+    else:
+      hi = mid - 1
+  full_rounds = lo
+  for f, n in enumerate(lengths):
+    kept[f] = min(n, full_rounds)
+  remaining -= sum(kept)
+  for f, n in enumerate(lengths):
+    if remaining <= 0:
+      break
+    if n > full_rounds:
+      kept[f] += 1
+      remaining -= 1
+  return kept
+
+
+def interleave_order(lengths):
+  """(file index, row index) of every element of the interleaved stream, in order."""
+  lengths = np.asarray(lengths, dtype=np.int64)
+  if lengths.size == 0 or lengths.max() == 0:
+    return np.zeros((0,), np.int64), np.zeros((0,), np.int64)
+  rounds = np.arange(int(lengths.max()), dtype=np.int64)
+  alive = rounds[:, None] < lengths[None, :]            # [round, file]
+  r_idx, f_idx = np.nonzero(alive)                      # row-major: round, then file order
+  return f_idx.astype(np.int64), r_idx.astype(np.int64)
+
+
+class LaggedDataset(object):
+  """Raw trials + lag spec + row plan: the object the models consume natively.
+
+  Iterating yields `({'input_1', 'input_2', 'attended_speaker'}, y)` float32 CUDA minibatches
+  exactly as brain_data.final_shuffle_and_batch (:325-393) would.
+  """
+
+  def __init__(self, x, x2, y, a, files, pre, post, pre2, post2, input_offset,
+               initial_batch_size, final_batch_size, repeat_count, shuffle_buffer_size, mode,
+               temporal_context=True, offset_counts=True, mixup_batch=False):
+    # x, x2, y, a: concatenated [frames, channels] CUDA tensors; files: [(name, start, length)].
+    self.x, self.x2, self.y, self.a = x, x2, y, a
+    self.files = list(files)
+    self.mode = mode
+    self.final_batch_size = int(final_batch_size)
+    self.repeat_count = int(repeat_count) if mode == 'train' else 1
+    shuffles = mode != 'program_test' and shuffle_buffer_size > 0
+    self.shuffle_buffer_size = int(shuffle_buffer_size) if shuffles else 0
+    self.mixup_batch = mixup_batch
+    wants = temporal_context and (pre or post or pre2 or post2 or
+                                  (input_offset if offset_counts else 0))
+    if wants:
+      self.pre, self.post, self.pre2, self.post2 = int(pre), int(post), int(pre2), int(post2)
+      self.input_offset = int(input_offset)
+      chunk = int(initial_batch_size)
+    else:
+      self.pre = self.post = self.pre2 = self.post2 = self.input_offset = 0
+      chunk = None
+    # ---- segments: one per (file, chunk)                      brain_data.py:492, :466-483
+    seg_file, sx, lx, s2, l2, rows = [], [], [], [], [], []
+    o = self.input_offset
+    for f, (_, start, length) in enumerate(self.files):
+      step = chunk or max(length, 1)
+      for c0 in range(0, length, step):
+        n = min(step, length - c0)
+        n_rows = max(n - abs(o), 0)
+        seg_file.append(f)
+        sx.append(start + c0 + max(o, 0)); lx.append(max(n - max(o, 0), 0))
+        s2.append(start + c0 + max(-o, 0)); l2.append(max(n - max(-o, 0), 0))
+        rows.append(n_rows)
+    self.seg_file = seg_file
+    self.seg_rows = rows
+    self._sx, self._lx, self._s2, self._l2 = sx, lx, s2, l2
+    # ---- kept rows: per-file prefix of the interleaved stream         brain_data.py:369-370
+    file_rows = [0] * len(self.files)
+    for f, n in zip(seg_file, rows):
+      file_rows[f] += n
+    self.file_rows = file_rows
+    self.total_rows = sum(file_rows)
+    b = self.final_batch_size
+    stream_len = self.total_rows * self.repeat_count
+    self.num_batches = stream_len // b if b > 0 else 0
+    kept_stream = self.num_batches * b
+    self.full_repeats = kept_stream // self.total_rows if self.total_rows else 0
+    self.partial_rows = kept_stream - self.full_repeats * self.total_rows
+    self.element_spec = (
+        {'input_1': TensorSpec((None, x.shape[1] * (self.pre + 1 + self.post))),
+         'input_2': TensorSpec((None, x2.shape[1] * (self.pre2 + 1 + self.post2))),
+         'attended_speaker': TensorSpec((None, a.shape[1]))},
+        TensorSpec((None, y.shape[1])))
+
+  # ---------------------------------------------------------------- plans for the kernels
+  def seg_keep_for_prefix(self, kept_total):
+    """Kept rows per segment when the stream is cut after `kept_total` elements."""
+    per_file = interleave_kept_prefix(self.file_rows, kept_total)
+    keep, used = [], [0] * len(self.files)
+    for f, n in zip(self.seg_file, self.seg_rows):
+      k = min(n, max(per_file[f] - used[f], 0))
+      keep.append(k)
+      used[f] += n
+    return keep
+
+  def passes(self):
+    """[(weight, seg_keep)]: the kept multiset of rows as weighted prefixes of one epoch."""
+    out = []
+    if self.full_repeats:
+      out.append((float(self.full_repeats), list(self.seg_rows)))
+    if self.partial_rows:
+      out.append((1.0, self.seg_keep_for_prefix(self.partial_rows)))
+    return out
+
+  def stream(self, which):
+    """ops.Stream of 'x' (input_1), 'x2' (input_2), 'y' (output) or 'a' (attention)."""
+    if which == 'x':
+      return ops.Stream(self.x, self.pre, self.post, self._sx, self._lx)
+    data = {'x2': self.x2, 'y': self.y, 'a': self.a}[which]
+    pre, post = (self.pre2, self.post2) if which == 'x2' else (0, 0)
+    if which == 'a':      # the attention stream is not shifted by input_offset (brain_data.py:471-475)
+      o = self.input_offset
+      starts = [s - max(o, 0) for s in self._sx]
+      lens = [l + max(o, 0) for l in self._lx]
+      return ops.Stream(data, 0, 0, starts, lens)
+    return ops.Stream(data, pre, post, self._s2, self._l2)
+
+  def seg_out_rows(self):
+    """First output row of each segment when all rows are laid out file after file."""
+    out, cur = [], 0
+    for n in self.seg_rows:
+      out.append(cur)
+      cur += n
+    return out
+
+  def stream_permutation(self, kept_total=None):
+    """int64 CUDA index: position in file-major row order of each stream element (one epoch)."""
+    fi, ri = interleave_order(self.file_rows)
+    file_base = np.concatenate(([0], np.cumsum(self.file_rows)[:-1])).astype(np.int64)
+    idx = file_base[fi] + ri
+    if kept_total is not None:
+      idx = idx[:kept_total]
+    return torch.from_numpy(idx).to(self.x.device)
+
+  def unlagged_rows(self, which):
+    """Rows of an un-lagged stream ('y' or 'a') in file-major order, [total_rows, channels]."""
+    s = self.stream(which)
+    parts = [s.data[st:st + n] for st, n in zip(s.seg_start, self.seg_rows)]
+    return torch.cat(parts, dim=0) if len(parts) != 1 else parts[0]
+
+  # ---------------------------------------------------------------- reference-style iteration
+  def __iter__(self):
+    if self.num_batches == 0:
+      return
+    out_rows = self.seg_out_rows()
+    x = ops.lagged_rows(self.stream('x'), self.seg_rows, out_rows, self.total_rows)
+    x2 = ops.lagged_rows(self.stream('x2'), self.seg_rows, out_rows, self.total_rows)
+    y = self.unlagged_rows('y')
+    a = self.unlagged_rows('a')
+    perm = self.stream_permutation()
+    if self.repeat_count > 1:
+      perm = perm.repeat(self.repeat_count)
+    b = self.final_batch_size
+    perm = perm[:self.num_batches * b]
+    if self.shuffle_buffer_size > 0:
+      gen = torch.Generator(device='cpu')
+      gen.manual_seed(random.getrandbits(31))
+      perm = perm[torch.randperm(perm.numel(), generator=gen).to(perm.device)]
+    for i in range(self.num_batches):
+      sel = perm[i * b:(i + 1) * b]
+      bx2, by = x2[sel], y[sel]
+      if self.mixup_batch:           # brain_data.py:378-382: shuffle x2 and y within the batch
+        bx2 = bx2[torch.randperm(b, device=bx2.device)]
+        by = by[torch.randperm(b, device=by.device)]
+      yield ({'input_1': x[sel], 'input_2': bx2, 'attended_speaker': a[sel]}, by)
+
+  def take(self, count):
+    """First `count` minibatches (count < 0: all), like tf.data.Dataset.take."""
+    batches = []
+    for i, item in enumerate(self):
+      if 0 <= count <= i:
+        break
+      batches.append(item)
+    return batches
+
+  def __repr__(self):
+    return ('<LaggedDataset mode=%s files=%d rows=%d batches=%d x %d ctx=(%d,%d|%d,%d) off=%d>' %
+            (self.mode, len(self.files), self.total_rows, self.num_batches,
+             self.final_batch_size, self.pre, self.post, self.pre2, self.post2,
+             self.input_offset))
+
+
+class BrainData(object):
+  """Describes the data of an experiment (brain_data.py:80-199); base class."""
+
+  def __init__(self, in_fields, out_field, frame_rate, pre_context=0, post_context=0,
+               in2_fields=None, in2_pre_context=0, in2_post_context=0, input_offset=0,
+               attended_field=None, initial_batch_size=1000000, final_batch_size=1000,
+               repeat_count=1, shuffle_buffer_size=1000, data_dir=None, data_pattern='',
+               train_file_pattern='', validate_file_pattern='', test_file_pattern=''):
+    if not in_fields:
+      raise ValueError('Must specify at least one input field.')
+    if not out_field:
+      raise ValueError('Must specify an output field.')
+    if frame_rate < 0:
+      raise ValueError('frame_rate must be >= 0')
+    if pre_context < 0:
+      raise ValueError('pre_context must be >= 0')
+    if post_context < 0:
+      raise ValueError('post_context must be >= 0')
+    if isinstance(in_fields, str):
+      in_fields = [in_fields,]
+    self.in1_fields = in_fields
+    if isinstance(in2_fields, str) and in2_fields:
+      in2_fields = [in2_fields,]
+    self.in2_fields = in2_fields
+    self.out_field = out_field
+    self.frame_rate = frame_rate
+    self.in1_pre_context = pre_context
+    self.in1_post_context = post_context
+    self.in2_pre_context = in2_pre_context
+    self.in2_post_context = in2_post_context
+    self.input_offset = input_offset
+    self.attended_field = attended_field
+    self.initial_batch_size = initial_batch_size
+    self.final_batch_size = final_batch_size
+    self.repeat_count = repeat_count
+    self.shuffle_buffer_size = shuffle_buffer_size
+    self.data_dir = data_dir
+    self.data_pattern = data_pattern
+    self.train_file_pattern = train_file_pattern or ''
+    self.validate_file_pattern = validate_file_pattern or ''
+    self.test_file_pattern = test_file_pattern or ''
+    self.use_saved_data = False
+    self._cached_file_names = []
+    self.all_files()
+
+  def all_files(self, max_count=0):
+    """List of files (trials) available; shuffled once (brain_data.py:201-210)."""
+    if not self._cached_file_names:
+      self._get_data_file_names()
+      if self._cached_file_names:
+        random.shuffle(self._cached_file_names)
+    if max_count > 0 and len(self._cached_file_names) > max_count:
+      return self._cached_file_names[:max_count]
+    return self._cached_file_names
+
+  def set_file_patterns(self, train, validate, test):
+    self.train_file_pattern = train
+    self.validate_file_pattern = validate
+    self.test_file_pattern = test
+
+  def create_dataset(self, mode='train', temporal_context=True, mixup_batch=False):
+    raise NotImplementedError
+
+  def _get_data_file_names(self):
+    self._cached_file_names = []
+
+  def filter_file_names(self, mode):
+    """Files used in `mode` (brain_data.py:253-323), incl. the allbut / allbut_NN patterns."""
+    if mode == 'program_test':
+      mode = 'test'
+    if mode not in set(['test', 'validate', 'train']):
+      raise ValueError('mode must be one of test, validate or train')
+    filename_list = self.all_files()
+    if not isinstance(filename_list, list):
+      raise TypeError('Filename_list is a %s, not a list.' % type(filename_list))
+    if mode.startswith('test'):
+      pattern_re = re.compile(self.test_file_pattern)
+    elif mode.startswith('validate'):
+      pattern_re = re.compile(self.validate_file_pattern)
+    else:
+      if self.train_file_pattern == 'allbut':
+        pattern_re = re.compile('')
+      else:
+        pattern_re = re.compile(self.train_file_pattern)
+    if mode == 'train' and self.train_file_pattern.startswith('allbut'):
+      if not (self.test_file_pattern and self.validate_file_pattern):
+        raise ValueError('Both test and validate must be specified if using '
+                         'allbut pattern')
+      test_re = re.compile(self.test_file_pattern)
+      validate_re = re.compile(self.validate_file_pattern)
+      filename_list = [f for f in filename_list
+                       if not (test_re.search(f) or validate_re.search(f))]
+      if self.train_file_pattern.startswith('allbut_'):
+        allbut = self.train_file_pattern.replace('allbut_', '', 1)
+        if allbut.isdigit():
+          count = int(allbut)
+        else:
+          raise ValueError('allbut_ spec must be an integer, not %s.' % allbut)
+        if count < len(filename_list):
+          filename_list = filename_list[:count]
+    else:
+      filename_list = [f for f in filename_list if pattern_re.search(f)]
+    return filename_list
+
+  def input_fields_width(self, input_number=1):
+    """Feature width after adding context (brain_data.py:505-541)."""
+    if input_number != 1 and input_number != 2:
+      raise ValueError('Only 1st or 2nd input is supported here.')
+    fields = self.in1_fields if input_number == 1 else self.in2_fields
+    if isinstance(fields, str) and fields:
+      fields = [fields,]
+    if fields:
+      for k in fields:
+        if k not in list(self.features.keys()):
+          raise TypeError('Can\'t find **%s** in valid features: %s' %
+                          (k, [','.join(list(self.features.keys()))]))
+      widths = [self.features[k].shape[0] for k in fields]
+    else:
+      widths = [1]
+    if input_number == 1:
+      return sum(widths) * (self.in1_pre_context + 1 + self.in1_post_context)
+    return sum(widths) * (self.in2_pre_context + 1 + self.in2_post_context)
+
+  def output_field_width(self):
+    if self.out_field not in list(self.features.keys()):
+      raise ValueError('Could not find output_field **%s** in %s' %
+                       (self.out_field, self.features.keys()))
+    return self.features[self.out_field].shape[0]
+
+  # Shared by the in-memory classes below.
+  def _make_dataset(self, mode, files, temporal_context, mixup_batch, offset_counts):
+    return LaggedDataset(
+        self._x, self._x2, self._y, self._a, files, self.in1_pre_context,
+        self.in1_post_context, self.in2_pre_context, self.in2_post_context, self.input_offset,
+        self.initial_batch_size, self.final_batch_size, self.repeat_count,
+        self.shuffle_buffer_size, mode, temporal_context=temporal_context,
+        offset_counts=offset_counts, mixup_batch=mixup_batch)
+
+
+def _check_2d(name, data):
+  if data.dim() != 2:
+    raise ValueError('%s must be 2-D (frames x channels), not %s' % (name, tuple(data.shape)))
+  return data
+
+
+class TestBrainData(BrainData):
+  """Dataset which produces fixed (saved) values (brain_data.py:550-642)."""
+
+  __test__ = False   # not a pytest class
+
+  def create_dataset(self, mode='train', temporal_context=True, mixup_batch=False):
+    if not hasattr(self, '_x'):
+      raise ValueError('Must call preserve_test_data before create_dataset.')
+    files = [('saved', 0, int(self._x.shape[0]))]
+    return self._make_dataset(mode, files, temporal_context, mixup_batch, offset_counts=True)
+
+  def preserve_test_data(self, input_data, output_data, input2_data=None, attention_data=None):
+    """Puts arrays (numpy, torch or DLPack) into the dataset (brain_data.py:588-642)."""
+    x = _check_2d('input_data', _lib.as_device_f32(input_data))
+    y = _check_2d('output_data', _lib.as_device_f32(output_data))
+    if x.shape[0] != y.shape[0]:
+      raise ValueError('input shape (%s) and output shape (%s) are not equal.' %
+                       (tuple(x.shape), tuple(y.shape)))
+    self.saved_input_data = x
+    self.saved_output_data = y
+    self.num_input_channels = int(x.shape[1])
+    self.num_output_channels = int(y.shape[1])
+    self.features = {'input_1': FixedLenFeature([int(x.shape[1]),]),
+                     'output': FixedLenFeature([int(y.shape[1]),])}
+    if input2_data is None:
+      x2 = torch.zeros((x.shape[0], 1), dtype=torch.float32, device=x.device)
+    else:
+      x2 = _check_2d('input2_data', _lib.as_device_f32(input2_data))
+    if x.shape[0] != x2.shape[0]:
+      raise ValueError('input shape (%s) and input2 shape (%s) are not equal.' %
+                       (tuple(x.shape), tuple(x2.shape)))
+    self.saved_input2_data = x2
+    self.features['input_2'] = FixedLenFeature([int(x2.shape[1]),])
+    if attention_data is None:
+      a = torch.zeros((x.shape[0], 1), dtype=torch.float32, device=x.device)
+    else:
+      a = _check_2d('attention_data', _lib.as_device_f32(attention_data))
+    if x.shape[0] != a.shape[0]:
+      raise ValueError('input shape (%s) and attention shape (%s) are not equal.' %
+                       (tuple(x.shape), tuple(a.shape)))
+    self.saved_attention_data = a
+    self.features['attention'] = FixedLenFeature([int(a.shape[1]),])
+    self._x, self._x2, self._y, self._a = x, x2, y, a
+
+
+class TrialBrainData(BrainData):
+  """Several named trials held in GPU memory: the in-memory equivalent of TFExampleData.
+
+  TFExampleData (brain_data.py:645-731) reads one TFRecord file per trial, selects files by
+  regular expression (train / validate / test, `allbut`), adds context per file and interleaves
+  the files.  This class keeps exactly those semantics with `add_trial(name, ...)` in place of
+  files on disk (the TFRecord parser itself is outside the hot path).
+  Like TFExampleData, an input_offset without any context is ignored (brain_data.py:761-763).
+  """
+
+  def __init__(self, *args, **kwargs):
+    self._trials = {}
+    self._dirty = True
+    super(TrialBrainData, self).__init__(*args, **kwargs)
+
+  def _get_data_file_names(self):
+    self._cached_file_names = list(self._trials.keys())
+
+  def add_trial(self, name, input_data, output_data, input2_data=None, attention_data=None):
+    x = _check_2d('input_data', _lib.as_device_f32(input_data))
+    y = _check_2d('output_data', _lib.as_device_f32(output_data))
+    n = int(x.shape[0])
+    if y.shape[0] != n:
+      raise ValueError('input shape (%s) and output shape (%s) are not equal.' %
+                       (tuple(x.shape), tuple(y.shape)))
+    x2 = (torch.zeros((n, 1), dtype=torch.float32, device=x.device) if input2_data is None
+          else _check_2d('input2_data', _lib.as_device_f32(input2_data)))
+    a = (torch.zeros((n, 1), dtype=torch.float32, device=x.device) if attention_data is None
+         else _check_2d('attention_data', _lib.as_device_f32(attention_data)))
+    if x2.shape[0] != n or a.shape[0] != n:
+      raise ValueError('all streams of a trial must have %d frames' % n)
+    self._trials[str(name)] = (x, x2, y, a)
+    self._cached_file_names = []
+    self._dirty = True
+    self.features = {'input_1': FixedLenFeature([int(x.shape[1]),]),
+                     'output': FixedLenFeature([int(y.shape[1]),]),
+                     'input_2': FixedLenFeature([int(x2.shape[1]),]),
+                     'attention': FixedLenFeature([int(a.shape[1]),])}
+
+  def _pack(self):
+    if not self._dirty:
+      return
+    names = sorted(self._trials.keys())
+    self._offsets = {}
+    cur = 0
+    for n in names:
+      self._offsets[n] = (cur, int(self._trials[n][0].shape[0]))
+      cur += self._offsets[n][1]
+    cat = lambda i: torch.cat([self._trials[n][i] for n in names], dim=0)
+    self._x, self._x2, self._y, self._a = cat(0), cat(1), cat(2), cat(3)
+    self._dirty = False
+
+  def create_dataset(self, mode='train', temporal_context=True, mixup_batch=False,
+                     mismatch_batch=False):
+    if mismatch_batch:
+      raise NotImplementedError('mismatch_batch randomisation is outside the decoding hot path.')
+    filename_list = self.filter_file_names(mode)
+    if not filename_list:
+      raise ValueError('No files to process in mode %s from directory %s: %s' %
+                       (mode, self.data_dir, self.all_files()))
+    self._pack()
+    files = [(n,) + self._offsets[n] for n in filename_list]
+    return self._make_dataset(mode, files, temporal_context, mixup_batch, offset_counts=False)
+
+
+def create_brain_dataset(data_type, in_fields, out_field, frame_rate, pre_context=0,
+                         post_context=0, in2_fields=None, in2_pre_context=0, in2_post_context=0,
+                         input_offset=0, attended_field=None, initial_batch_size=1000000,
+                         final_batch_size=1000, repeat_count=1, shuffle_buffer_size=1000,
+                         data_dir=None, data_pattern='', train_file_pattern=None,
+                         validate_file_pattern=None, test_file_pattern=None):
+  """Creates any of the brain datasets that we know about (brain_data.py:959-1049).
+
+  'test' -> TestBrainData, 'trials' -> TrialBrainData (in-memory multi-file).  The 'tfrecord'
+  reader of the reference is outside this package's scope.
+  """
+  if not isinstance(data_type, str):
+    raise TypeError('create_brain_dataset type must be a string.')
+  if frame_rate <= 0:
+    raise ValueError('frame_rate must be greater than 0.')
+  kwargs = dict(pre_context=pre_context, post_context=post_context, in2_fields=in2_fields,
+                in2_pre_context=in2_pre_context, in2_post_context=in2_post_context,
+                input_offset=input_offset, attended_field=attended_field,
+                initial_batch_size=initial_batch_size, final_batch_size=final_batch_size,
+                repeat_count=repeat_count, shuffle_buffer_size=shuffle_buffer_size,
+                data_dir=data_dir, data_pattern=data_pattern,
+                train_file_pattern=train_file_pattern,
+                validate_file_pattern=validate_file_pattern,
+                test_file_pattern=test_file_pattern)
+  if data_type == 'test':
+    return TestBrainData(in_fields, out_field, frame_rate, **kwargs)
+  if data_type in ('trials', 'memory'):
+    return TrialBrainData(in_fields, out_field, frame_rate, **kwargs)
+  if data_type in ('tfrecord', 'tfrecords', 'tfexample'):
+    raise TypeError('create_brain_dataset: the TFRecord reader is not part of the B200 hot path; '
+                    'load trials with TrialBrainData.add_trial.')
+  raise TypeError('create_brain_dataset unknown data type %s' % data_type)

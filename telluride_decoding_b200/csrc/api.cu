@@ -1,0 +1,28 @@
+// Status plumbing of libtdgram.so.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace td {
+namespace {
+thread_local char g_error[1024] = "";
+}
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+}  // namespace td
+
+extern "C" const char* td_last_error(void) { return td::g_error; }
+extern "C" int td_version(void) { return TD_VERSION; }
+extern "C" int td_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  TD_CHECK_CUDA(cudaGetDevice(&dev));
+  if (sm_count) TD_CHECK_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (cc_major) TD_CHECK_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_minor) TD_CHECK_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return TD_OK;
+}

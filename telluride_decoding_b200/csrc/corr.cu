@@ -1,0 +1,319 @@
+// Correlation, windowing and decision kernels (memory-bound; one pass over the signals).
+//
+//   td_column_moments_f64  -- Decoder.add_data_correlator sums      infer_decoder.py:299-303
+//   td_windowed_corr_f32   -- per-frame correlation signal, reduction and sliding-window means
+//                             infer_decoder.py:327-328, :441-450, result_store.py:262-271,
+//                             infer.py:260-266; and per-window Pearson r brain_model.py:62-79
+//   td_wta_decide_u8       -- AttentionDecoder.attention             attention_decoder.py:134
+//
+// Windows [i*S, i*S+W) of every requested shape start and end on multiples of
+// g = gcd(all W, all S), so each segment is reduced ONCE into per-g-frame partial sums
+// (coalesced loads, warp-shuffle reduction, float64) held in shared memory, and every window of
+// every shape is then a short sum of consecutive partials: the data is read exactly once.
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+namespace td {
+namespace {
+
+constexpr int MAX_SIZES = 16;
+constexpr int CORR_THREADS = 256;
+constexpr int MAX_PARTIALS = 24576;      // doubles of shared memory per block (192 KiB)
+
+struct WinSpec {
+  int n_sizes;
+  long long W[MAX_SIZES];
+  long long S[MAX_SIZES];
+  long long g;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Per-frame scalar of mode 0 / mode 1 (float32 arithmetic in the reference's operation order).
+__device__ __forceinline__ float frame_signal(const float* a, const float* b, int dims, int mode,
+                                              int reduction, const float* mu_a, const float* mu_b,
+                                              const float* power) {
+  if (mode == 0) return a[0];
+  if (reduction == 0 || reduction == 1) {
+    const int d = reduction;
+    return ((a[d] - mu_a[d]) * (b[d] - mu_b[d])) / power[d];
+  }
+  // mean (2) and mean-squared (3): numpy float32 mean over the (contiguous) feature axis.
+  // numpy sums < 8 values left to right and 8..128 values with eight interleaved accumulators
+  // combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) plus a sequential remainder; same here.
+  float r[8];
+  float s = 0.0f;
+  const int body = (dims >= 8) ? dims - (dims & 7) : 0;
+  for (int d = 0; d < dims; ++d) {
+    float c = ((a[d] - mu_a[d]) * (b[d] - mu_b[d])) / power[d];
+    if (reduction == 3) {
+      const float sg = (c > 0.0f) ? 1.0f : ((c < 0.0f) ? -1.0f : 0.0f);
+      c = sg * (c * c);
+    }
+    if (d < body) {
+      if (d < 8) r[d] = c; else r[d & 7] += c;
+      if (d == body - 1) s = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    } else {
+      s += c;
+    }
+  }
+  return s / (float)dims;
+}
+
+// One block per segment.  ncol partial columns per g-frame chunk:
+//   mode 0/1: 1 (the reduced signal)     mode 2: 5*dims (a, b, aa, bb, ab per column)
+__global__ void __launch_bounds__(CORR_THREADS)
+windowed_corr_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b,
+                     long long ldb, int dims, const long long* __restrict__ seg_start,
+                     const long long* __restrict__ seg_len, WinSpec ws, int mode, int reduction,
+                     const float* __restrict__ mu_a, const float* __restrict__ mu_b,
+                     const float* __restrict__ power, const long long* __restrict__ win_base,
+                     int n_seg, double* __restrict__ out, int out_cols) {
+  extern __shared__ double part[];
+  const int seg = blockIdx.x;
+  const long long n = seg_len[seg];
+  const long long g = ws.g;
+  const long long nchunk = n / g;
+  const int ncol = (mode == 2) ? 5 * dims : 1;
+  const float* A = a + seg_start[seg] * lda;
+  const float* B = b ? b + seg_start[seg] * ldb : nullptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+
+  // ---- phase 1: partial sums per chunk ------------------------------------------------------
+  if (g >= 32) {
+    for (long long ch = warp; ch < nchunk; ch += nwarp) {
+      if (mode != 2) {
+        double s = 0.0;
+        for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32)
+          s += (double)frame_signal(A + t * lda, B ? B + t * ldb : nullptr, dims, mode, reduction,
+                                    mu_a, mu_b, power);
+        s = warp_sum(s);
+        if (lane == 0) part[ch] = s;
+      } else {
+        for (int d = 0; d < dims; ++d) {
+          double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
+          for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32) {
+            const double x = (double)A[t * lda + d], y = (double)B[t * ldb + d];
+            sa += x; sb += y; saa += x * x; sbb += y * y; sab += x * y;
+          }
+          sa = warp_sum(sa); sb = warp_sum(sb); saa = warp_sum(saa); sbb = warp_sum(sbb);
+          sab = warp_sum(sab);
+          if (lane == 0) {
+            double* p = part + ch * ncol + 5 * d;
+            p[0] = sa; p[1] = sb; p[2] = saa; p[3] = sbb; p[4] = sab;
+          }
+        }
+      }
+    }
+  } else {
+    for (long long ch = threadIdx.x; ch < nchunk; ch += blockDim.x) {
+      if (mode != 2) {
+        double s = 0.0;
+        for (long long t = ch * g; t < (ch + 1) * g; ++t)
+          s += (double)frame_signal(A + t * lda, B ? B + t * ldb : nullptr, dims, mode, reduction,
+                                    mu_a, mu_b, power);
+        part[ch] = s;
+      } else {
+        for (int d = 0; d < dims; ++d) {
+          double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
+          for (long long t = ch * g; t < (ch + 1) * g; ++t) {
+            const double x = (double)A[t * lda + d], y = (double)B[t * ldb + d];
+            sa += x; sb += y; saa += x * x; sbb += y * y; sab += x * y;
+          }
+          double* p = part + ch * ncol + 5 * d;
+          p[0] = sa; p[1] = sb; p[2] = saa; p[3] = sbb; p[4] = sab;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: every window of every shape ---------------------------------------------------
+  for (int j = 0; j < ws.n_sizes; ++j) {
+    const long long W = ws.W[j], S = ws.S[j];
+    if (n < W) continue;
+    const long long nwin = (n - W) / S + 1;
+    const long long cw = W / g, cs = S / g;
+    const long long base = win_base[(long long)j * n_seg + seg];
+    if (mode != 2) {
+      for (long long i = threadIdx.x; i < nwin; i += blockDim.x) {
+        double s = 0.0;
+        for (long long c = i * cs; c < i * cs + cw; ++c) s += part[c];
+        out[(base + i) * out_cols] = s / (double)W;
+      }
+    } else {
+      // one warp per window: lanes over columns, then the all-columns zero rule
+      for (long long i = warp; i < nwin; i += nwarp) {
+        double prod_x = 1.0, prod_y = 1.0;
+        for (int d0 = 0; d0 < dims; d0 += 32) {
+          const int d = d0 + lane;
+          double r = 0.0, xp = 1.0, yp = 1.0;
+          if (d < dims) {
+            double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
+            for (long long c = i * cs; c < i * cs + cw; ++c) {
+              const double* p = part + c * ncol + 5 * d;
+              sa += p[0]; sb += p[1]; saa += p[2]; sbb += p[3]; sab += p[4];
+            }
+            const double inv = 1.0 / (double)W;
+            xp = saa - sa * sa * inv;
+            yp = sbb - sb * sb * inv;
+            // A constant column has zero power in the reference's centred float32 sums; raw
+            // float64 moments leave rounding dust instead.
+            if (xp <= saa * 1e-13) xp = 0.0;
+            if (yp <= sbb * 1e-13) yp = 0.0;
+            r = (sab - sa * sb * inv) / (sqrt(xp) * sqrt(yp));
+            out[(base + i) * out_cols + d] = r;
+          }
+          // product over columns of the powers (brain_model.py:72-73)
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            xp *= __shfl_xor_sync(0xffffffffu, xp, o);
+            yp *= __shfl_xor_sync(0xffffffffu, yp, o);
+          }
+          prod_x *= xp;
+          prod_y *= yp;
+        }
+        if (!(prod_x > 0.0) || !(prod_y > 0.0)) {
+          __syncwarp();
+          for (int d = lane; d < dims; d += 32) out[(base + i) * out_cols + d] = 0.0;
+        }
+      }
+    }
+  }
+}
+
+__global__ void column_moments_kernel(const float* __restrict__ a, long long lda,
+                                      const float* __restrict__ b, long long ldb, long long n,
+                                      int dims, double* sums) {
+  // threadIdx.x -> column (strided), threadIdx.y + blockIdx -> rows
+  __shared__ double red[4][8][33];
+  for (int d0 = 0; d0 < dims; d0 += 32) {
+    const int d = d0 + threadIdx.x;
+    double sa = 0, sb = 0, saa = 0, sbb = 0;
+    if (d < dims) {
+      for (long long t = (long long)blockIdx.x * blockDim.y + threadIdx.y; t < n;
+           t += (long long)gridDim.x * blockDim.y) {
+        const double x = (double)a[t * lda + d], y = (double)b[t * ldb + d];
+        sa += x; sb += y; saa += x * x; sbb += y * y;
+      }
+    }
+    red[0][threadIdx.y][threadIdx.x] = sa;
+    red[1][threadIdx.y][threadIdx.x] = sb;
+    red[2][threadIdx.y][threadIdx.x] = saa;
+    red[3][threadIdx.y][threadIdx.x] = sbb;
+    __syncthreads();
+    if (threadIdx.y < 4 && d < dims) {
+      double s = 0;
+      for (int y = 0; y < 8; ++y) s += red[threadIdx.y][y][threadIdx.x];
+      atomicAdd(sums + (long long)threadIdx.y * dims + d, s);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void wta_kernel(const double* __restrict__ r1, const double* __restrict__ r2, long long n,
+                           uint8_t* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (r1[i] > r2[i]) ? 1 : 0;
+}
+
+}  // namespace
+}  // namespace td
+
+using namespace td;
+
+extern "C" int64_t td_window_count(int64_t n_frames, int64_t W, int64_t S) {
+  if (W <= 0 || S <= 0 || n_frames < W) return 0;
+  return (n_frames - W) / S + 1;
+}
+
+extern "C" int td_column_moments_f64(const float* a, int64_t lda, const float* b, int64_t ldb,
+                                     int64_t n, int dims, double* sums, void* stream) {
+  TD_REQUIRE(a && b && sums && dims > 0 && n >= 0 && lda >= dims && ldb >= dims,
+             "td_column_moments_f64: bad arguments");
+  if (n == 0) return TD_OK;
+  const int blocks = (int)std::min<int64_t>(1184, ceil_div(n, 8));
+  column_moments_kernel<<<blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>(a, lda, b, ldb, n, dims, sums);
+  TD_CHECK_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+extern "C" int td_windowed_corr_f32(const float* a, int64_t lda, const float* b, int64_t ldb, int dims,
+                                    const int64_t* seg_start, const int64_t* seg_len, int n_seg,
+                                    const int64_t* W, const int64_t* S, int n_sizes, int mode,
+                                    int reduction, const float* mu_a, const float* mu_b,
+                                    const float* power, double* out, int64_t* out_offset, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_REQUIRE(a && seg_start && seg_len && W && S && n_seg > 0, "td_windowed_corr_f32: null argument");
+  TD_REQUIRE(n_sizes >= 1 && n_sizes <= MAX_SIZES, "td_windowed_corr_f32: n_sizes must be in [1, %d]", MAX_SIZES);
+  TD_REQUIRE(mode >= 0 && mode <= 2, "td_windowed_corr_f32: unknown mode %d", mode);
+  TD_REQUIRE(dims >= 1 && lda >= (mode == 0 ? 1 : dims), "td_windowed_corr_f32: bad dims/lda");
+  if (mode != 0) TD_REQUIRE(b && ldb >= dims, "td_windowed_corr_f32: second signal missing");
+  if (mode == 1) {
+    TD_REQUIRE(mu_a && mu_b && power, "td_windowed_corr_f32: global statistics missing");
+    TD_REQUIRE(reduction >= 0 && reduction <= 3, "td_windowed_corr_f32: unknown reduction %d", reduction);
+    TD_REQUIRE(reduction != 1 || dims >= 2, "td_windowed_corr_f32: 'second' needs >= 2 columns");
+    TD_REQUIRE(dims <= 128, "td_windowed_corr_f32: at most 128 correlation columns");
+  }
+  WinSpec ws;
+  ws.n_sizes = n_sizes;
+  long long g = 0;
+  for (int j = 0; j < n_sizes; ++j) {
+    TD_REQUIRE(W[j] >= 1 && S[j] >= 1, "td_windowed_corr_f32: window %d has width %lld step %lld (step 0 never terminates in the reference either)",
+               j, (long long)W[j], (long long)S[j]);
+    ws.W[j] = W[j];
+    ws.S[j] = S[j];
+    g = std::gcd(g, (long long)W[j]);
+    g = std::gcd(g, (long long)S[j]);
+  }
+  ws.g = g;
+  const int ncol = (mode == 2) ? 5 * dims : 1;
+  const int out_cols = (mode == 2) ? dims : 1;
+  int64_t max_chunks = 0;
+  std::vector<long long> win_base((size_t)n_sizes * n_seg);
+  int64_t total = 0;
+  for (int j = 0; j < n_sizes; ++j) {
+    if (out_offset) out_offset[j] = total;
+    for (int s = 0; s < n_seg; ++s) {
+      win_base[(size_t)j * n_seg + s] = total;
+      total += td_window_count(seg_len[s], W[j], S[j]);
+    }
+  }
+  if (out_offset) out_offset[n_sizes] = total;
+  for (int s = 0; s < n_seg; ++s) max_chunks = std::max<int64_t>(max_chunks, seg_len[s] / g);
+  if (total == 0) return TD_OK;
+  TD_REQUIRE(out != nullptr, "td_windowed_corr_f32: null output");
+  if (max_chunks * ncol > MAX_PARTIALS) {
+    set_error("td_windowed_corr_f32: %lld partial sums per segment exceed %d (segment too long for gcd(W,S)=%lld); split the segment",
+              (long long)(max_chunks * ncol), MAX_PARTIALS, (long long)g);
+    return TD_ERR_UNSUPPORTED;
+  }
+  std::vector<long long> ss(seg_start, seg_start + n_seg), sl(seg_len, seg_len + n_seg);
+  long long *ss_d, *sl_d, *wb_d;
+  int rc = upload(ss, &ss_d, st); if (rc) return rc;
+  rc = upload(sl, &sl_d, st); if (rc) return rc;
+  rc = upload(win_base, &wb_d, st); if (rc) return rc;
+  const size_t smem = (size_t)std::max<int64_t>(1, max_chunks * ncol) * sizeof(double);
+  TD_CHECK_CUDA(cudaFuncSetAttribute(windowed_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_PARTIALS * sizeof(double))));
+  windowed_corr_kernel<<<n_seg, CORR_THREADS, smem, st>>>(a, lda, b, ldb, dims, ss_d, sl_d, ws, mode, reduction, mu_a, mu_b, power, wb_d, n_seg, out, out_cols);
+  TD_CHECK_CUDA(cudaGetLastError());
+  cudaFreeAsync(ss_d, st);
+  cudaFreeAsync(sl_d, st);
+  cudaFreeAsync(wb_d, st);
+  return TD_OK;
+}
+
+extern "C" int td_wta_decide_u8(const double* r1, const double* r2, int64_t n, uint8_t* out, void* stream) {
+  TD_REQUIRE(r1 && r2 && out && n >= 0, "td_wta_decide_u8: bad arguments");
+  if (n == 0) return TD_OK;
+  wta_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(r1, r2, n, out);
+  TD_CHECK_CUDA(cudaGetLastError());
+  return TD_OK;
+}

@@ -1,0 +1,720 @@
+// Lagged (implicit-Hankel) Gram on tcgen05 tensor cores, 3xTF32, for sm_100a.
+//
+// Replaces the reference's minibatch loop `sum_xtx += np.matmul(x.T, x)` over the materialised
+// lagged design (telluride_decoding/brain_model.py:429-444, cca.py:311-332; the design itself is
+// built by brain_data.py:446-455).  Here the design Z = [X_0 | X_1] never exists:
+//
+//   1. stage:  every raw stream [T, C] (time-major) is rewritten once as two channel-major
+//      planes hi = tf32(x), lo = tf32(x - hi), segments separated by >= (pre+post) zero frames.
+//      Row (stream q, lag k, channel c) of Z' is then the staged row c read at a time shift of
+//      (k - pre): a plain TMA box at a shifted coordinate.  Zero padding at segment edges comes
+//      from the zero gaps / TMA out-of-bounds fill.
+//   2. gram:   persistent warp-specialised kernel.  K dimension = time, cut into 32-frame
+//      k-tiles; M/N = rows of Z' in 128-row operand tiles made of CB-channel TMA boxes.
+//      Per k-tile and operand the producer lands hi and lo tiles (K-major, 128B swizzle) and one
+//      thread issues hi*hi + hi*lo + lo*hi tcgen05.mma (kind::tf32) into a TMEM accumulator.
+//      Every `chunk` k-tiles the accumulator is drained by the epilogue warps into fp32
+//      registers (round-to-nearest adds; bounds the tensor-core accumulation length), while the
+//      MMA warp continues in the second TMEM buffer.  Work = (superchunk, lower-triangle tile,
+//      k-range) linearised and split evenly over CTAs (stream-K); partial tiles are combined with
+//      fp32 red.add into G.  Rows >= keep of a segment tail k-tile are zeroed in shared memory.
+//   3. the computed triangle is mirrored by td_symmetrize_f32.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace td {
+
+int launch_gram_simt(const td_stream* streams, int n_streams, const int64_t* seg_keep, int n_seg,
+                     float* G, int64_t ldg, cudaStream_t st);
+
+namespace {
+
+constexpr int BK = 32;                       // frames per k-tile (one 128-byte swizzle row)
+constexpr int TILE_ROWS = 128;               // operand rows per CTA
+constexpr int STAGES = 3;
+constexpr int OPERAND_BYTES = TILE_ROWS * BK * 4;       // 16 KiB
+constexpr int STAGE_BYTES = 4 * OPERAND_BYTES;          // A_hi, A_lo, B_hi, B_lo
+constexpr int NUM_THREADS = 320;             // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
+constexpr int NUM_EPI_WARPS = 8;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(8 * (3 * STAGES + 4) + 8 <= 256, "barrier block too small");
+
+struct GramParams {
+  const int4* groups;     // [n_groups_pad] {stream, aligned time shift, first channel, shift plane}
+  const int2* ktiles;     // [NK] {staged time of design row 0 of the tile, valid rows}
+  const int* out_idx;     // [Dpad] tile-space row -> row/col of G, -1 for padding
+  float* G;
+  long long ldg;
+  int CB;                 // channels per TMA box
+  int groups_per_tile;    // TILE_ROWS / CB
+  int ntri;               // lower-triangle tile count
+  long long NK;           // k-tiles in total
+  int KS;                 // k-tiles per superchunk
+  int chunk_kt;           // k-tiles per TMEM flush
+  long long total_steps;  // NSC * ntri * KS
+};
+
+struct WorkItem {
+  int tm, tn;
+  long long kt_begin, kt_end;
+};
+
+// Linearised (superchunk, tile, k-tile) space; identical decode in every warp role.
+struct WorkIter {
+  long long p, hi;
+  __device__ WorkIter(const GramParams& P, int worker, int n_workers) {
+    p = P.total_steps * worker / n_workers;
+    hi = P.total_steps * (worker + 1) / n_workers;
+  }
+  __device__ bool next(const GramParams& P, WorkItem& it) {
+    while (p < hi) {
+      long long item = p / P.KS;
+      int kt0 = (int)(p - item * P.KS);
+      long long sc = item / P.ntri;
+      int tile = (int)(item - sc * P.ntri);
+      long long len = min((long long)(P.KS - kt0), hi - p);
+      long long b = sc * P.KS + kt0;
+      long long e = min(b + len, P.NK);
+      p += len;
+      if (b < e) {
+        int tm = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+        while ((long long)(tm + 1) * (tm + 2) / 2 <= tile) ++tm;
+        while ((long long)tm * (tm + 1) / 2 > tile) --tm;
+        it.tm = tm;
+        it.tn = tile - tm * (tm + 1) / 2;
+        it.kt_begin = b;
+        it.kt_end = e;
+        return true;
+      }
+    }
+    return false;
+  }
+};
+
+// Zero frames [valid, BK) of every row of the four operand tiles of one stage (K-major, 128-byte
+// swizzle: element t of row r sits in 16-byte chunk (t/4) ^ (r%8)).  Executed by one warp.
+__device__ __forceinline__ void zero_tail_frames(uint32_t sbase, int valid, int lane) {
+  for (int r = lane; r < 4 * TILE_ROWS; r += 32) {
+    const uint32_t rowaddr = sbase + r * (BK * 4);
+    for (int t = valid; t < BK; ++t) {
+      const uint32_t a = rowaddr + ((((uint32_t)t >> 2) ^ ((uint32_t)r & 7u)) << 4) +
+                         (((uint32_t)t & 3u) << 2);
+      asm volatile("st.shared::cta.b32 [%0], %1;" ::"r"(a), "r"(0u) : "memory");
+    }
+  }
+  ptx::fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor-core proxy
+  __syncwarp();
+}
+
+// CG = 1: one CTA per 128x128 tile.  CG = 2: a CTA pair (cluster of 2) per 256x256 tile, each CTA
+// staging 128 rows of A and 128 rows of B; the pair leader issues tcgen05.mma.cta_group::2.
+template <int CG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
+                        const __grid_constant__ CUtensorMap tmap1, const GramParams P) {
+  constexpr int BN = TILE_ROWS * CG;          // accumulator columns (N of the MMA)
+  constexpr int NACC = BN / 2;                // accumulator values per epilogue thread
+  constexpr uint32_t TMEM_COLS = 2 * BN;      // double-buffered accumulator
+  constexpr uint32_t IDESC = ptx::umma_idesc_tf32(128 * CG, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // TMA bytes of this CTA
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };     // MMAs of the stage retired
+  auto pready_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };  // leader: peer stage ready
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const int worker = blockIdx.x / CG;
+  const int n_workers = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap0);
+    ptx::prefetch_tmap(&tmap1);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(pready_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(tfull_bar(b), 1);
+      ptx::mbar_init(tempty_bar(b), NUM_EPI_WARPS * CG);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<CG>(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one lane) =====================
+    if (lane == 0) {
+      WorkIter wi(P, worker, n_workers);
+      WorkItem it;
+      int stage = 0;
+      uint32_t phase = 0;
+      while (wi.next(P, it)) {
+        const int ga = (it.tm * CG + (int)rank) * P.groups_per_tile;
+        const int gb = (it.tn * CG + (int)rank) * P.groups_per_tile;
+        for (long long kt = it.kt_begin; kt < it.kt_end; ++kt) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          const int2 kti = __ldg(&P.ktiles[kt]);
+          const uint32_t fb = full_bar(stage);
+          ptx::mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+#pragma unroll 1
+          for (int op = 0; op < 2; ++op) {
+            const int g0 = op ? gb : ga;
+            const uint32_t obase = sbase + op * 2 * OPERAND_BYTES;
+#pragma unroll 1
+            for (int g = 0; g < P.groups_per_tile; ++g) {
+              const int4 gd = __ldg(&P.groups[g0 + g]);
+              const CUtensorMap* tm = gd.x ? &tmap1 : &tmap0;
+              const uint32_t dst = obase + g * P.CB * (BK * 4);
+              ptx::tma_load_3d(dst, tm, fb, kti.x + gd.y, gd.z, 2 * gd.w);                      // hi plane
+              ptx::tma_load_3d(dst + OPERAND_BYTES, tm, fb, kti.x + gd.y, gd.z, 2 * gd.w + 1);  // lo plane
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA warp =====================
+    // Every CTA waits for its own stage and zeroes segment-tail frames; with CG == 2 the peer then
+    // reports the stage to the leader (remote mbarrier arrive) and only the leader issues MMAs.
+    WorkIter wi(P, worker, n_workers);
+    WorkItem it;
+    int stage = 0;
+    uint32_t phase = 0;
+    int buf = 0;
+    uint32_t tphase[2] = {0u, 0u};
+    const bool issuer = (CG == 1 || rank == 0);
+    const uint32_t pready_leader0 = (CG == 2) ? ptx::mapa(pready_bar(0), 0) : 0u;
+    while (wi.next(P, it)) {
+      for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
+        const long long c1 = min(it.kt_end, c0 + (long long)P.chunk_kt);
+        if (issuer) {
+          ptx::mbar_wait(tempty_bar(buf), tphase[buf] ^ 1u);
+          ptx::tc_fence_after();
+        }
+        for (long long kt = c0; kt < c1; ++kt) {
+          const int valid = __ldg(&P.ktiles[kt]).y;
+          const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+          ptx::mbar_wait(full_bar(stage), phase);
+          // Rows >= valid of a segment's last k-tile are not design rows (end of trial, or rows
+          // lost to drop_remainder, brain_data.py:369-370): zero them in both operands.
+          if (valid < BK) zero_tail_frames(sbase, valid, lane);
+          if constexpr (CG == 2) {
+            if (!issuer) {
+              if (lane == 0) ptx::mbar_arrive_cluster(pready_leader0 + 8u * stage);
+            } else {
+              ptx::mbar_wait(pready_bar(stage), phase);
+            }
+          }
+          if (issuer) {
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const int ksteps = (valid + 7) >> 3;
+              const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+              const uint64_t a_hi = ptx::umma_desc_k_sw128(sbase);
+              const uint64_t a_lo = ptx::umma_desc_k_sw128(sbase + OPERAND_BYTES);
+              const uint64_t b_hi = ptx::umma_desc_k_sw128(sbase + 2 * OPERAND_BYTES);
+              const uint64_t b_lo = ptx::umma_desc_k_sw128(sbase + 3 * OPERAND_BYTES);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);   // 8 frames = 32 B = 2 x 16 B
+                const uint32_t acc = (kt > c0 || ks > 0) ? 1u : 0u;
+                ptx::mma_tf32<CG>(d, a_hi + adv, b_hi + adv, IDESC, acc);
+                ptx::mma_tf32<CG>(d, a_hi + adv, b_lo + adv, IDESC, 1u);
+                ptx::mma_tf32<CG>(d, a_lo + adv, b_hi + adv, IDESC, 1u);
+              }
+              ptx::mma_commit<CG>(empty_bar(stage));          // stage reusable once these retire
+              if (kt == c1 - 1) ptx::mma_commit<CG>(tfull_bar(buf));
+            }
+            __syncwarp();
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tphase[buf] ^= 1u;
+        buf ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps: TMEM -> fp32 registers -> red.add =====================
+    const int ew = warp - 2;
+    const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32)
+    const int half = ew >> 2;                  // column half of the accumulator
+    WorkIter wi(P, worker, n_workers);
+    WorkItem it;
+    int buf = 0;
+    uint32_t fphase[2] = {0u, 0u};
+    const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+    float acc[NACC];
+    while (wi.next(P, it)) {
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
+      for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
+        ptx::mbar_wait(tfull_bar(buf), fphase[buf]);
+        fphase[buf] ^= 1u;
+        ptx::tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + half * NACC);
+#pragma unroll
+        for (int j = 0; j < NACC / 32; ++j) {
+          float v[32];
+          ptx::tmem_ld32(taddr + j * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) ptx::mbar_arrive_cluster(tempty_leader0 + 8u * buf);
+          else ptx::mbar_arrive(tempty_bar(buf));
+        }
+        buf ^= 1;
+      }
+      // Tile (tm, tn), tm >= tn: element (m, n) is stored at G[n][m] (upper triangle) so that the
+      // 32 lanes of a warp (consecutive m) write consecutive addresses.
+      const int m_row = (it.tm * CG + (int)rank) * TILE_ROWS + quad * 32 + lane;
+      const int m_out = __ldg(&P.out_idx[m_row]);
+      const int n_row0 = it.tn * BN + half * NACC;
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) {
+        const int n_row = n_row0 + i;
+        const int n_out = __ldg(&P.out_idx[n_row]);
+        if (m_out >= 0 && n_out >= 0 && n_row <= m_row)
+          atomicAdd(P.G + (long long)n_out * P.ldg + m_out, acc[i]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage: raw [T, C] time-major  ->  planes[2][Cpad][Tp] channel-major, hi / lo tf32 split.
+// ---------------------------------------------------------------------------------------------
+// With n_shift = 4 every plane pair s holds the stream advanced by s frames, so that a lag shift
+// d is read from pair (d mod 4) at the 16-byte aligned coordinate d - (d mod 4): TMA box origins
+// must be 16-byte aligned along the contiguous dimension.
+__global__ void stage_split_kernel(StreamView s, const int64_t* __restrict__ seg_off, int seg0,
+                                   float* __restrict__ planes, int64_t Tp, int Cpad, int n_shift) {
+  __shared__ float tile[32][33];
+  const int seg = seg0 + blockIdx.y;
+  const int64_t len = s.seg_len[seg];
+  const int64_t t0 = (int64_t)blockIdx.x * 32;
+  if (t0 >= len) return;
+  const int c0 = blockIdx.z * 32;
+  const float* src = s.data + (s.seg_start[seg] + t0) * s.ld;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + threadIdx.x;
+    float v = 0.0f;
+    if (t0 + r < len && c < s.channels) v = src[(int64_t)r * s.ld + c];
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  const int64_t plane = (int64_t)Cpad * Tp;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const int64_t t = t0 + threadIdx.x;
+    if (c < s.channels && t < len) {
+      const float v = tile[threadIdx.x][r];
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      const float hi = __uint_as_float(hb);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+      const int64_t o = (int64_t)c * Tp + seg_off[seg] + t;
+      for (int sh = 0; sh < n_shift; ++sh) {
+        planes[(2 * sh) * plane + o - sh] = hi;
+        planes[(2 * sh + 1) * plane + o - sh] = __uint_as_float(lb);
+      }
+    }
+  }
+}
+
+__global__ void symmetrize_kernel(float* __restrict__ G, int64_t n, int64_t ldg, int from_upper) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;                        // handle block pairs (bi <= bj) once
+  // Source block: the computed triangle's (bi, bj) if from_upper, else (bj, bi).
+  const int sr = from_upper ? bi : bj, sc = from_upper ? bj : bi;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = (int64_t)sr * 32 + r, j = (int64_t)sc * 32 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < n && j < n) ? G[i * ldg + j] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = (int64_t)sc * 32 + r, j = (int64_t)sr * 32 + threadIdx.x;   // mirrored block
+    if (i < n && j < n) {
+      const bool dst_is_uncomputed = from_upper ? (i > j) : (i < j);
+      if (dst_is_uncomputed) G[i * ldg + j] = tile[threadIdx.x][r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side plan.
+// ---------------------------------------------------------------------------------------------
+struct GramPlan {
+  int n_streams = 0, CB = 0, cg = 1, n_seg = 0, n_shift = 4;
+  int L[2] = {0, 0}, C[2] = {0, 0}, Cpad[2] = {0, 0}, pre[2] = {0, 0};
+  int64_t Tp = 0, Dz = 0, Dpad = 0, NK = 0;
+  int nt = 0, ntri = 0, n_groups = 0, tile = 0;
+  std::vector<int64_t> seg_off;
+  size_t off_stage[2] = {0, 0}, off_groups = 0, off_ktiles = 0, off_outidx = 0, off_segoff = 0,
+         off_segtab = 0, total = 0;
+};
+
+int pick_cb(int channels_min_max) {
+  // Largest TMA box height whose channel padding wastes <= 10 %.
+  const int cands[4] = {64, 32, 16, 8};
+  for (int cb : cands) {
+    const int64_t padded = round_up(channels_min_max, cb);
+    if ((double)padded <= 1.10 * channels_min_max) return cb;
+  }
+  return 8;
+}
+
+int make_plan(const td_stream* streams, int n_streams, const int64_t* seg_keep, int n_seg,
+              const td_gram_options* opt, GramPlan* pl) {
+  TD_REQUIRE(n_streams == 1 || n_streams == 2, "td_lagged_gram: n_streams must be 1 or 2, not %d",
+             n_streams);
+  TD_REQUIRE(n_seg > 0, "td_lagged_gram: no segments");
+  for (int q = 0; q < n_streams; ++q) {
+    int rc = check_stream(&streams[q], seg_keep, n_seg, "td_lagged_gram");
+    if (rc) return rc;
+  }
+  pl->n_streams = n_streams;
+  pl->n_seg = n_seg;
+  {
+    const char* e = getenv("TD_STAGE_SHIFTS");     // development switch: 1 = unaligned TMA origins
+    pl->n_shift = (e && e[0] == '1') ? 1 : 4;
+  }
+  int cg = opt ? opt->cta_group : 0;
+  int cb = 64;
+  int halo = 0;
+  pl->Dz = 0;
+  for (int q = 0; q < n_streams; ++q) {
+    pl->L[q] = lags_of(streams[q]);
+    pl->C[q] = streams[q].channels;
+    pl->pre[q] = streams[q].pre;
+    cb = std::min(cb, pick_cb(streams[q].channels));
+    halo = std::max(halo, streams[q].pre + streams[q].post);
+    pl->Dz += width_of(streams[q]);
+  }
+  pl->CB = cb;
+  int64_t n_groups = 0;
+  for (int q = 0; q < n_streams; ++q) {
+    pl->Cpad[q] = (int)round_up(pl->C[q], cb);
+    n_groups += (int64_t)pl->L[q] * (pl->Cpad[q] / cb);
+  }
+  if (cg == 0) cg = (n_groups * cb >= 1024) ? 2 : 1;
+  TD_REQUIRE(cg == 1 || cg == 2, "td_lagged_gram: cta_group must be 0, 1 or 2");
+  pl->cg = cg;
+  pl->tile = TILE_ROWS * cg;
+  pl->Dpad = round_up(n_groups * cb, pl->tile);
+  pl->n_groups = (int)(pl->Dpad / cb);
+  pl->nt = (int)(pl->Dpad / pl->tile);
+  pl->ntri = pl->nt * (pl->nt + 1) / 2;
+  TD_REQUIRE(pl->Dpad < (1LL << 30), "td_lagged_gram: design too wide");
+
+  // Segment placement in staged time: zero gap >= halo between segments, 32-frame aligned starts.
+  pl->seg_off.resize(n_seg);
+  int64_t cur = round_up(halo, 32);
+  int64_t nk = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    pl->seg_off[s] = cur;
+    int64_t len = 0;
+    for (int q = 0; q < n_streams; ++q) len = std::max(len, streams[q].seg_len[s]);
+    cur = round_up(cur + len + halo, 32);
+    nk += ceil_div(seg_keep[s], BK);
+  }
+  pl->Tp = round_up(cur + BK + halo, 32);
+  pl->NK = nk;
+  TD_REQUIRE(pl->Tp < (1LL << 31) - 4096, "td_lagged_gram: more than 2^31 staged frames");
+
+  size_t off = 0;
+  for (int q = 0; q < n_streams; ++q) {
+    pl->off_stage[q] = off;
+    off += (size_t)2 * pl->n_shift * pl->Cpad[q] * pl->Tp * sizeof(float);
+    off = (size_t)round_up((int64_t)off, 1024);
+  }
+  pl->off_groups = off;  off += (size_t)round_up((int64_t)pl->n_groups * sizeof(int4), 1024);
+  pl->off_ktiles = off;  off += (size_t)round_up(std::max<int64_t>(nk, 1) * sizeof(int2), 1024);
+  pl->off_outidx = off;  off += (size_t)round_up(pl->Dpad * sizeof(int), 1024);
+  pl->off_segoff = off;  off += (size_t)round_up((int64_t)n_seg * sizeof(int64_t), 1024);
+  pl->off_segtab = off;  off += (size_t)round_up((int64_t)n_seg * 2 * n_streams * sizeof(int64_t), 1024);
+  pl->total = off;
+  return TD_OK;
+}
+
+// TD_DEBUG=1: synchronise after every phase and report on stderr (development aid).
+bool debug_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TD_DEBUG"); v = (e && e[0] && e[0] != '0') ? 1 : 0; }
+  return v == 1;
+}
+int debug_sync(cudaStream_t st, const char* what) {
+  if (!debug_enabled()) return TD_OK;
+  cudaError_t e = cudaStreamSynchronize(st);
+  fprintf(stderr, "[tdgram] %s: %s\n", what, cudaGetErrorString(e));
+  fflush(stderr);
+  if (e != cudaSuccess) { set_error("%s failed: %s", what, cudaGetErrorString(e)); return TD_ERR_CUDA; }
+  return TD_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* fn) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    TD_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return TD_ERR_CUDA;
+    }
+    cached = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *fn = cached;
+  return TD_OK;
+}
+
+int make_tmap(CUtensorMap* m, float* planes, int64_t Tp, int Cpad, int CB, int n_shift) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[3] = {(cuuint64_t)Tp, (cuuint64_t)Cpad, (cuuint64_t)(2 * n_shift)};
+  cuuint64_t strides[2] = {(cuuint64_t)Tp * 4, (cuuint64_t)Tp * 4 * (cuuint64_t)Cpad};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)CB, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, planes, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (Tp=%lld Cpad=%d CB=%d)", (int)r,
+              (long long)Tp, Cpad, CB);
+    return TD_ERR_CUDA;
+  }
+  return TD_OK;
+}
+
+}  // namespace
+}  // namespace td
+
+using namespace td;
+
+extern "C" int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_streams,
+                                              const int64_t* seg_keep, int n_seg,
+                                              const td_gram_options* opt, size_t* bytes) {
+  TD_REQUIRE(streams && seg_keep && bytes, "td_lagged_gram_workspace_bytes: null argument");
+  if (opt && opt->method == 1) { *bytes = 0; return TD_OK; }
+  GramPlan pl;
+  int rc = make_plan(streams, n_streams, seg_keep, n_seg, opt, &pl);
+  if (rc) return rc;
+  *bytes = pl.total;
+  return TD_OK;
+}
+
+extern "C" int td_symmetrize_f32(float* G, int64_t n, int64_t ldg, int from_upper, void* stream) {
+  TD_REQUIRE(G && n >= 0 && ldg >= n, "td_symmetrize_f32: bad arguments");
+  if (n == 0) return TD_OK;
+  const int nb = (int)ceil_div(n, 32);
+  symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, (cudaStream_t)stream>>>(G, n, ldg, from_upper);
+  TD_CHECK_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const int64_t* seg_keep,
+                                  int n_seg, float* G, int64_t ldg, const td_gram_options* opt,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_REQUIRE(streams && seg_keep && G, "td_lagged_gram_f32: null argument");
+  if (opt && opt->method == 1) {
+    int64_t Dz = 0;
+    for (int q = 0; q < n_streams; ++q) {
+      int rc = check_stream(&streams[q], seg_keep, n_seg, "td_lagged_gram");
+      if (rc) return rc;
+      Dz += width_of(streams[q]);
+    }
+    TD_REQUIRE(ldg >= Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)Dz);
+    return launch_gram_simt(streams, n_streams, seg_keep, n_seg, G, ldg, st);
+  }
+  TD_REQUIRE(opt == nullptr || opt->method == 0, "td_lagged_gram_f32: unknown method %d", opt->method);
+  GramPlan pl;
+  int rc = make_plan(streams, n_streams, seg_keep, n_seg, opt, &pl);
+  if (rc) return rc;
+  TD_REQUIRE(ldg >= pl.Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)pl.Dz);
+  if (workspace_bytes < pl.total || !workspace) {
+    set_error("td_lagged_gram_f32: workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
+    return TD_ERR_WORKSPACE;
+  }
+  int dev = 0, sms = 0, cc_major = 0;
+  TD_CHECK_CUDA(cudaGetDevice(&dev));
+  TD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  TD_CHECK_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_major != 10) {
+    set_error("td_lagged_gram_f32: the tcgen05 kernel needs an sm_100 device (found sm_%d)", cc_major * 10);
+    return TD_ERR_UNSUPPORTED;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+
+  // ---- tables -------------------------------------------------------------------------------
+  std::vector<int4> groups(pl.n_groups);
+  std::vector<int> out_idx(pl.Dpad, -1);
+  {
+    int g = 0;
+    int64_t col0 = 0;
+    for (int q = 0; q < n_streams; ++q) {
+      const int per_lag = pl.Cpad[q] / pl.CB;
+      for (int k = 0; k < pl.L[q]; ++k)
+        for (int b = 0; b < per_lag; ++b, ++g) {
+          const int d = k - pl.pre[q];
+          const int sh = (pl.n_shift == 4) ? ((d % 4) + 4) % 4 : 0;
+          groups[g] = make_int4(q, d - sh, b * pl.CB, sh);
+          for (int i = 0; i < pl.CB; ++i) {
+            const int c = b * pl.CB + i;
+            if (c < pl.C[q]) out_idx[(int64_t)g * pl.CB + i] = (int)(col0 + (int64_t)k * pl.C[q] + c);
+          }
+        }
+      col0 += width_of(streams[q]);
+    }
+    for (; g < pl.n_groups; ++g) groups[g] = make_int4(0, 0, pl.Cpad[0], 0);   // fully out of bounds -> zeros
+  }
+  std::vector<int2> ktiles;
+  ktiles.reserve(pl.NK);
+  for (int s = 0; s < n_seg; ++s)
+    for (int64_t j = 0; j * BK < seg_keep[s]; ++j)
+      ktiles.push_back(make_int2((int)(pl.seg_off[s] + j * BK),
+                                 (int)std::min<int64_t>(BK, seg_keep[s] - j * BK)));
+  std::vector<int64_t> segtab((size_t)n_seg * 2 * n_streams);
+  for (int q = 0; q < n_streams; ++q)
+    for (int s = 0; s < n_seg; ++s) {
+      segtab[((size_t)q * 2 + 0) * n_seg + s] = streams[q].seg_start[s];
+      segtab[((size_t)q * 2 + 1) * n_seg + s] = streams[q].seg_len[s];
+    }
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_groups, groups.data(), groups.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  if (!ktiles.empty())
+    TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_ktiles, ktiles.data(), ktiles.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_outidx, out_idx.data(), out_idx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_segoff, pl.seg_off.data(), (size_t)n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_segtab, segtab.data(), segtab.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+
+  // ---- stage ----------------------------------------------------------------------------------
+  CUtensorMap tmaps[2];
+  for (int q = 0; q < n_streams; ++q) {
+    float* planes = reinterpret_cast<float*>(ws + pl.off_stage[q]);
+    TD_CHECK_CUDA(cudaMemsetAsync(planes, 0, (size_t)2 * pl.n_shift * pl.Cpad[q] * pl.Tp * sizeof(float), st));
+    StreamView sv;
+    sv.data = streams[q].data_dev;
+    sv.ld = streams[q].ld;
+    sv.channels = streams[q].channels;
+    sv.pre = streams[q].pre;
+    sv.lags = pl.L[q];
+    const int64_t* tab = reinterpret_cast<const int64_t*>(ws + pl.off_segtab);
+    sv.seg_start = tab + ((size_t)q * 2 + 0) * n_seg;
+    sv.seg_len = tab + ((size_t)q * 2 + 1) * n_seg;
+    int64_t maxlen = 0;
+    for (int s = 0; s < n_seg; ++s) maxlen = std::max(maxlen, streams[q].seg_len[s]);
+    if (maxlen > 0) {
+      for (int s0 = 0; s0 < n_seg; s0 += 32768) {
+        dim3 grid((unsigned)ceil_div(maxlen, 32), (unsigned)std::min(32768, n_seg - s0),
+                  (unsigned)ceil_div(pl.C[q], 32));
+        stage_split_kernel<<<grid, dim3(32, 8), 0, st>>>(
+            sv, reinterpret_cast<const int64_t*>(ws + pl.off_segoff), s0, planes, pl.Tp, pl.Cpad[q], pl.n_shift);
+        TD_CHECK_CUDA(cudaGetLastError());
+      }
+    }
+    rc = make_tmap(&tmaps[q], planes, pl.Tp, pl.Cpad[q], pl.CB, pl.n_shift);
+    if (rc) return rc;
+  }
+  if ((rc = debug_sync(st, "stage"))) return rc;
+  if (n_streams == 1) tmaps[1] = tmaps[0];
+
+  // ---- gram -----------------------------------------------------------------------------------
+  TD_CHECK_CUDA(cudaMemset2DAsync(G, (size_t)ldg * sizeof(float), 0, (size_t)pl.Dz * sizeof(float), (size_t)pl.Dz, st));
+  if (pl.NK > 0) {
+    GramParams P;
+    P.groups = reinterpret_cast<const int4*>(ws + pl.off_groups);
+    P.ktiles = reinterpret_cast<const int2*>(ws + pl.off_ktiles);
+    P.out_idx = reinterpret_cast<const int*>(ws + pl.off_outidx);
+    P.G = G;
+    P.ldg = ldg;
+    P.CB = pl.CB;
+    P.groups_per_tile = TILE_ROWS / pl.CB;
+    P.ntri = pl.ntri;
+    P.NK = pl.NK;
+    int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 512;
+    P.chunk_kt = std::max(1, chunk_rows / BK);
+    // Superchunk: the staged frames all tiles sweep together; sized to stay L2 resident (~24 MB).
+    int64_t sc_rows = (opt && opt->superchunk_rows > 0) ? opt->superchunk_rows : 0;
+    if (sc_rows == 0) {
+      int64_t cpad_sum = 0;
+      for (int q = 0; q < n_streams; ++q) cpad_sum += pl.Cpad[q];
+      sc_rows = (24LL << 20) / (cpad_sum * 8 * pl.n_shift);
+      sc_rows = std::max<int64_t>(sc_rows, 4096);
+    }
+    int64_t ks = std::max<int64_t>(P.chunk_kt, round_up(ceil_div(sc_rows, BK), P.chunk_kt));
+    ks = std::min<int64_t>(ks, round_up(pl.NK, P.chunk_kt));
+    P.KS = (int)ks;
+    const int64_t nsc = ceil_div(pl.NK, ks);
+    P.total_steps = nsc * pl.ntri * ks;
+    int workers = sms / pl.cg;
+    if (opt && opt->max_ctas > 0) workers = std::max(1, std::min(workers, opt->max_ctas / pl.cg));
+    // No more workers than there are chunk-sized pieces of work.
+    workers = (int)std::max<int64_t>(1, std::min<int64_t>(workers, ceil_div(P.total_steps, P.chunk_kt)));
+    if (pl.cg == 1) {
+      TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      lagged_gram_umma_kernel<1><<<workers, NUM_THREADS, SMEM_BYTES, st>>>(tmaps[0], tmaps[1], P);
+    } else {
+      TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(workers * 2);
+      cfg.blockDim = dim3(NUM_THREADS);
+      cfg.dynamicSmemBytes = SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lagged_gram_umma_kernel<2>, tmaps[0], tmaps[1], P));
+    }
+    TD_CHECK_CUDA(cudaGetLastError());
+    if (debug_enabled())
+      fprintf(stderr, "[tdgram] gram launch: cg=%d workers=%d CB=%d Dz=%lld Dpad=%lld ntri=%d NK=%lld KS=%d chunk_kt=%d total=%lld Tp=%lld\n",
+              pl.cg, workers, pl.CB, (long long)pl.Dz, (long long)pl.Dpad, pl.ntri, (long long)pl.NK, P.KS, P.chunk_kt,
+              (long long)P.total_steps, (long long)pl.Tp);
+    if ((rc = debug_sync(st, "gram kernel"))) return rc;
+  }
+  return td_symmetrize_f32(G, pl.Dz, ldg, /*from_upper=*/1, stream);
+}

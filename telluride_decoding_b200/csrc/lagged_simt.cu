@@ -1,0 +1,405 @@
+// CUDA-core kernels that read the raw time-major streams directly through the lag mapping
+//   X_s[t, k*C + c] = x_s[t - pre + k, c]  (0 outside the segment)      brain_data.py:446-455
+//   * gram_simt:   fp32 FMA Gram, on-device cross-check of the tcgen05 kernel (method 1)
+//   * thin:        X'[v | 1] and [v | 1]'[v | 1] in float64            brain_model.py:436-439
+//   * predict:     (X - mean) W + b, the Dense / CCA-rotation forward   brain_model.py:340-341,
+//                                                                       cca.py:157-158
+//   * rows:        the lagged rows themselves (compat iterator only)
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace td {
+
+namespace {
+
+struct MultiView {
+  StreamView s[2];
+  int n_streams;
+  int64_t width[2];     // channels * lags
+  int64_t Dz;
+};
+
+// Element (row t of segment seg, design column j) of Z = [X_0 | X_1].
+__device__ __forceinline__ float design_at(const MultiView& mv, int seg, int64_t t, int64_t j) {
+  int q = 0;
+  if (mv.n_streams == 2 && j >= mv.width[0]) { q = 1; j -= mv.width[0]; }
+  const StreamView& s = mv.s[q];
+  const int k = (int)(j / s.channels);
+  const int c = (int)(j - (int64_t)k * s.channels);
+  const int64_t u = t - s.pre + k;
+  if (u < 0 || u >= s.seg_len[seg]) return 0.0f;
+  return __ldg(s.data + (s.seg_start[seg] + u) * s.ld + c);
+}
+
+constexpr int GT = 64;   // output tile
+constexpr int GK = 16;   // frames per step
+
+// One block: 64x64 tile of the upper triangle, a slice of segments (blockIdx.z).
+__global__ void __launch_bounds__(256) gram_simt_kernel(MultiView mv, const int64_t* seg_keep,
+                                                        int n_seg, int seg_per_z, float* G,
+                                                        int64_t ldg) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  __shared__ float As[GK][GT + 1];
+  __shared__ float Bs[GK][GT + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  const int s0 = blockIdx.z * seg_per_z, s1 = min(n_seg, s0 + seg_per_z);
+  for (int seg = s0; seg < s1; ++seg) {
+    const int64_t keep = seg_keep[seg];
+    for (int64_t t0 = 0; t0 < keep; t0 += GK) {
+      for (int e = threadIdx.x; e < GK * GT; e += 256) {
+        const int r = e / GT, col = e % GT;
+        const int64_t t = t0 + r;
+        const int64_t ja = (int64_t)bi * GT + col, jb = (int64_t)bj * GT + col;
+        As[r][col] = (t < keep && ja < mv.Dz) ? design_at(mv, seg, t, ja) : 0.0f;
+        Bs[r][col] = (t < keep && jb < mv.Dz) ? design_at(mv, seg, t, jb) : 0.0f;
+      }
+      __syncthreads();
+      float part[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) part[a][b] = 0.0f;
+#pragma unroll
+      for (int r = 0; r < GK; ++r) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) av[a] = As[r][ty * 4 + a];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bv[b] = Bs[r][tx * 4 + b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) part[a][b] = fmaf(av[a], bv[b], part[a][b]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] += (double)part[a][b];
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t i = (int64_t)bi * GT + ty * 4 + a, j = (int64_t)bj * GT + tx * 4 + b;
+      if (i < mv.Dz && j < mv.Dz && j >= i) atomicAdd(G + i * ldg + j, (float)acc[a][b]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int THIN_TB = 512;   // frames per block
+constexpr int THIN_QMAX = 16;
+
+__global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, int has_v, int Q,
+                                                   const int64_t* seg_keep, const int* blk_seg,
+                                                   const int64_t* blk_t0, double* xtv,
+                                                   double* vtv) {
+  __shared__ float Vs[THIN_TB][THIN_QMAX];
+  const int seg = blk_seg[blockIdx.x];
+  const int64_t t0 = blk_t0[blockIdx.x];
+  const int64_t keep = seg_keep[seg];
+  const int rows = (int)min((int64_t)THIN_TB, keep - t0);
+  for (int e = threadIdx.x; e < rows * Q; e += blockDim.x) {
+    const int r = e / Q, q = e % Q;
+    float val = 1.0f;
+    if (q < Q - 1) {
+      const int64_t u = t0 + r;
+      val = (has_v && u < v.seg_len[seg]) ? __ldg(v.data + (v.seg_start[seg] + u) * v.ld + q) : 0.0f;
+    }
+    Vs[r][q] = val;
+  }
+  __syncthreads();
+  const int64_t Dx = (int64_t)x.channels * x.lags;
+  const int64_t len = x.seg_len[seg];
+  const float* base = x.data + x.seg_start[seg] * x.ld;
+  for (int64_t j = threadIdx.x; j < Dx; j += blockDim.x) {
+    const int k = (int)(j / x.channels);
+    const int c = (int)(j - (int64_t)k * x.channels);
+    double acc[THIN_QMAX];
+#pragma unroll
+    for (int q = 0; q < THIN_QMAX; ++q) acc[q] = 0.0;
+    for (int r = 0; r < rows; ++r) {
+      const int64_t u = t0 + r - x.pre + k;
+      if (u < 0 || u >= len) continue;
+      const double xv = (double)__ldg(base + u * x.ld + c);
+#pragma unroll
+      for (int q = 0; q < THIN_QMAX; ++q)
+        if (q < Q) acc[q] += xv * (double)Vs[r][q];
+    }
+#pragma unroll
+    for (int q = 0; q < THIN_QMAX; ++q)
+      if (q < Q) atomicAdd(xtv + j * Q + q, acc[q]);
+  }
+  for (int e = threadIdx.x; e < Q * Q; e += blockDim.x) {
+    const int a = e / Q, b = e % Q;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += (double)Vs[r][a] * (double)Vs[r][b];
+    atomicAdd(vtv + e, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int PR_ROWS = 4;     // rows per warp
+constexpr int PR_QC = 8;       // output columns per pass
+
+__global__ void __launch_bounds__(256) predict_kernel(StreamView x, const int64_t* seg_keep,
+                                                      const int64_t* out_row, const int* blk_seg,
+                                                      const int64_t* blk_t0, int rows_per_block,
+                                                      const float* __restrict__ W,
+                                                      const float* __restrict__ bias,
+                                                      const float* __restrict__ mean, int Dy,
+                                                      float* out, int64_t ldo) {
+  const int seg = blk_seg[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t keep = seg_keep[seg];
+  const int64_t t0 = blk_t0[blockIdx.x] + (int64_t)warp * PR_ROWS;
+  if (t0 >= keep || warp * PR_ROWS >= rows_per_block) return;
+  const int64_t len = x.seg_len[seg];
+  const float* base = x.data + x.seg_start[seg] * x.ld;
+  const int64_t Dx = (int64_t)x.channels * x.lags;
+  for (int q0 = 0; q0 < Dy; q0 += PR_QC) {
+    float acc[PR_ROWS][PR_QC];
+#pragma unroll
+    for (int r = 0; r < PR_ROWS; ++r)
+#pragma unroll
+      for (int q = 0; q < PR_QC; ++q) acc[r][q] = 0.0f;
+    int k = lane / x.channels, c = lane % x.channels;
+    for (int64_t j = lane; j < Dx; j += 32) {
+      float w[PR_QC];
+#pragma unroll
+      for (int q = 0; q < PR_QC; ++q) w[q] = (q0 + q < Dy) ? __ldg(W + j * Dy + q0 + q) : 0.0f;
+      const float mu = mean ? __ldg(mean + j) : 0.0f;
+#pragma unroll
+      for (int r = 0; r < PR_ROWS; ++r) {
+        const int64_t u = t0 + r - x.pre + k;
+        float xv = (u >= 0 && u < len) ? __ldg(base + u * x.ld + c) : 0.0f;
+        xv -= mu;
+#pragma unroll
+        for (int q = 0; q < PR_QC; ++q) acc[r][q] = fmaf(xv, w[q], acc[r][q]);
+      }
+      c += 32;
+      while (c >= x.channels) { c -= x.channels; ++k; }
+    }
+#pragma unroll
+    for (int r = 0; r < PR_ROWS; ++r)
+#pragma unroll
+      for (int q = 0; q < PR_QC; ++q) {
+        float s = acc[r][q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && q0 + q < Dy && t0 + r < keep)
+          out[(out_row[seg] + t0 + r) * ldo + q0 + q] = s + (bias ? bias[q0 + q] : 0.0f);
+      }
+  }
+}
+
+__global__ void rows_kernel(StreamView x, const int64_t* seg_keep, const int64_t* out_row,
+                            const int* blk_seg, const int64_t* blk_t0, int rows_per_block,
+                            float* out, int64_t ldo) {
+  const int seg = blk_seg[blockIdx.x];
+  const int64_t keep = seg_keep[seg];
+  const int64_t len = x.seg_len[seg];
+  const int64_t Dx = (int64_t)x.channels * x.lags;
+  const float* base = x.data + x.seg_start[seg] * x.ld;
+  for (int r = 0; r < rows_per_block; ++r) {
+    const int64_t t = blk_t0[blockIdx.x] + r;
+    if (t >= keep) break;
+    for (int64_t j = threadIdx.x; j < Dx; j += blockDim.x) {
+      const int k = (int)(j / x.channels);
+      const int c = (int)(j - (int64_t)k * x.channels);
+      const int64_t u = t - x.pre + k;
+      out[(out_row[seg] + t) * ldo + j] = (u >= 0 && u < len) ? __ldg(base + u * x.ld + c) : 0.0f;
+    }
+  }
+}
+
+// Device copies of the segment tables of one stream (+ keep, out_row), stream-ordered.
+struct DevTables {
+  std::vector<void*> ptrs;
+  cudaStream_t st;
+  explicit DevTables(cudaStream_t s) : st(s) {}
+  ~DevTables() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+  template <typename T>
+  int put(const T* host, size_t n, const T** dev) {
+    std::vector<T> h(host, host + n);
+    T* d = nullptr;
+    int rc = upload(h, &d, st);
+    if (rc) return rc;
+    ptrs.push_back(d);
+    *dev = d;
+    return TD_OK;
+  }
+};
+
+int make_view(const td_stream* s, int n_seg, DevTables& tabs, StreamView* v) {
+  v->data = s->data_dev;
+  v->ld = s->ld;
+  v->channels = s->channels;
+  v->pre = s->pre;
+  v->lags = lags_of(*s);
+  int rc = tabs.put(s->seg_start, n_seg, &v->seg_start);
+  if (rc) return rc;
+  return tabs.put(s->seg_len, n_seg, &v->seg_len);
+}
+
+// (segment, first row) of every block when each block covers `rows` kept rows of one segment.
+int make_blocks(const int64_t* seg_keep, int n_seg, int rows, DevTables& tabs, const int** blk_seg,
+                const int64_t** blk_t0, int64_t* n_blocks) {
+  std::vector<int> bs;
+  std::vector<int64_t> bt;
+  for (int s = 0; s < n_seg; ++s)
+    for (int64_t t = 0; t < seg_keep[s]; t += rows) { bs.push_back(s); bt.push_back(t); }
+  *n_blocks = (int64_t)bs.size();
+  int rc = tabs.put(bs.data(), bs.size(), blk_seg);
+  if (rc) return rc;
+  return tabs.put(bt.data(), bt.size(), blk_t0);
+}
+
+}  // namespace
+
+int check_stream(const td_stream* s, const int64_t* seg_keep, int n_seg, const char* what) {
+  TD_REQUIRE(s != nullptr, "%s: null stream", what);
+  TD_REQUIRE(s->data_dev != nullptr, "%s: stream has no data", what);
+  TD_REQUIRE(s->channels > 0, "%s: stream must have at least one channel, not %d", what, s->channels);
+  TD_REQUIRE(s->pre >= 0, "%s: pre_context must be >= 0", what);
+  TD_REQUIRE(s->post >= 0, "%s: post_context must be >= 0", what);
+  TD_REQUIRE(s->ld >= s->channels, "%s: row stride %lld < channels %d", what, (long long)s->ld, s->channels);
+  TD_REQUIRE(s->seg_start && s->seg_len, "%s: missing segment table", what);
+  for (int i = 0; i < n_seg; ++i) {
+    TD_REQUIRE(s->seg_start[i] >= 0 && s->seg_len[i] >= 0, "%s: negative segment bounds at %d", what, i);
+    if (seg_keep)
+      TD_REQUIRE(seg_keep[i] >= 0, "%s: negative keep count at segment %d", what, i);
+  }
+  return TD_OK;
+}
+
+int launch_gram_simt(const td_stream* streams, int n_streams, const int64_t* seg_keep, int n_seg,
+                     float* G, int64_t ldg, cudaStream_t st) {
+  DevTables tabs(st);
+  MultiView mv;
+  mv.n_streams = n_streams;
+  mv.Dz = 0;
+  mv.width[0] = mv.width[1] = 0;
+  for (int q = 0; q < n_streams; ++q) {
+    int rc = make_view(&streams[q], n_seg, tabs, &mv.s[q]);
+    if (rc) return rc;
+    mv.width[q] = width_of(streams[q]);
+    mv.Dz += mv.width[q];
+  }
+  if (n_streams == 1) mv.s[1] = mv.s[0];
+  const int64_t* keep_dev;
+  int rc = tabs.put(seg_keep, n_seg, &keep_dev);
+  if (rc) return rc;
+  TD_CHECK_CUDA(cudaMemset2DAsync(G, (size_t)ldg * sizeof(float), 0, (size_t)mv.Dz * sizeof(float), (size_t)mv.Dz, st));
+  const int nb = (int)ceil_div(mv.Dz, GT);
+  int zsplit = std::max(1, std::min(n_seg, (int)(1024 / std::max(1, nb * (nb + 1) / 2))));
+  const int seg_per_z = (int)ceil_div(n_seg, zsplit);
+  zsplit = (int)ceil_div(n_seg, seg_per_z);
+  gram_simt_kernel<<<dim3(nb, nb, zsplit), 256, 0, st>>>(mv, keep_dev, n_seg, seg_per_z, G, ldg);
+  TD_CHECK_CUDA(cudaGetLastError());
+  return td_symmetrize_f32(G, mv.Dz, ldg, 1, st);
+}
+
+}  // namespace td
+
+using namespace td;
+
+extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const int64_t* seg_keep,
+                                  int n_seg, double* xtv, double* vtv, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_REQUIRE(x && seg_keep && xtv && vtv && n_seg > 0, "td_lagged_thin_f64: null argument");
+  int rc = check_stream(x, seg_keep, n_seg, "td_lagged_thin_f64");
+  if (rc) return rc;
+  int Q = 1;
+  if (v) {
+    rc = check_stream(v, seg_keep, n_seg, "td_lagged_thin_f64");
+    if (rc) return rc;
+    TD_REQUIRE(v->pre == 0 && v->post == 0, "td_lagged_thin_f64: the thin stream must not have context");
+    Q = v->channels + 1;
+  }
+  if (Q > THIN_QMAX) {
+    set_error("td_lagged_thin_f64: %d target columns (+1) exceed %d; use td_lagged_gram_f32 with two streams", Q - 1, THIN_QMAX);
+    return TD_ERR_UNSUPPORTED;
+  }
+  DevTables tabs(st);
+  StreamView xv, vv;
+  rc = make_view(x, n_seg, tabs, &xv);
+  if (rc) return rc;
+  vv = xv;
+  if (v) { rc = make_view(v, n_seg, tabs, &vv); if (rc) return rc; }
+  const int64_t* keep_dev;
+  rc = tabs.put(seg_keep, n_seg, &keep_dev);
+  if (rc) return rc;
+  const int* blk_seg; const int64_t* blk_t0; int64_t nblk;
+  rc = make_blocks(seg_keep, n_seg, THIN_TB, tabs, &blk_seg, &blk_t0, &nblk);
+  if (rc) return rc;
+  const int64_t Dx = width_of(*x);
+  TD_CHECK_CUDA(cudaMemsetAsync(xtv, 0, (size_t)Dx * Q * sizeof(double), st));
+  TD_CHECK_CUDA(cudaMemsetAsync(vtv, 0, (size_t)Q * Q * sizeof(double), st));
+  if (nblk > 0) {
+    thin_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, xtv, vtv);
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
+  return TD_OK;
+}
+
+extern "C" int td_lagged_predict_f32(const td_stream* x, const int64_t* seg_keep,
+                                     const int64_t* out_row, int n_seg, const float* W,
+                                     const float* bias, const float* mean, int Dy, float* out,
+                                     int64_t ldo, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_REQUIRE(x && seg_keep && out_row && W && out && n_seg > 0, "td_lagged_predict_f32: null argument");
+  TD_REQUIRE(Dy >= 1 && Dy <= 64 && ldo >= Dy, "td_lagged_predict_f32: Dy=%d ldo=%lld out of range", Dy, (long long)ldo);
+  int rc = check_stream(x, seg_keep, n_seg, "td_lagged_predict_f32");
+  if (rc) return rc;
+  DevTables tabs(st);
+  StreamView xv;
+  rc = make_view(x, n_seg, tabs, &xv);
+  if (rc) return rc;
+  const int64_t *keep_dev, *orow_dev;
+  rc = tabs.put(seg_keep, n_seg, &keep_dev); if (rc) return rc;
+  rc = tabs.put(out_row, n_seg, &orow_dev); if (rc) return rc;
+  const int rows_per_block = 8 * PR_ROWS;
+  const int* blk_seg; const int64_t* blk_t0; int64_t nblk;
+  rc = make_blocks(seg_keep, n_seg, rows_per_block, tabs, &blk_seg, &blk_t0, &nblk);
+  if (rc) return rc;
+  if (nblk > 0) {
+    predict_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, W, bias, mean, Dy, out, ldo);
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
+  return TD_OK;
+}
+
+extern "C" int td_lagged_rows_f32(const td_stream* x, const int64_t* seg_keep, const int64_t* out_row,
+                                  int n_seg, float* out, int64_t ldo, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_REQUIRE(x && seg_keep && out_row && out && n_seg > 0, "td_lagged_rows_f32: null argument");
+  int rc = check_stream(x, seg_keep, n_seg, "td_lagged_rows_f32");
+  if (rc) return rc;
+  TD_REQUIRE(ldo >= width_of(*x), "td_lagged_rows_f32: ldo too small");
+  DevTables tabs(st);
+  StreamView xv;
+  rc = make_view(x, n_seg, tabs, &xv);
+  if (rc) return rc;
+  const int64_t *keep_dev, *orow_dev;
+  rc = tabs.put(seg_keep, n_seg, &keep_dev); if (rc) return rc;
+  rc = tabs.put(out_row, n_seg, &orow_dev); if (rc) return rc;
+  const int rows_per_block = 16;
+  const int* blk_seg; const int64_t* blk_t0; int64_t nblk;
+  rc = make_blocks(seg_keep, n_seg, rows_per_block, tabs, &blk_seg, &blk_t0, &nblk);
+  if (rc) return rc;
+  if (nblk > 0) {
+    rows_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, out, ldo);
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
+  return TD_OK;
+}

@@ -1,0 +1,214 @@
+"""Python faces of the libtdgram.so entry points (one function per C symbol).
+
+Tensors are torch CUDA tensors (they cross into the library as raw device pointers, i.e. what
+DLPack hands over); segment tables, lambda lists and window shapes are host lists.  Each wrapper
+cites the reference code the kernel replaces.
+"""
+
+import ctypes
+
+import torch
+
+from telluride_decoding_b200 import _lib
+from telluride_decoding_b200._lib import Stream  # re-export  pylint: disable=unused-import
+
+REDUCTIONS = {'first': 0, 'second': 1, 'mean': 2, 'mean-squared': 3}
+
+
+def _streams_array(streams):
+  arr = (_lib.TdStream * len(streams))()
+  for i, s in enumerate(streams):
+    arr[i] = s.c_struct()
+  return arr
+
+
+def gram_options(method=0, cta_group=0, chunk_rows=0, superchunk_rows=0, max_ctas=0):
+  return _lib.TdGramOptions(method, cta_group, chunk_rows, superchunk_rows, max_ctas)
+
+
+class GramWorkspace(object):
+  """Caches the staging workspace between calls of the same shape (torch owns the memory)."""
+
+  def __init__(self):
+    self.buffer = None
+
+  def get(self, nbytes, device):
+    if self.buffer is None or self.buffer.numel() < nbytes or self.buffer.device != device:
+      self.buffer = None
+      self.buffer = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    return self.buffer
+
+
+_default_workspace = GramWorkspace()
+
+
+def lagged_gram(streams, seg_keep, out=None, options=None, workspace=None):
+  """G = Z'Z over the implicit lagged design Z = [X_0 | X_1]  (brain_model.py:437, cca.py:325-327).
+
+  Returns a float32 [Dz, Dz] CUDA tensor (full symmetric)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = streams[0].data.device
+  dz = sum(s.width for s in streams)
+  if out is None:
+    out = torch.empty((dz, dz), dtype=torch.float32, device=device)
+  options = options or gram_options()
+  carr = _streams_array(streams)
+  keep = _lib.i64_array(seg_keep)
+  nbytes = ctypes.c_size_t(0)
+  _lib.check(lib.td_lagged_gram_workspace_bytes(carr, len(streams), keep, len(seg_keep),
+                                                ctypes.byref(options), ctypes.byref(nbytes)))
+  ws = (workspace or _default_workspace).get(nbytes.value, device)
+  with torch.cuda.device(device):
+    _lib.check(lib.td_lagged_gram_f32(carr, len(streams), keep, len(seg_keep), _lib.ptr(out),
+                                      ctypes.c_int64(out.stride(0)), ctypes.byref(options),
+                                      _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+                                      _lib.current_stream_ptr()))
+  return out
+
+
+def lagged_thin(x, v, seg_keep):
+  """(X'[v|1], [v|1]'[v|1]) in float64  (brain_model.py:436-439, cca.py:328-329)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = x.data.device
+  q = (v.channels if v is not None else 0) + 1
+  xtv = torch.empty((x.width, q), dtype=torch.float64, device=device)
+  vtv = torch.empty((q, q), dtype=torch.float64, device=device)
+  xs = x.c_struct()
+  vs = v.c_struct() if v is not None else None
+  with torch.cuda.device(device):
+    _lib.check(lib.td_lagged_thin_f64(ctypes.byref(xs), ctypes.byref(vs) if vs is not None else None,
+                                      _lib.i64_array(seg_keep), len(seg_keep), _lib.ptr(xtv),
+                                      _lib.ptr(vtv), _lib.current_stream_ptr()))
+  return xtv, vtv
+
+
+def lagged_predict(x, seg_keep, out_row, weights, bias=None, mean=None, out=None, total_rows=None):
+  """out = (X - mean) W + b on the implicit design (brain_model.py:340-341, cca.py:157-158)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = x.data.device
+  weights = weights.contiguous()
+  dy = int(weights.shape[1])
+  if int(weights.shape[0]) != x.width:
+    raise ValueError('weights have %d rows, the lagged input has %d columns' %
+                     (weights.shape[0], x.width))
+  if out is None:
+    if total_rows is None:
+      total_rows = max([r + k for r, k in zip(out_row, seg_keep)] + [0])
+    out = torch.empty((total_rows, dy), dtype=torch.float32, device=device)
+  xs = x.c_struct()
+  with torch.cuda.device(device):
+    _lib.check(lib.td_lagged_predict_f32(ctypes.byref(xs), _lib.i64_array(seg_keep),
+                                         _lib.i64_array(out_row), len(seg_keep), _lib.ptr(weights),
+                                         _lib.ptr(bias), _lib.ptr(mean), dy, _lib.ptr(out),
+                                         ctypes.c_int64(out.stride(0)), _lib.current_stream_ptr()))
+  return out
+
+
+def lagged_rows(x, seg_keep, out_row, total_rows):
+  """The lagged rows themselves, [total_rows, C*L]  (brain_data.py:453-455); tests / compat only."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  out = torch.zeros((total_rows, x.width), dtype=torch.float32, device=x.data.device)
+  xs = x.c_struct()
+  with torch.cuda.device(x.data.device):
+    _lib.check(lib.td_lagged_rows_f32(ctypes.byref(xs), _lib.i64_array(seg_keep),
+                                      _lib.i64_array(out_row), len(seg_keep), _lib.ptr(out),
+                                      ctypes.c_int64(out.stride(0)), _lib.current_stream_ptr()))
+  return out
+
+
+def ridge_solve(g_aug, c_aug, n, lambdas, method=0):
+  """[n_lambda, Da, Dy] float32 solutions of (G/n + lambda I) W = C/n  (brain_model.py:447-479)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  g_aug = g_aug.to(torch.float64).contiguous()
+  c_aug = c_aug.to(torch.float64).contiguous()
+  da, dy = int(c_aug.shape[0]), int(c_aug.shape[1])
+  lambdas = [float(l) for l in lambdas]
+  out = torch.empty((len(lambdas), da, dy), dtype=torch.float32, device=g_aug.device)
+  with torch.cuda.device(g_aug.device):
+    _lib.check(lib.td_ridge_solve(_lib.ptr(g_aug), _lib.ptr(c_aug), da, dy, ctypes.c_double(n),
+                                  _lib.f64_array(lambdas), len(lambdas), int(method),
+                                  _lib.ptr(out), _lib.current_stream_ptr()))
+  return out
+
+
+def cca_solve(gxx, gyy, gxy, sum_x, sum_y, n_frames, n_norm, reg, eps_eig, dim):
+  """(rot_x, rot_y, mean_x, mean_y, e) float32  (cca.py:337-367)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = gxx.device
+  f64 = lambda t: t.to(torch.float64).contiguous()
+  gxx, gyy, gxy, sum_x, sum_y = f64(gxx), f64(gyy), f64(gxy), f64(sum_x).reshape(-1), f64(sum_y).reshape(-1)
+  d1, d2 = int(gxx.shape[0]), int(gyy.shape[0])
+  rot_x = torch.empty((d1, dim), dtype=torch.float32, device=device)
+  rot_y = torch.empty((d2, dim), dtype=torch.float32, device=device)
+  mean_x = torch.empty((1, d1), dtype=torch.float32, device=device)
+  mean_y = torch.empty((1, d2), dtype=torch.float32, device=device)
+  e = torch.empty((dim,), dtype=torch.float32, device=device)
+  with torch.cuda.device(device):
+    _lib.check(lib.td_cca_solve(_lib.ptr(gxx), _lib.ptr(gyy), _lib.ptr(gxy), _lib.ptr(sum_x),
+                                _lib.ptr(sum_y), d1, d2, ctypes.c_double(n_frames),
+                                ctypes.c_double(n_norm), ctypes.c_double(reg),
+                                ctypes.c_double(eps_eig), int(dim), _lib.ptr(rot_x), _lib.ptr(rot_y),
+                                _lib.ptr(mean_x), _lib.ptr(mean_y), _lib.ptr(e),
+                                _lib.current_stream_ptr()))
+  return rot_x, rot_y, mean_x, mean_y, e
+
+
+def column_moments(a, b, sums=None):
+  """sums[4, dims] (float64) += [sum a, sum b, sum a^2, sum b^2]  (infer_decoder.py:299-303)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  dims = int(a.shape[1])
+  if sums is None:
+    sums = torch.zeros((4, dims), dtype=torch.float64, device=a.device)
+  with torch.cuda.device(a.device):
+    _lib.check(lib.td_column_moments_f64(_lib.ptr(a), ctypes.c_int64(a.stride(0)), _lib.ptr(b),
+                                         ctypes.c_int64(b.stride(0)), ctypes.c_int64(a.shape[0]),
+                                         dims, _lib.ptr(sums), _lib.current_stream_ptr()))
+  return sums
+
+
+def window_count(n_frames, width, step):
+  return int(_lib.load().td_window_count(int(n_frames), int(width), int(step)))
+
+
+def windowed_corr(a, b, seg_start, seg_len, widths, steps, mode, reduction='first', mu_a=None,
+                  mu_b=None, power=None):
+  """Sliding-window values for every (width, step) shape in one pass over the data.
+
+  mode 'plain' | 'global' | 'local' (see tdgram.h).  Returns (values float64 [windows, cols],
+  offsets list with n_sizes+1 entries); rows are ordered size, segment, window."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  mode_id = {'plain': 0, 'global': 1, 'local': 2}[mode]
+  dims = int(a.shape[1]) if mode_id else 1
+  total = sum(window_count(n, w, s) for w, s in zip(widths, steps) for n in seg_len)
+  cols = dims if mode_id == 2 else 1
+  out = torch.empty((max(total, 1), cols), dtype=torch.float64, device=a.device)
+  offsets = (ctypes.c_int64 * (len(widths) + 1))()
+  with torch.cuda.device(a.device):
+    _lib.check(lib.td_windowed_corr_f32(
+        _lib.ptr(a), ctypes.c_int64(a.stride(0)), _lib.ptr(b),
+        ctypes.c_int64(b.stride(0) if b is not None else 0), dims, _lib.i64_array(seg_start),
+        _lib.i64_array(seg_len), len(seg_len), _lib.i64_array(widths), _lib.i64_array(steps),
+        len(widths), mode_id, REDUCTIONS.get(reduction, 0), _lib.ptr(mu_a), _lib.ptr(mu_b),
+        _lib.ptr(power), _lib.ptr(out), offsets, _lib.current_stream_ptr()))
+  return out[:total], [int(o) for o in offsets]
+
+
+def wta_decide(r1, r2):
+  """uint8 [n]: r1 > r2  (attention_decoder.py:134)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  r1 = r1.to(torch.float64).contiguous().reshape(-1)
+  r2 = r2.to(torch.float64).contiguous().reshape(-1)
+  out = torch.empty((r1.numel(),), dtype=torch.uint8, device=r1.device)
+  with torch.cuda.device(r1.device):
+    _lib.check(lib.td_wta_decide_u8(_lib.ptr(r1), _lib.ptr(r2), ctypes.c_int64(r1.numel()),
+                                    _lib.ptr(out), _lib.current_stream_ptr()))
+  return out
