@@ -96,11 +96,20 @@ int td_lagged_gram_f32(const td_stream* streams, int n_streams,
  * (brain_model.py:436-439), `sum_x`/`sum_y` of cca.py:328-329.
  *   V = [v_0 .. v_{Q-2}, 1]  (v = thin stream without lags, may be NULL: then V = [1])
  *   xtv_dev [Dx, Q] double  = X'V        vtv_dev [Q, Q] double = V'V   (V'V[Q-1,Q-1] = row count)
+ * over design rows [seg_first[s], seg_keep[s]) (seg_first may be NULL = 0).
  * Both are zeroed by the call.  Q = (v ? v->channels : 0) + 1 <= 16.
  * ------------------------------------------------------------------------------------- */
 int td_lagged_thin_f64(const td_stream* x, const td_stream* v,
-                       const int64_t* seg_keep, int n_seg,
+                       const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
                        double* xtv_dev, double* vtv_dev, void* cuda_stream);
+
+/* Gram over the row ranges [seg_first[s], seg_keep[s]) of each segment (seg_first NULL = 0), on
+ * CUDA cores in fp32 with float64 carry.  Used for the small leave-one-out corrections: the
+ * < batch_size rows that `drop_remainder` (brain_data.py:369-370) removes from a fold's training
+ * stream are a suffix of some segments, and their Gram is subtracted from the all-rows Gram. */
+int td_lagged_gram_range_f32(const td_stream* streams, int n_streams, const int64_t* seg_first,
+                             const int64_t* seg_keep, int n_seg, float* G_dev, int64_t ldg,
+                             void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------
  * Forward pass.  Replaces Keras Dense on the lagged batch (brain_model.py:340-341) and one half

@@ -475,10 +475,20 @@ class TrialBrainData(BrainData):
     self._trials[str(name)] = (x, x2, y, a)
     self._cached_file_names = []
     self._dirty = True
+    # Feature table keyed by the experiment's own field names (the first input field carries the
+    # whole input width), plus the generic names TestBrainData uses.
     self.features = {'input_1': FixedLenFeature([int(x.shape[1]),]),
                      'output': FixedLenFeature([int(y.shape[1]),]),
                      'input_2': FixedLenFeature([int(x2.shape[1]),]),
                      'attention': FixedLenFeature([int(a.shape[1]),])}
+    self.features[self.in1_fields[0]] = FixedLenFeature([int(x.shape[1]),])
+    for extra in self.in1_fields[1:]:
+      self.features.setdefault(extra, FixedLenFeature([0,]))
+    self.features[self.out_field] = FixedLenFeature([int(y.shape[1]),])
+    if self.in2_fields:
+      self.features[self.in2_fields[0]] = FixedLenFeature([int(x2.shape[1]),])
+    if self.attended_field:
+      self.features[self.attended_field] = FixedLenFeature([int(a.shape[1]),])
 
   def _pack(self):
     if not self._dirty:

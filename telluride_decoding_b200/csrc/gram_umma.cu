@@ -34,8 +34,8 @@
 
 namespace td {
 
-int launch_gram_simt(const td_stream* streams, int n_streams, const int64_t* seg_keep, int n_seg,
-                     float* G, int64_t ldg, cudaStream_t st);
+int launch_gram_simt(const td_stream* streams, int n_streams, const int64_t* seg_first,
+                     const int64_t* seg_keep, int n_seg, float* G, int64_t ldg, cudaStream_t st);
 
 namespace {
 
@@ -565,7 +565,7 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       Dz += width_of(streams[q]);
     }
     TD_REQUIRE(ldg >= Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)Dz);
-    return launch_gram_simt(streams, n_streams, seg_keep, n_seg, G, ldg, st);
+    return launch_gram_simt(streams, n_streams, nullptr, seg_keep, n_seg, G, ldg, st);
   }
   TD_REQUIRE(opt == nullptr || opt->method == 0, "td_lagged_gram_f32: unknown method %d", opt->method);
   GramPlan pl;

@@ -37,9 +37,9 @@ constexpr int GT = 64;   // output tile
 constexpr int GK = 16;   // frames per step
 
 // One block: 64x64 tile of the upper triangle, a slice of segments (blockIdx.z).
-__global__ void __launch_bounds__(256) gram_simt_kernel(MultiView mv, const int64_t* seg_keep,
-                                                        int n_seg, int seg_per_z, float* G,
-                                                        int64_t ldg) {
+__global__ void __launch_bounds__(256) gram_simt_kernel(MultiView mv, const int64_t* seg_first,
+                                                        const int64_t* seg_keep, int n_seg,
+                                                        int seg_per_z, float* G, int64_t ldg) {
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bj < bi) return;
   __shared__ float As[GK][GT + 1];
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(MultiView mv, const int6
   const int s0 = blockIdx.z * seg_per_z, s1 = min(n_seg, s0 + seg_per_z);
   for (int seg = s0; seg < s1; ++seg) {
     const int64_t keep = seg_keep[seg];
-    for (int64_t t0 = 0; t0 < keep; t0 += GK) {
+    for (int64_t t0 = seg_first ? seg_first[seg] : 0; t0 < keep; t0 += GK) {
       for (int e = threadIdx.x; e < GK * GT; e += 256) {
         const int r = e / GT, col = e % GT;
         const int64_t t = t0 + r;
@@ -253,11 +253,11 @@ int make_view(const td_stream* s, int n_seg, DevTables& tabs, StreamView* v) {
 
 // (segment, first row) of every block when each block covers `rows` kept rows of one segment.
 int make_blocks(const int64_t* seg_keep, int n_seg, int rows, DevTables& tabs, const int** blk_seg,
-                const int64_t** blk_t0, int64_t* n_blocks) {
+                const int64_t** blk_t0, int64_t* n_blocks, const int64_t* seg_first = nullptr) {
   std::vector<int> bs;
   std::vector<int64_t> bt;
   for (int s = 0; s < n_seg; ++s)
-    for (int64_t t = 0; t < seg_keep[s]; t += rows) { bs.push_back(s); bt.push_back(t); }
+    for (int64_t t = seg_first ? seg_first[s] : 0; t < seg_keep[s]; t += rows) { bs.push_back(s); bt.push_back(t); }
   *n_blocks = (int64_t)bs.size();
   int rc = tabs.put(bs.data(), bs.size(), blk_seg);
   if (rc) return rc;
@@ -282,8 +282,8 @@ int check_stream(const td_stream* s, const int64_t* seg_keep, int n_seg, const c
   return TD_OK;
 }
 
-int launch_gram_simt(const td_stream* streams, int n_streams, const int64_t* seg_keep, int n_seg,
-                     float* G, int64_t ldg, cudaStream_t st) {
+int launch_gram_simt(const td_stream* streams, int n_streams, const int64_t* seg_first,
+                     const int64_t* seg_keep, int n_seg, float* G, int64_t ldg, cudaStream_t st) {
   DevTables tabs(st);
   MultiView mv;
   mv.n_streams = n_streams;
@@ -297,14 +297,16 @@ int launch_gram_simt(const td_stream* streams, int n_streams, const int64_t* seg
   }
   if (n_streams == 1) mv.s[1] = mv.s[0];
   const int64_t* keep_dev;
+  const int64_t* first_dev = nullptr;
   int rc = tabs.put(seg_keep, n_seg, &keep_dev);
   if (rc) return rc;
+  if (seg_first && (rc = tabs.put(seg_first, n_seg, &first_dev))) return rc;
   TD_CHECK_CUDA(cudaMemset2DAsync(G, (size_t)ldg * sizeof(float), 0, (size_t)mv.Dz * sizeof(float), (size_t)mv.Dz, st));
   const int nb = (int)ceil_div(mv.Dz, GT);
   int zsplit = std::max(1, std::min(n_seg, (int)(1024 / std::max(1, nb * (nb + 1) / 2))));
   const int seg_per_z = (int)ceil_div(n_seg, zsplit);
   zsplit = (int)ceil_div(n_seg, seg_per_z);
-  gram_simt_kernel<<<dim3(nb, nb, zsplit), 256, 0, st>>>(mv, keep_dev, n_seg, seg_per_z, G, ldg);
+  gram_simt_kernel<<<dim3(nb, nb, zsplit), 256, 0, st>>>(mv, first_dev, keep_dev, n_seg, seg_per_z, G, ldg);
   TD_CHECK_CUDA(cudaGetLastError());
   return td_symmetrize_f32(G, mv.Dz, ldg, 1, st);
 }
@@ -313,8 +315,24 @@ int launch_gram_simt(const td_stream* streams, int n_streams, const int64_t* seg
 
 using namespace td;
 
-extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const int64_t* seg_keep,
-                                  int n_seg, double* xtv, double* vtv, void* stream) {
+extern "C" int td_lagged_gram_range_f32(const td_stream* streams, int n_streams, const int64_t* seg_first,
+                                        const int64_t* seg_keep, int n_seg, float* G, int64_t ldg,
+                                        void* stream) {
+  TD_REQUIRE(streams && seg_keep && G && n_seg > 0, "td_lagged_gram_range_f32: null argument");
+  TD_REQUIRE(n_streams == 1 || n_streams == 2, "td_lagged_gram_range_f32: n_streams must be 1 or 2");
+  int64_t Dz = 0;
+  for (int q = 0; q < n_streams; ++q) {
+    int rc = check_stream(&streams[q], seg_keep, n_seg, "td_lagged_gram_range_f32");
+    if (rc) return rc;
+    Dz += width_of(streams[q]);
+  }
+  TD_REQUIRE(ldg >= Dz, "td_lagged_gram_range_f32: ldg too small");
+  return launch_gram_simt(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, (cudaStream_t)stream);
+}
+
+extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const int64_t* seg_first,
+                                  const int64_t* seg_keep, int n_seg, double* xtv, double* vtv,
+                                  void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   TD_REQUIRE(x && seg_keep && xtv && vtv && n_seg > 0, "td_lagged_thin_f64: null argument");
   int rc = check_stream(x, seg_keep, n_seg, "td_lagged_thin_f64");
@@ -340,7 +358,7 @@ extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const 
   rc = tabs.put(seg_keep, n_seg, &keep_dev);
   if (rc) return rc;
   const int* blk_seg; const int64_t* blk_t0; int64_t nblk;
-  rc = make_blocks(seg_keep, n_seg, THIN_TB, tabs, &blk_seg, &blk_t0, &nblk);
+  rc = make_blocks(seg_keep, n_seg, THIN_TB, tabs, &blk_seg, &blk_t0, &nblk, seg_first);
   if (rc) return rc;
   const int64_t Dx = width_of(*x);
   TD_CHECK_CUDA(cudaMemsetAsync(xtv, 0, (size_t)Dx * Q * sizeof(double), st));

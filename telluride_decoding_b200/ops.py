@@ -67,7 +67,24 @@ def lagged_gram(streams, seg_keep, out=None, options=None, workspace=None):
   return out
 
 
-def lagged_thin(x, v, seg_keep):
+def lagged_gram_range(streams, seg_first, seg_keep, out=None):
+  """Gram over design rows [seg_first, seg_keep) of each segment (CUDA cores; small corrections)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = streams[0].data.device
+  dz = sum(s.width for s in streams)
+  if out is None:
+    out = torch.empty((dz, dz), dtype=torch.float32, device=device)
+  carr = _streams_array(streams)
+  with torch.cuda.device(device):
+    _lib.check(lib.td_lagged_gram_range_f32(carr, len(streams), _lib.i64_array(seg_first),
+                                            _lib.i64_array(seg_keep), len(seg_keep), _lib.ptr(out),
+                                            ctypes.c_int64(out.stride(0)),
+                                            _lib.current_stream_ptr()))
+  return out
+
+
+def lagged_thin(x, v, seg_keep, seg_first=None):
   """(X'[v|1], [v|1]'[v|1]) in float64  (brain_model.py:436-439, cca.py:328-329)."""
   _lib.require_cuda()
   lib = _lib.load()
@@ -79,6 +96,7 @@ def lagged_thin(x, v, seg_keep):
   vs = v.c_struct() if v is not None else None
   with torch.cuda.device(device):
     _lib.check(lib.td_lagged_thin_f64(ctypes.byref(xs), ctypes.byref(vs) if vs is not None else None,
+                                      _lib.i64_array(seg_first) if seg_first is not None else None,
                                       _lib.i64_array(seg_keep), len(seg_keep), _lib.ptr(xtv),
                                       _lib.ptr(vtv), _lib.current_stream_ptr()))
   return xtv, vtv

@@ -1,0 +1,155 @@
+"""GPU parity of the decision layer: global statistics, per-frame correlation + reductions,
+sliding windows for several sizes in one pass, winner-take-all decisions (bit-identical)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_numpy as ora
+from telluride_decoding_b200 import attention_decoder
+from telluride_decoding_b200 import brain_model
+from telluride_decoding_b200 import infer
+from telluride_decoding_b200 import infer_decoder
+from telluride_decoding_b200 import ops
+from tests import gpu_util
+
+pytestmark = pytest.mark.gpu
+
+WINDOWS = [10, 100, 200, 400, 700, 1000]      # infer.py:376
+
+
+def _golden(golden_dir):
+  return np.load(os.path.join(golden_dir, 'decoder.npz'))
+
+
+def _stats(truth, pred):
+  cor = ora.Correlator()
+  for s in range(0, truth.shape[0], 200):
+    cor.add(truth[s:s + 200], pred[s:s + 200])
+  return cor
+
+
+@pytest.mark.parametrize('reduction', ['first', 'second', 'mean', 'mean-squared'])
+def test_windowed_global_correlation_matches_reference(golden_dir, reduction):
+  g = _golden(golden_dir)
+  truth, pred = g['truth'], g['pred']
+  cor = _stats(truth, pred)
+  t = lambda v: torch.as_tensor(np.ascontiguousarray(v), device='cuda')
+  vals, off = ops.windowed_corr(t(truth), t(pred), [0], [truth.shape[0]], WINDOWS,
+                                [w // 2 for w in WINDOWS], 'global', reduction=reduction,
+                                mu_a=t(cor.mean_x), mu_b=t(cor.mean_y), power=t(cor.power))
+  vals = vals.cpu().numpy()[:, 0]
+  for i, w in enumerate(WINDOWS):
+    want = g['s1_%s_w%d_res' % (reduction, w)]
+    got = vals[off[i]:off[i + 1]]
+    assert got.shape == want.shape                      # window count (N - W)//S + 1
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+
+
+def test_labels_windows_and_wta_decisions_bit_identical(golden_dir):
+  g = _golden(golden_dir)
+  t = lambda v: torch.as_tensor(np.ascontiguousarray(v), device='cuda')
+  n = g['truth'].shape[0]
+  res = {}
+  for which, p in (('s1', g['pred']), ('s2', g['pred2'])):
+    cor = _stats(g['truth'], p)
+    vals, off = ops.windowed_corr(t(g['truth']), t(p), [0], [n], WINDOWS, [w // 2 for w in WINDOWS],
+                                  'global', reduction='first', mu_a=t(cor.mean_x),
+                                  mu_b=t(cor.mean_y), power=t(cor.power))
+    res[which] = (vals, off)
+  labs, off = ops.windowed_corr(t(g['label']), None, [0], [n], WINDOWS, [w // 2 for w in WINDOWS],
+                                'plain')
+  labs = labs.cpu().numpy()[:, 0]
+  for i, w in enumerate(WINDOWS):
+    np.testing.assert_array_equal(labs[off[i]:off[i + 1]], g['s1_first_w%d_lab' % w])
+    r1 = res['s1'][0][off[i]:off[i + 1], 0]
+    r2 = res['s2'][0][off[i]:off[i + 1], 0]
+    wta = ops.wta_decide(r1, r2).cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(wta, g['wta_w%d' % w])
+    np.testing.assert_array_equal(attention_decoder.step_decisions(wta), g['step_w%d' % w])
+
+
+def test_column_moments_and_multi_segment_windows():
+  rng = np.random.RandomState(3)
+  a = rng.randn(5000, 3).astype(np.float32) + 1
+  b = rng.randn(5000, 3).astype(np.float32) * 2
+  t = lambda v: torch.as_tensor(v, device='cuda')
+  sums = ops.column_moments(t(a), t(b)).cpu().numpy()
+  a64, b64 = a.astype(np.float64), b.astype(np.float64)
+  np.testing.assert_allclose(sums, [a64.sum(0), b64.sum(0), (a64 ** 2).sum(0), (b64 ** 2).sum(0)],
+                             rtol=1e-12)
+  # windows never straddle trials: three segments, odd window shape (gcd 1 path)
+  seg_start, seg_len = [0, 1500, 3100], [1500, 1600, 1900]
+  vals, off = ops.windowed_corr(t(a), None, seg_start, seg_len, [301, 64], [150, 32], 'plain')
+  vals = vals.cpu().numpy()[:, 0]
+  want = []
+  for w, s in ((301, 150), (64, 32)):
+    for st, n in zip(seg_start, seg_len):
+      sig = a64[st:st + n, 0]
+      want += [sig[i:i + w].mean() for i in ora.window_starts(n, w, s)]
+  np.testing.assert_allclose(vals, want, rtol=1e-12)
+  assert off[1] == sum(ops.window_count(n, 301, 150) for n in seg_len)
+  from telluride_decoding_b200 import _lib
+  with pytest.raises(_lib.TdError, match='step 0 never terminates'):
+    ops.windowed_corr(t(a), None, [0], [100], [1], [0], 'plain')
+
+
+def test_local_pearson_windows_and_zero_rule():
+  rng = np.random.RandomState(5)
+  a = rng.randn(3000, 4).astype(np.float32) + 3
+  b = (0.5 * a + rng.randn(3000, 4)).astype(np.float32)
+  t = lambda v: torch.as_tensor(v, device='cuda')
+  vals, _ = ops.windowed_corr(t(a), t(b), [0], [3000], [500], [500], 'local')
+  want = np.array([ora.pearson_correlation(a[i:i + 500].astype(np.float64),
+                                           b[i:i + 500].astype(np.float64))
+                   for i in range(0, 3000, 500)])
+  np.testing.assert_allclose(vals.cpu().numpy(), want, rtol=1e-9, atol=1e-12)
+  a[:, 2] = 7.0      # a constant column zeroes the whole vector (brain_model.py:72-79)
+  vals, _ = ops.windowed_corr(t(a), t(b), [0], [3000], [500], [500], 'local')
+  assert np.all(vals.cpu().numpy() == 0)
+
+
+def test_decoder_end_to_end_attention_accuracy():
+  """Two-speaker synthetic experiment in the spirit of test/infer_test.py:158-176: the attended
+  envelope drives the EEG; accuracy > 0.95 for windows >= 100 frames, and the window values equal
+  the oracle's run on the same model outputs."""
+  rng = np.random.RandomState(21)
+  n, c, post = 12000, 16, 7
+  env1 = rng.randn(n + post, 1).astype(np.float32)
+  env2 = rng.randn(n + post, 1).astype(np.float32)
+  label = ((np.arange(n) // 3000) % 2).astype(np.float32).reshape(-1, 1)   # 0: speaker 1 attended
+  att = np.where(label > 0, env2[:n], env1[:n])
+  mix = rng.randn(post + 1, c).astype(np.float32)
+  eeg = np.zeros((n, c), np.float32)
+  for k in range(post + 1):          # EEG lags the attended envelope
+    eeg[k:] += att[:n - k] * mix[k]
+  eeg += 0.5 * rng.randn(n, c).astype(np.float32)
+  kw = dict(post_context=post, final_batch_size=200)
+  bd_fit = gpu_util.make_test_data(eeg, att.astype(np.float32), a=label, **kw)
+  ds_fit = bd_fit.create_dataset('train')
+  model = brain_model.BrainModelLinearRegression(ds_fit, regularization_lambda=0.1)
+  model.fit(ds_fit)
+  bd1 = gpu_util.make_test_data(eeg, env1[:n], a=label, **kw)
+  bd2 = gpu_util.make_test_data(eeg, env2[:n], a=label, **kw)
+  dec = infer_decoder.create_decoder('linear', reduction='first', model=model)
+  dec.train_statistics(bd1.create_dataset('train'), bd2.create_dataset('train'))
+  acc = infer.run_reduction_test(dec, bd1.create_dataset('test'), bd2.create_dataset('test'), 'wta')
+  assert all(acc[w] > 0.95 for w in WINDOWS if w >= 100), acc
+  assert acc[10] > 0.6
+  acc_step = infer.run_reduction_test(dec, bd1.create_dataset('test'), bd2.create_dataset('test'),
+                                      'stepped')
+  assert acc_step[1000] > 0.8
+  # oracle on the same predictions
+  pred = model.predict(bd1.create_dataset('test'))
+  cor = ora.Correlator()
+  for e in (env1[:n], env2[:n]):
+    for s in range(0, n, 200):
+      cor.add(e[s:s + 200], pred[s:s + 200])
+  assert np.allclose(np.float32(dec.correlation_params.mean_x), cor.mean_x, rtol=1e-4, atol=1e-6)
+  assert np.allclose(np.float32(dec.correlation_params.power), cor.power, rtol=1e-4)
+  res = dec.windowed_results(bd1.create_dataset('test'), [200])[200]
+  sig = ora.reduce_correlations(cor.correlate(env1[:n], pred), 'first')
+  want, want_lab = ora.windowed_means(sig, label, 200)
+  np.testing.assert_allclose(res[0], want, rtol=1e-3, atol=1e-5)
+  np.testing.assert_array_equal(res[1], want_lab)

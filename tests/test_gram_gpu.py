@@ -1,0 +1,155 @@
+"""GPU parity: the tcgen05 lagged Gram (both tile modes), the thin products, the forward and the
+row materialiser against the oracle; size-independent properties at larger shapes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_numpy as ora
+from telluride_decoding_b200 import ops
+from tests import gpu_util
+
+pytestmark = pytest.mark.gpu
+
+GRAM_TOL = 1e-5     # BASELINE.json north_star: relative Frobenius error of the Gram
+
+
+def _dataset(n, c, pre, post, batch, seed, c2=1, pre2=0, post2=0, offset=0, chunk=1000000, dy=1):
+  rng = np.random.RandomState(seed)
+  x = (rng.randn(n, c) + 0.2).astype(np.float32)
+  x2 = rng.randn(n, c2).astype(np.float32)
+  y = rng.randn(n, dy).astype(np.float32)
+  bd = gpu_util.make_test_data(x, y, x2, pre_context=pre, post_context=post, in2_pre_context=pre2,
+                               in2_post_context=post2, input_offset=offset,
+                               initial_batch_size=chunk, final_batch_size=batch)
+  ds = bd.create_dataset('train')
+  batches = gpu_util.oracle_batches(x, y, x2, None, pre, post, pre2, post2, offset, batch, chunk)
+  return ds, batches
+
+
+@pytest.mark.parametrize('cta_group', [1, 2])
+@pytest.mark.parametrize('n,c,pre,post,batch', [
+    (1000, 2, 1, 1, 100),       # C=2, L=3 (SURVEY build-plan shape)
+    (1000, 3, 1, 2, 100),       # golden ridge_small shape
+    (3000, 32, 16, 16, 500),    # C=32, L=33 (test/brain_model_test.py:728-776)
+    (7680, 64, 0, 31, 768),     # C=64, L=32 (config 2 shape, one trial)
+    (2501, 8, 0, 7, 300),       # rows lost to drop_remainder (tail mask)
+    (4100, 148, 3, 3, 1000),    # MEG fixture width, channel padding 148 -> 160
+])
+def test_gram_matches_oracle(n, c, pre, post, batch, cta_group):
+  ds, batches = _dataset(n, c, pre, post, batch, seed=n + c)
+  (w, keep), = ds.passes()
+  g = ops.lagged_gram([ds.stream('x')], keep,
+                      options=ops.gram_options(cta_group=cta_group)).cpu().numpy()
+  x64 = gpu_util.design64(batches)
+  want = x64.T @ x64
+  assert gpu_util.rel_fro(g, want) < GRAM_TOL
+  np.testing.assert_array_equal(g, g.T)            # exactly symmetric, like numpy's syrk path
+  # the reference's own float32 accumulation is no closer to float64 than we are x 30
+  ref32 = 0
+  for b in batches:
+    xb = np.asarray(b[0]['input_1'])
+    ref32 = ref32 + np.matmul(xb.T, xb)
+  assert gpu_util.rel_fro(g, ref32) < GRAM_TOL
+
+
+def test_simt_cross_check_agrees():
+  ds, batches = _dataset(2000, 20, 2, 2, 200, seed=5)
+  keep = ds.seg_rows
+  g0 = ops.lagged_gram([ds.stream('x')], keep).cpu().numpy()
+  g1 = ops.lagged_gram([ds.stream('x')], keep, options=ops.gram_options(method=1)).cpu().numpy()
+  x64 = gpu_util.design64(batches)
+  assert gpu_util.rel_fro(g1, x64.T @ x64) < 1e-6
+  assert gpu_util.rel_fro(g0, g1) < GRAM_TOL
+
+
+@pytest.mark.parametrize('offset,chunk', [(0, 1000000), (3, 1000000), (-2, 1000000), (0, 700), (2, 640)])
+def test_two_stream_gram_offsets_and_chunks(offset, chunk):
+  """Z = [X | Y] with different contexts, input_offset and chunk-edge zero padding
+  (brain_data.py:466-483, :492)."""
+  ds, batches = _dataset(2600, 12, 1, 3, 100, seed=9, c2=5, pre2=2, post2=1, offset=offset,
+                         chunk=chunk)
+  (w, keep), = ds.passes()
+  g = ops.lagged_gram([ds.stream('x'), ds.stream('x2')], keep).cpu().numpy()
+  z = np.concatenate([gpu_util.design64(batches), gpu_util.design64(batches, 'input_2')], axis=1)
+  assert g.shape == (z.shape[1], z.shape[1])
+  assert gpu_util.rel_fro(g, z.T @ z) < GRAM_TOL
+
+
+def test_thin_products_and_rows_and_predict():
+  ds, batches = _dataset(1500, 7, 2, 1, 250, seed=3, dy=3)
+  (w, keep), = ds.passes()
+  xtv, vtv = ops.lagged_thin(ds.stream('x'), ds.stream('y'), keep)
+  x64 = gpu_util.design64(batches)
+  y64 = np.concatenate([np.asarray(b[1], dtype=np.float64) for b in batches], axis=0)
+  v = np.concatenate([y64, np.ones((y64.shape[0], 1))], axis=1)
+  np.testing.assert_allclose(xtv.cpu().numpy(), x64.T @ v, rtol=1e-10, atol=1e-9)
+  np.testing.assert_allclose(vtv.cpu().numpy(), v.T @ v, rtol=1e-10, atol=1e-9)
+  assert vtv[-1, -1].item() == 1500
+  # the lagged rows are bit-identical to the reference's tf.signal.frame layout
+  got = [b for b in ds]
+  assert len(got) == len(batches) == 6
+  for (gd, gy), (od, oy) in zip(got, batches):
+    np.testing.assert_array_equal(gd['input_1'].cpu().numpy(), od['input_1'])
+    np.testing.assert_array_equal(gd['input_2'].cpu().numpy(), od['input_2'])
+    np.testing.assert_array_equal(gy.cpu().numpy(), oy)
+  # forward kernel = Dense on the lagged rows
+  rng = np.random.RandomState(1)
+  wmat = rng.randn(x64.shape[1], 3).astype(np.float32)
+  bias = rng.randn(3).astype(np.float32)
+  mean = rng.randn(x64.shape[1]).astype(np.float32)
+  out = ops.lagged_predict(ds.stream('x'), ds.seg_rows, ds.seg_out_rows(),
+                           torch.as_tensor(wmat, device='cuda'), torch.as_tensor(bias, device='cuda'),
+                           torch.as_tensor(mean, device='cuda'), total_rows=ds.total_rows)
+  want = (x64 - mean) @ wmat + bias
+  np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-4, atol=1e-4)
+
+
+def test_lag_goldens_through_the_kernel():
+  """test/brain_data_test.py:291-294, :317-320 via td_lagged_rows_f32."""
+  t = np.arange(40, dtype=np.float32)
+  x = np.stack([t, 1000 + t], axis=1)
+  y = (3000 + t).reshape(-1, 1)
+  for pre, post, want in ((2, 0, [[0, 0, 0, 0, 0, 1000], [0, 0, 0, 1000, 1, 1001],
+                                  [0, 1000, 1, 1001, 2, 1002]]),
+                          (0, 2, [[0, 1000, 1, 1001, 2, 1002], [1, 1001, 2, 1002, 3, 1003],
+                                  [2, 1002, 3, 1003, 4, 1004]])):
+    bd = gpu_util.make_test_data(x, y, pre_context=pre, post_context=post, final_batch_size=20)
+    (inputs, out), = bd.create_dataset('program_test').take(1)
+    np.testing.assert_array_equal(inputs['input_1'][:3].cpu().numpy(), want)
+    np.testing.assert_array_equal(out[:3, 0].cpu().numpy(), [3000, 3001, 3002])
+    assert bd.input_fields_width() == 6
+
+
+def test_segment_additivity_and_toeplitz_structure_at_scale():
+  """Properties that hold at any size: G(all trials) = sum of per-trial G, and every interior
+  lag block equals the channel autocorrelation at that lag."""
+  rng = np.random.RandomState(11)
+  c, post, n_trials, n = 64, 31, 6, 7680
+  x = rng.randn(n_trials * n, c).astype(np.float32)
+  xd = torch.as_tensor(x, device='cuda')
+  starts = [i * n for i in range(n_trials)]
+  lens = [n] * n_trials
+  full = ops.lagged_gram([ops.Stream(xd, 0, post, starts, lens)], lens).to(torch.float64)
+  parts = 0
+  for s in starts:
+    parts = parts + ops.lagged_gram([ops.Stream(xd, 0, post, [s], [n])], [n]).to(torch.float64)
+  assert gpu_util.rel_fro(full.cpu().numpy(), parts.cpu().numpy()) < 5e-6
+  # block (k, k') with k' - k = tau: sum over trials of x[u]' x[u + tau] for rows with both in range
+  x64 = x.astype(np.float64).reshape(n_trials, n, c)
+  k, tau = 5, 9
+  want = sum(x64[i, k:n - tau].T @ x64[i, k + tau:n] for i in range(n_trials))
+  blk = full[k * c:(k + 1) * c, (k + tau) * c:(k + tau + 1) * c].cpu().numpy()
+  assert gpu_util.rel_fro(blk, want) < 1e-4      # off-diagonal block: sqrt(T)-sized entries
+  diag = full[k * c:(k + 1) * c, k * c:(k + 1) * c].cpu().numpy()
+  want_d = sum(x64[i, k:n].T @ x64[i, k:n] for i in range(n_trials))
+  assert gpu_util.rel_fro(diag, want_d) < GRAM_TOL
+
+
+def test_argument_errors_surface_as_exceptions():
+  x = torch.zeros((100, 4), device='cuda')
+  from telluride_decoding_b200 import _lib
+  with pytest.raises(_lib.TdError, match='n_streams'):
+    s = ops.Stream(x, 0, 0, [0], [100])
+    ops.lagged_gram([s, s, s], [100])
+  with pytest.raises(ValueError, match='weights have'):
+    ops.lagged_predict(ops.Stream(x, 0, 1, [0], [100]), [100], [0], torch.zeros((3, 1), device='cuda'))

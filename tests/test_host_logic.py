@@ -1,0 +1,197 @@
+"""CPU: host-side logic of the package against the oracle / the reference's goldens --
+row plans (interleave, drop_remainder, chunks, offsets), stores, decoders, options."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_numpy as ora
+from telluride_decoding_b200 import attention_decoder
+from telluride_decoding_b200 import brain_data
+from telluride_decoding_b200 import decoding
+from telluride_decoding_b200 import infer
+from telluride_decoding_b200 import infer_decoder
+from telluride_decoding_b200 import regression
+from telluride_decoding_b200 import result_store
+
+
+@pytest.mark.parametrize('lengths,batch', [([3, 1, 2], 4), ([10, 10, 10], 7), ([5, 50, 20, 1], 16),
+                                           ([100], 33), ([7, 0, 9], 5)])
+def test_kept_prefix_matches_oracle_interleave(lengths, batch):
+  fi, _ = ora.interleave_order(lengths)
+  kept_total = (len(fi) // batch) * batch
+  want = [int(np.sum(fi[:kept_total] == f)) for f in range(len(lengths))]
+  assert brain_data.interleave_kept_prefix(lengths, kept_total) == want
+  f2, r2 = brain_data.interleave_order(lengths)
+  np.testing.assert_array_equal(f2, fi)
+  np.testing.assert_array_equal(r2, ora.interleave_order(lengths)[1])
+
+
+def _dataset(files_len, pre=0, post=0, pre2=0, post2=0, offset=0, chunk=1000000, batch=10,
+             mode='test', repeat=1, offset_counts=True):
+  n = sum(files_len)
+  x = torch.zeros((n, 3))
+  x2 = torch.zeros((n, 2))
+  y = torch.zeros((n, 1))
+  a = torch.zeros((n, 1))
+  files, cur = [], 0
+  for i, l in enumerate(files_len):
+    files.append(('f%d' % i, cur, l))
+    cur += l
+  return brain_data.LaggedDataset(x, x2, y, a, files, pre, post, pre2, post2, offset, chunk, batch,
+                                  repeat, 0, mode, offset_counts=offset_counts)
+
+
+def test_segments_chunks_and_offsets_follow_window_data():
+  ds = _dataset([25], pre=1, post=1, offset=2, chunk=10, batch=4)
+  # chunks of 10, 10, 5 frames; offset 2 drops 2 rows of x per chunk (brain_data.py:466-470)
+  assert ds.seg_rows == [8, 8, 3]
+  sx = ds.stream('x')
+  assert sx.seg_start == [2, 12, 22] and sx.seg_len == [8, 8, 3]
+  sy = ds.stream('y')
+  assert sy.seg_start == [0, 10, 20] and sy.seg_len == [10, 10, 5]
+  assert ds.total_rows == 19 and ds.num_batches == 4
+  assert ds.seg_keep_for_prefix(16) == [8, 8, 0]
+  ds = _dataset([25], pre=1, offset=-3, chunk=10, batch=4)
+  assert ds.seg_rows == [7, 7, 2]
+  assert ds.stream('y').seg_start == [3, 13, 23]
+  assert ds.stream('x').seg_start == [0, 10, 20] and ds.stream('x').seg_len == [10, 10, 5]
+  # no context at all: one segment per file, offset ignored for TFExampleData-like sources
+  ds = _dataset([25], offset=2, offset_counts=False)
+  assert ds.seg_rows == [25] and ds.input_offset == 0
+  assert ds.element_spec[0]['input_1'].shape[-1] == 3
+
+
+def test_passes_cover_repeat_and_remainder():
+  ds = _dataset([10, 4], batch=4, mode='train', repeat=3)      # 42 rows -> 10 batches = 40 rows
+  assert ds.num_batches == 10
+  (w1, k1), (w2, k2) = ds.passes()
+  assert w1 == 2.0 and k1 == [10, 4]
+  assert w2 == 1.0 and sum(k2) == 12
+  assert k2 == brain_data.interleave_kept_prefix([10, 4], 12)
+  ds = _dataset([10, 4], batch=7, mode='test', repeat=3)      # repeat only applies in train mode
+  assert ds.num_batches == 2 and ds.passes() == [(1.0, [10, 4])]
+
+
+def test_file_filters_allbut(monkeypatch):
+  monkeypatch.setattr(brain_data._lib, 'as_device_f32',
+                      lambda a, device=None: torch.as_tensor(np.asarray(a, dtype=np.float32)))
+  bd = brain_data.TrialBrainData('eeg', 'intensity', 100.0, final_batch_size=5,
+                                 shuffle_buffer_size=0)
+  for i in range(4):
+    bd.add_trial('trial_%02d' % i, np.zeros((20 + i, 2)), np.zeros((20 + i, 1)))
+  assert sorted(bd.all_files()) == ['trial_00', 'trial_01', 'trial_02', 'trial_03']
+  bd.set_file_patterns('allbut', 'trial_02', 'trial_02')
+  assert sorted(bd.filter_file_names('train')) == ['trial_00', 'trial_01', 'trial_03']
+  assert bd.filter_file_names('test') == ['trial_02']
+  ds = bd.create_dataset('train')
+  assert ds.total_rows == 20 + 21 + 23 and ds.num_batches == 12
+  bd.set_file_patterns('allbut', '', 'trial_02')
+  with pytest.raises(ValueError, match='Both test and validate must be specified'):
+    bd.filter_file_names('train')
+  with pytest.raises(ValueError, match='mode must be one of'):
+    bd.filter_file_names('bogus')
+  assert bd.input_fields_width() == 2 and bd.output_field_width() == 1
+
+
+def test_brain_data_argument_errors():
+  with pytest.raises(ValueError, match='pre_context must be >= 0'):
+    brain_data.TestBrainData('in', 'out', 100.0, pre_context=-1)
+  with pytest.raises(ValueError, match='Must specify at least one input field'):
+    brain_data.TestBrainData('', 'out', 100.0)
+  with pytest.raises(ValueError, match='Must call preserve_test_data'):
+    brain_data.TestBrainData('in', 'out', 100.0).create_dataset('train')
+  with pytest.raises(TypeError, match='unknown data type'):
+    brain_data.create_brain_dataset('nope', 'in', 'out', 100.0)
+  with pytest.raises(ValueError, match='frame_rate must be greater than 0'):
+    brain_data.create_brain_dataset('test', 'in', 'out', 0)
+
+
+def test_result_store_windows_match_reference(golden_dir):
+  g = np.load(os.path.join(golden_dir, 'decoder.npz'))
+  store = result_store.TwoResultStore(window_width=201, window_step=100)
+  sig = np.arange(1000, dtype=np.float64).reshape(-1, 1)
+  got = []
+  for s in range(0, 1000, 130):
+    store.add_data(sig[s:s + 130], sig[s:s + 130] + 0.5)
+    for p1, p2 in store.next_window():
+      got.append((p1[0, 0], p1[-1, 0], p2[0, 0], p1.shape[0]))
+  np.testing.assert_array_equal(np.asarray(got), g['store_201_100'])
+  np.testing.assert_array_equal(result_store.window_starts(1000, 201, 100), np.arange(8) * 100)
+  # pre_context primes store 1 with zeros (test/result_store_test.py:112-147)
+  ws = result_store.WindowedDataStore(window_step=2, window_width=4, pre_context=2)
+  ws.add_data(np.arange(1, 9, dtype=float).reshape(-1, 1))
+  wins = [w[:, 0].tolist() for w in ws.next_window()]
+  assert wins == [[0, 0, 1, 2], [1, 2, 3, 4], [3, 4, 5, 6], [5, 6, 7, 8]]
+  ns = result_store.NumpyStore(init_frame_count=4)
+  for i in range(5):
+    ns.add_data(np.full((3, 2), i, dtype=float))
+  assert ns.count == 15 and ns.all_data.shape == (15, 2) and ns.all_data[-1, 0] == 4
+  first = next(ns.next_window(6))
+  assert first.shape == (6, 2) and ns.count == 9
+  with pytest.raises(ValueError, match='window_step'):
+    result_store.WindowedDataStore(window_step=5, window_width=4)
+
+
+def test_streaming_decoder_matches_reference(golden_dir):
+  g = np.load(os.path.join(golden_dir, 'decoder.npz'))
+  truth, pred, batch = g['truth'], g['pred'], int(g['batch'])
+
+  class Dec(infer_decoder.Decoder):
+    def decode_one(self, input_dict, ground_truth):
+      return ground_truth, input_dict['pred']
+
+  dec = Dec(lambda d: None, reduction='mean-squared')
+  for s in range(0, truth.shape[0], batch):
+    dec.add_data_correlator(truth[s:s + batch], pred[s:s + batch])
+  np.testing.assert_array_equal(dec.correlation_params.power, g['s1_power'])
+  np.testing.assert_array_equal(dec.compute_correlation(truth, pred), g['s1_corr'])
+  batches = [({'pred': pred[s:s + batch], 'attended_speaker': g['label'][s:s + batch]},
+              truth[s:s + batch]) for s in range(0, truth.shape[0], batch)]
+  res = [np.mean(r) for r, _ in dec.test_by_window(batches, 200)]
+  np.testing.assert_allclose(res, g['s1_mean-squared_w200_res'], rtol=0, atol=1e-15)
+  with pytest.raises(ValueError, match='Unknown reduction technique'):
+    infer_decoder.Decoder(reduction='bogus')
+  with pytest.raises(TypeError, match='callable model'):
+    infer_decoder.Decoder(decoding_model=3)
+  np.testing.assert_array_equal(
+      infer_decoder.average_data(np.arange(12, dtype=float).reshape(6, 2), 2),
+      [[1, 2], [5, 6], [9, 10]])
+  assert abs(infer_decoder.calculate_dprime(g['s2_corr'][:, 0], g['s1_corr'][:, 0]) -
+             float(g['dprime'])) < 1e-12
+
+
+def test_attention_decoders_reference_sequences():
+  cor2 = [1] * 13
+  cor1 = [2] * 7 + [0] * 6
+  ad = attention_decoder.create_attention_decoder('wta')
+  assert [ad.attention(a, b)[0] for a, b in zip(cor1, cor2)] == [True] * 7 + [False] * 6
+  sd = attention_decoder.create_attention_decoder('stepped')
+  assert [sd.attention(a, b)[0] for a, b in zip(cor1, cor2)] == [True] * 11 + [False] * 2
+  np.testing.assert_array_equal(attention_decoder.step_decisions([True] * 2 + [False] * 11),
+                                [True] * 3 + [False] * 10)
+  with pytest.raises(ValueError, match='Unknown type'):
+    attention_decoder.create_attention_decoder('bogus')
+  assert infer.find_first_segment(np.array([0, 0, 0, 1, 1, 0])) == 3
+  assert infer.find_first_segment(np.array([1, 1, 1])) == 0
+
+
+def test_regularization_parsing_and_options():
+  np.testing.assert_allclose(regression.parse_regularization_values('normal'),
+                             10.0 ** np.arange(-6, 1))
+  np.testing.assert_allclose(regression.parse_regularization_values('0.1,1,10'), [0.1, 1, 10])
+  assert regression.parse_regularization_values(0.5) == [0.5]
+  with pytest.raises(TypeError):
+    regression.parse_regularization_values(3)
+  opts = decoding.DecodingOptions()
+  assert opts.batch_size == 512 and opts.test_metric == 'pearson_correlation_first'
+  r = regression.RegressionLinear(opts)
+  assert r.preset_flags() == 'linear'
+  assert opts.post_context == 20 and opts.batch_size == 100 and opts.shuffle_buffer_size == 0
+  r = regression.RegressionCCA(decoding.DecodingOptions())
+  r.preset_flags()
+  assert (r.my_flags.post_context, r.my_flags.input2_pre_context, r.my_flags.cca_dimensions) == (21, 15, 5)
+  assert 'batch_size=100' in opts.experiment_parameters()
+  with pytest.raises(TypeError, match='DecodingOptions'):
+    decoding.create_brain_model({}, None)

@@ -1,0 +1,249 @@
+"""GPU parity of the model API (fit / evaluate / predict, lambda sweep, CCA) against the fixtures
+written by the unmodified reference and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_numpy as ora
+from telluride_decoding_b200 import brain_model
+from telluride_decoding_b200 import cca
+from telluride_decoding_b200 import decoding
+from tests import gpu_util
+
+pytestmark = pytest.mark.gpu
+
+W_TOL = 1e-4     # BASELINE.json north_star: decoder weights and correlations
+
+
+def _golden(golden_dir, name):
+  return np.load(os.path.join(golden_dir, name + '.npz'))
+
+
+@pytest.mark.parametrize('name', ['ridge_small', 'ridge_c8l8'])
+def test_ridge_matches_reference_fixture(golden_dir, name):
+  g = _golden(golden_dir, name)
+  bd = gpu_util.make_test_data(g['x'], g['y'], pre_context=int(g['pre']),
+                               post_context=int(g['post']), final_batch_size=int(g['batch']))
+  ds = bd.create_dataset('train')
+  for tag, lamb, use_offset, use_ridge in (('ridge0', 0.0, True, True), ('ridge1em2', 1e-2, True, True),
+                                           ('ridge10', 10.0, True, True), ('nooffset', 0.1, False, True),
+                                           ('shrink03', 0.3, True, False)):
+    w, b, cov_x, cov_xy, shrink = brain_model.calculate_linear_regressor_parameters_from_dataset(
+        ds, lamb=lamb, use_offset=use_offset, use_ridge=use_ridge)
+    assert gpu_util.rel_fro(w, g[tag + '_w']) < W_TOL, tag
+    assert gpu_util.rel_fro(cov_x, g[tag + '_cov_x']) < 1e-5, tag
+    assert gpu_util.rel_fro(cov_xy, g[tag + '_cov_xy']) < 1e-5, tag
+    if use_offset:
+      assert np.allclose(b, g[tag + '_b'], rtol=W_TOL, atol=W_TOL * np.abs(g[tag + '_b']).max()), tag
+      assert b.shape == (1, g['y'].shape[1])
+    else:
+      assert b.shape == (1,) and b[0] == 0
+    assert float(shrink) == float(g[tag + '_shrinkage'])
+    assert w.dtype == np.float32
+  with pytest.raises(ValueError, match='Regularization lambda must be between 0 and 1'):
+    brain_model.calculate_linear_regressor_parameters_from_dataset(ds, lamb=2, use_ridge=False)
+  with pytest.raises(TypeError, match='must be a tf.data.Dataset object'):
+    brain_model.calculate_linear_regressor_parameters_from_dataset([1, 2, 3])
+
+
+def test_linear_model_recovers_known_weights_like_reference_test():
+  """test/brain_model_test.py:852-911: y = xW + b exactly -> W, b to 1e-5, eval MSE < 1e-5."""
+  rng = np.random.RandomState(0)
+  x = rng.randn(1000, 2).astype(np.float32)
+  wt = np.array([[1, 3], [2, 4]], np.float32)
+  bt = np.array([5, 6], np.float32)
+  y = x @ wt + bt
+  bd = gpu_util.make_test_data(x, y, final_batch_size=100)
+  ds = bd.create_dataset('train')
+  model = brain_model.BrainModelLinearRegression(ds, regularization_lambda=0.0)
+  assert model.fit(ds) == {}
+  np.testing.assert_allclose(model.w_estimate, wt, atol=1e-5)
+  np.testing.assert_allclose(model.b_estimate, bt, atol=1e-5)
+  w, b = model.weight_matrices
+  assert w.shape == (2, 2) and b.shape == (2,)
+  res = model.evaluate(bd.create_dataset('test'))
+  assert set(res) == {'loss', 'pearson_correlation_first'}
+  assert res['loss'] < 1e-5 and res['pearson_correlation_first'] > 0.9999
+  pred = model.predict({'input_1': x[:7]})
+  np.testing.assert_allclose(pred, y[:7], rtol=1e-5)
+  with pytest.raises(TypeError, match='must be called with'):
+    model.fit([1, 2])
+  with pytest.raises(ValueError, match='Y value not needed'):
+    model.fit(ds, y=3)
+  with pytest.raises(TypeError, match='must be called with tf.data.Dataset'):
+    model.evaluate({'input_1': x})
+
+
+def test_trf_simulation_32ch_33lags():
+  """test/brain_model_test.py:728-776 in spirit: 32 channels x 33 lags, r > 0.99 and weights
+  equal to the oracle's."""
+  rng = np.random.RandomState(4)
+  n, c, pre, post = 6000, 32, 16, 16
+  x = rng.randn(n, c).astype(np.float32)
+  w_true = (rng.randn((pre + 1 + post) * c, 1) / 8).astype(np.float32)
+  y = (ora.add_context(x, pre, post) @ w_true + 0.05 * rng.randn(n, 1)).astype(np.float32)
+  bd = gpu_util.make_test_data(x, y, pre_context=pre, post_context=post, final_batch_size=500)
+  ds = bd.create_dataset('train')
+  model = brain_model.BrainModelLinearRegression(ds, regularization_lambda=1e-3)
+  model.fit(ds)
+  batches = gpu_util.oracle_batches(x, y, pre=pre, post=post, batch=500)
+  w, b, _, _, _ = ora.linear_regressor_from_batches(batches, 1e-3)
+  assert gpu_util.rel_fro(model.w_estimate, w) < W_TOL
+  got = model.evaluate(bd.create_dataset('test'))
+  want = ora.evaluate_linear(batches, w, b)
+  assert got['pearson_correlation_first'] > 0.99
+  assert abs(got['pearson_correlation_first'] - want['pearson_correlation_first']) < W_TOL
+  assert abs(got['loss'] - want['loss']) < W_TOL * want['loss'] + 1e-7
+  # predictions over the dataset come back in stream order
+  pred = model.predict(bd.create_dataset('test'))
+  ref = np.concatenate([np.asarray(bb[0]['input_1']) @ w + b for bb in batches], axis=0)
+  np.testing.assert_allclose(pred, ref, rtol=1e-3, atol=1e-4)
+
+
+def test_lambda_sweep_one_factorisation_equals_per_lambda_solves():
+  rng = np.random.RandomState(8)
+  n, c, post = 5000, 16, 7
+  x = rng.randn(n, c).astype(np.float32)
+  x[:, 1] = x[:, 0] + 0.01 * x[:, 1]        # ill-conditioned pair of channels
+  y = (x[:, :1] * 0.5 + rng.randn(n, 1)).astype(np.float32)
+  bd = gpu_util.make_test_data(x, y, post_context=post, final_batch_size=500)
+  ds = bd.create_dataset('train')
+  stats = brain_model.RegressionStats.from_dataset(ds)
+  lambdas = np.logspace(-6, 3, 20)
+  chol = brain_model.solve_regression(stats, lambdas, method=0)
+  eigh = brain_model.solve_regression(stats, lambdas, method=1)
+  batches = gpu_util.oracle_batches(x, y, post=post, batch=500)
+  for lam, (w0, b0), (w1, b1) in zip(lambdas, chol, eigh):
+    assert gpu_util.rel_fro(w1.cpu().numpy(), w0.cpu().numpy()) < 1e-5
+    if lam >= 1e-3:      # the reference's own float32 LU is only trustworthy when conditioned
+      w, b, _, _, _ = ora.linear_regressor_from_batches(batches, float(lam))
+      assert gpu_util.rel_fro(w0.cpu().numpy(), w) < W_TOL, lam
+      assert abs(float(b0[0]) - float(b[0, 0])) < W_TOL
+
+
+def test_multi_trial_interleaved_fit_and_evaluate():
+  """Three trials of unequal length: kept rows are a per-trial prefix of the round-robin stream
+  and evaluate's batches mix trials (brain_data.py:725-728)."""
+  from telluride_decoding_b200 import brain_data
+  rng = np.random.RandomState(12)
+  lens = [1300, 900, 1111]
+  bd = brain_data.TrialBrainData('eeg', 'intensity', 100.0, pre_context=2, post_context=3,
+                                 final_batch_size=200, shuffle_buffer_size=0)
+  files = []
+  wt = rng.randn(6 * 5, 1).astype(np.float32)
+  for i, n in enumerate(lens):
+    x = rng.randn(n, 5).astype(np.float32)
+    y = (ora.add_context(x, 2, 3) @ wt + 0.2 * rng.randn(n, 1)).astype(np.float32)
+    bd.add_trial('t%d' % i, x, y)
+    z = np.zeros((n, 1), np.float32)
+    files.append(ora.file_rows(x, z, y, z, 2, 3))
+  ds = bd.create_dataset('train')
+  assert ds.num_batches == sum(lens) // 200
+  model = brain_model.BrainModelLinearRegression(ds, regularization_lambda=0.1)
+  model.fit(ds)
+  batches = ora.batches_from_files(files, 200)
+  w, b, _, _, _ = ora.linear_regressor_from_batches(batches, 0.1)
+  assert gpu_util.rel_fro(model.w_estimate, w) < W_TOL
+  got = model.evaluate(bd.create_dataset('test'))
+  want = ora.evaluate_linear(batches, w, b)
+  assert abs(got['pearson_correlation_first'] - want['pearson_correlation_first']) < W_TOL
+  # iteration reproduces the interleaved minibatches bit for bit
+  for (gd, gy), (od, oy) in zip(bd.create_dataset('program_test'), batches):
+    np.testing.assert_array_equal(gd['input_1'].cpu().numpy(), od['input_1'])
+    np.testing.assert_array_equal(gy.cpu().numpy(), oy)
+
+
+def _cca_compare(rot_x, rot_y, e, g):
+  # joint sign per component is arbitrary in the reference (SVD); align before comparing
+  for i in range(rot_x.shape[1]):
+    s = np.sign(np.sum(rot_x[:, i] * g['rot_x'][:, i]))
+    assert s != 0
+    assert gpu_util.rel_fro(s * rot_x[:, i], g['rot_x'][:, i]) < 2e-4, i
+    assert gpu_util.rel_fro(s * rot_y[:, i], g['rot_y'][:, i]) < 2e-4, i
+  np.testing.assert_allclose(e, g['e'], rtol=W_TOL)
+
+
+def test_cca_matches_reference_fixture(golden_dir):
+  g = _golden(golden_dir, 'cca_small')
+  n = g['x'].shape[0]
+  bd = gpu_util.make_test_data(g['x'], np.ones((n, 1), np.float32), g['x2'],
+                               post_context=int(g['post1']), in2_post_context=int(g['post2']),
+                               final_batch_size=int(g['batch']))
+  ds = bd.create_dataset('train')
+  rot_x, rot_y, mean_x, mean_y, e = cca.calculate_cca_parameters_from_dataset(
+      ds, int(g['dim']), regularization=float(g['reg']), mini_batch_count=0)
+  _cca_compare(rot_x, rot_y, e, g)
+  np.testing.assert_allclose(mean_x, g['mean_x'], atol=1e-6)
+  np.testing.assert_allclose(mean_y, g['mean_y'], atol=1e-6)
+  assert rot_x.dtype == np.float32 and mean_x.shape == (1, rot_x.shape[0])
+  # model API + evaluate against the oracle forward / per-batch Pearson
+  model = cca.BrainModelCCA(ds, cca_dims=int(g['dim']), regularization_lambda=float(g['reg']))
+  assert model.fit(ds) == {}
+  res = model.evaluate(bd.create_dataset('test'))
+  batches = gpu_util.oracle_batches(g['x'], np.ones((n, 1), np.float32), g['x2'], None, 0,
+                                    int(g['post1']), 0, int(g['post2']), 0, int(g['batch']))
+  want = ora.evaluate_cca(batches, g['mean_x'], g['mean_y'], g['rot_x'], g['rot_y'])
+  assert set(res) == {'loss', 'cca_pearson_correlation_first'}
+  assert abs(res['cca_pearson_correlation_first'] - want['cca_pearson_correlation_first']) < W_TOL
+  assert res['loss'] == res['cca_pearson_correlation_first']
+  out = model.predict({'input_1': batches[0][0]['input_1'], 'input_2': batches[0][0]['input_2']})
+  assert out.shape == (int(g['batch']), 2 * int(g['dim']))
+  with pytest.raises(ValueError, match='regularization lambda must be >= 0'):
+    cca.calculate_cca_parameters_from_dataset(ds, 3, regularization=-1)
+  with pytest.raises(TypeError, match='must be a tf.data.Dataset object'):
+    cca.calculate_cca_parameters_from_dataset([1], 3)
+
+
+def test_cca_seed42_structure_like_reference_test(golden_dir):
+  """test/cca_test.py:80-123 construction: eigenvalue pattern and the reference's own output."""
+  g = _golden(golden_dir, 'cca_seed42')
+  bd = gpu_util.make_test_data(g['x'], np.ones((g['x'].shape[0], 1), np.float32), g['y'],
+                               final_batch_size=100)
+  ds = bd.create_dataset('train')
+  rot_x, rot_y, _, _, e = cca.calculate_cca_parameters_from_dataset(ds, 3, regularization=0.1,
+                                                                     mini_batch_count=0)
+  assert e[0] > 0.9 and e[1] > 0.6 and e[2] < 0.1
+  np.testing.assert_allclose(e, g['e'], rtol=W_TOL)
+  # mini_batch_count limits the statistics to the first batches of the stream (cca.py:311)
+  first5 = cca.calculate_cca_parameters_from_dataset(ds, 3, 0.1, mini_batch_count=5)
+  batches = [({'input_1': g['x'][i:i + 100], 'input_2': g['y'][i:i + 100]}, None)
+             for i in range(0, 2000, 100)]
+  want = ora.cca_from_batches(batches, 3, 0.1, mini_batch_count=5)
+  np.testing.assert_allclose(first5[4], want[4], rtol=W_TOL)
+
+
+def test_cca_width_errors_like_reference_test():
+  """test/cca_test.py:199-220."""
+  x = np.random.randn(200, 1).astype(np.float32)
+  bd = gpu_util.make_test_data(x, x, x, final_batch_size=50)
+  with pytest.raises(ValueError, match=r'Input 1 feature width \(1\) should not be <= 1'):
+    cca.BrainModelCCA(bd.create_dataset('train'))
+
+
+def test_create_brain_model_and_train_and_test():
+  rng = np.random.RandomState(2)
+  x = rng.randn(2000, 4).astype(np.float32)
+  y = (x[:, :1] + 0.1 * rng.randn(2000, 1)).astype(np.float32)
+  bd = gpu_util.make_test_data(x, y, post_context=2, final_batch_size=100)
+  opts = decoding.DecodingOptions(dnn_regressor='linear', regularization_lambda=0.01)
+  model = decoding.create_brain_model(opts, bd.create_dataset('train'))
+  train_res, test_res = decoding.train_and_test(opts, bd, model)
+  assert train_res == {} and test_res['pearson_correlation_first'] > 0.99
+  with pytest.raises(TypeError, match='outside the B200 dense decoding path'):
+    decoding.create_brain_model(decoding.DecodingOptions(), bd.create_dataset('train'))
+
+
+def test_pearson_known_answer():
+  """test/brain_model_test.py:1046-1082."""
+  d = np.array([[1, 43, 99], [2, 21, 65], [3, 25, 79], [4, 42, 75], [5, 57, 87], [6, 59, 81]],
+               dtype=np.float32)
+  r = brain_model.pearson_correlation(torch.as_tensor(d[:, 1:2], device='cuda'),
+                                      torch.as_tensor(d[:, 2:3], device='cuda'))
+  assert abs(float(r[0]) - 0.5298) < 1e-4
+  assert abs(float(brain_model.pearson_correlation_first(d[:, 1:2], d[:, 2:3])) - 0.5298) < 1e-4
+  x = np.random.random((6, 2))
+  y = np.random.random((6, 2))
+  npcor = np.diag(np.corrcoef(x, y, rowvar=False)[:2, 2:])
+  np.testing.assert_allclose(brain_model.pearson_correlation(x, y).numpy(), npcor, atol=2e-7)
