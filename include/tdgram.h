@@ -76,19 +76,26 @@ int td_device_info(int* sm_count, int* cc_major, int* cc_minor);
 typedef struct td_gram_options {
   int32_t method;        /* 0 = tcgen05 3xTF32 (default), 1 = fp32 SIMT cross-check */
   int32_t cta_group;     /* 0 = auto, 1 = 128x128 tiles per CTA, 2 = CTA-pair 256x256 tiles */
-  int32_t chunk_rows;    /* TMEM flush period in frames (0 = default 512) */
+  int32_t chunk_rows;    /* TMEM flush period in frames (0 = default 128) */
   int32_t superchunk_rows; /* L2 working-set period in frames (0 = auto) */
   int32_t max_ctas;      /* 0 = all SMs */
-  int32_t reserved[3];
+  int32_t reserved[3];   /* reserved[0] = 1: record CUDA events around the Gram kernel */
 } td_gram_options;
 
 int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_streams,
-                                   const int64_t* seg_keep, int n_seg,
+                                   const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
                                    const td_gram_options* opt, size_t* bytes);
+/* Design rows [seg_first[s], seg_keep[s]) of every segment are accumulated (seg_first NULL = 0):
+ * a prefix for drop_remainder, a sub-range when a trial's frames are shared between GPUs (the
+ * lag halo is read from the neighbouring frames of the same segment, not zero padded). */
 int td_lagged_gram_f32(const td_stream* streams, int n_streams,
-                       const int64_t* seg_keep, int n_seg,
+                       const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
                        float* G_dev, int64_t ldg, const td_gram_options* opt,
                        void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
+/* Device time (ms) of the most recent tcgen05 Gram kernel launched by this thread with
+ * opt->reserved[0] = 1 (CUDA events on the caller's stream; synchronises on the stop event).
+ * Negative if none was recorded.  For the bench's roofline line. */
+float td_last_gram_kernel_ms(void);
 
 /* ---------------------------------------------------------------------------------------
  * Thin products against the un-lagged targets and the ones column.  Replaces

@@ -14,6 +14,19 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
 }
+
+int ensure_mempool_config() {
+  static bool done[64] = {false};
+  int dev = 0;
+  TD_CHECK_CUDA(cudaGetDevice(&dev));
+  if (done[dev & 63]) return TD_OK;
+  cudaMemPool_t pool;
+  TD_CHECK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t threshold = UINT64_MAX;
+  TD_CHECK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  done[dev & 63] = true;
+  return TD_OK;
+}
 }  // namespace td
 
 extern "C" const char* td_last_error(void) { return td::g_error; }

@@ -41,11 +41,17 @@ int check_stream(const td_stream* s, const int64_t* seg_keep, int n_seg, const c
 inline int lags_of(const td_stream& s) { return s.pre + 1 + s.post; }
 inline int64_t width_of(const td_stream& s) { return (int64_t)s.channels * lags_of(s); }
 
+// Keep stream-ordered allocations cached in the device's default pool (the default release
+// threshold of 0 hands the memory back to the driver at every synchronisation).
+int ensure_mempool_config();
+
 // Small host->device table upload into stream-ordered memory (freed with cudaFreeAsync).
 template <typename T>
 int upload(const std::vector<T>& host, T** dev, cudaStream_t st) {
   size_t bytes = host.size() * sizeof(T);
   if (bytes == 0) bytes = sizeof(T);
+  int rc = ensure_mempool_config();
+  if (rc) return rc;
   TD_CHECK_CUDA(cudaMallocAsync((void**)dev, bytes, st));
   if (!host.empty())
     TD_CHECK_CUDA(cudaMemcpyAsync(*dev, host.data(), host.size() * sizeof(T),

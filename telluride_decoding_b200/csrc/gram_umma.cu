@@ -51,7 +51,7 @@ static_assert(8 * (3 * STAGES + 4) + 8 <= 256, "barrier block too small");
 
 struct GramParams {
   const int4* groups;     // [n_groups_pad] {stream, aligned time shift, first channel, shift plane}
-  const int2* ktiles;     // [NK] {staged time of design row 0 of the tile, valid rows}
+  const int2* ktiles;     // [NK] {staged time of design row 0 of the tile, begin | end << 8}: rows [begin, end) exist
   const int* out_idx;     // [Dpad] tile-space row -> row/col of G, -1 for padding
   float* G;
   long long ldg;
@@ -69,22 +69,35 @@ struct WorkItem {
   long long kt_begin, kt_end;
 };
 
-// Linearised (superchunk, tile, k-tile) space; identical decode in every warp role.
+// Work = (superchunk, lower-triangle tile, k-tile).  All workers sweep the SAME superchunk at the
+// same time (its staged frames stay L2 resident while every tile consumes them): inside superchunk
+// sc the ntri * KS k-tile steps are split evenly over the workers (stream-K), then everyone moves
+// on to sc + 1.  Identical decode in every warp role.
 struct WorkIter {
-  long long p, hi;
-  __device__ WorkIter(const GramParams& P, int worker, int n_workers) {
-    p = P.total_steps * worker / n_workers;
-    hi = P.total_steps * (worker + 1) / n_workers;
+  long long sc, nsc, per_sc, p, hi;
+  int worker, n_workers;
+  __device__ WorkIter(const GramParams& P, int worker_, int n_workers_) {
+    worker = worker_;
+    n_workers = n_workers_;
+    per_sc = (long long)P.ntri * P.KS;
+    nsc = P.total_steps / per_sc;
+    sc = -1;
+    p = hi = 0;
   }
   __device__ bool next(const GramParams& P, WorkItem& it) {
-    while (p < hi) {
-      long long item = p / P.KS;
-      int kt0 = (int)(p - item * P.KS);
-      long long sc = item / P.ntri;
-      int tile = (int)(item - sc * P.ntri);
-      long long len = min((long long)(P.KS - kt0), hi - p);
-      long long b = sc * P.KS + kt0;
-      long long e = min(b + len, P.NK);
+    for (;;) {
+      if (p >= hi) {
+        if (++sc >= nsc) return false;
+        const int w = (int)((worker + sc) % n_workers);     // rotate who gets the ragged pieces
+        p = per_sc * w / n_workers;
+        hi = per_sc * (w + 1) / n_workers;
+        continue;
+      }
+      const int tile = (int)(p / P.KS);
+      const int kt0 = (int)(p - (long long)tile * P.KS);
+      const long long len = min((long long)(P.KS - kt0), hi - p);
+      const long long b = sc * P.KS + kt0;
+      const long long e = min(b + len, P.NK);
       p += len;
       if (b < e) {
         int tm = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
@@ -97,16 +110,16 @@ struct WorkIter {
         return true;
       }
     }
-    return false;
   }
 };
 
-// Zero frames [valid, BK) of every row of the four operand tiles of one stage (K-major, 128-byte
-// swizzle: element t of row r sits in 16-byte chunk (t/4) ^ (r%8)).  Executed by one warp.
-__device__ __forceinline__ void zero_tail_frames(uint32_t sbase, int valid, int lane) {
+// Zero the frames outside [begin, end) of every row of the four operand tiles of one stage
+// (K-major, 128-byte swizzle: element t of row r sits in 16-byte chunk (t/4) ^ (r%8)).  One warp.
+__device__ __forceinline__ void zero_outside_frames(uint32_t sbase, int begin, int end, int lane) {
   for (int r = lane; r < 4 * TILE_ROWS; r += 32) {
     const uint32_t rowaddr = sbase + r * (BK * 4);
-    for (int t = valid; t < BK; ++t) {
+    for (int t = 0; t < BK; ++t) {
+      if (t >= begin && t < end) continue;
       const uint32_t a = rowaddr + ((((uint32_t)t >> 2) ^ ((uint32_t)r & 7u)) << 4) +
                          (((uint32_t)t & 3u) << 2);
       asm volatile("st.shared::cta.b32 [%0], %1;" ::"r"(a), "r"(0u) : "memory");
@@ -218,12 +231,14 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
           ptx::tc_fence_after();
         }
         for (long long kt = c0; kt < c1; ++kt) {
-          const int valid = __ldg(&P.ktiles[kt]).y;
+          const int range = __ldg(&P.ktiles[kt]).y;
+          const int begin = range & 0xff, end = range >> 8;
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           ptx::mbar_wait(full_bar(stage), phase);
-          // Rows >= valid of a segment's last k-tile are not design rows (end of trial, or rows
-          // lost to drop_remainder, brain_data.py:369-370): zero them in both operands.
-          if (valid < BK) zero_tail_frames(sbase, valid, lane);
+          // Frames outside [begin, end) of a k-tile are not design rows of this call (end of
+          // trial, rows lost to drop_remainder, brain_data.py:369-370, or another rank's share
+          // of the trial): zero them in both operands.
+          if (begin > 0 || end < BK) zero_outside_frames(sbase, begin, end, lane);
           if constexpr (CG == 2) {
             if (!issuer) {
               if (lane == 0) ptx::mbar_arrive_cluster(pready_leader0 + 8u * stage);
@@ -234,15 +249,15 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
           if (issuer) {
             ptx::tc_fence_after();
             if (lane == 0) {
-              const int ksteps = (valid + 7) >> 3;
+              const int ks0 = begin >> 3, ks1 = (end + 7) >> 3;
               const uint32_t d = tmem_base + (uint32_t)(buf * BN);
               const uint64_t a_hi = ptx::umma_desc_k_sw128(sbase);
               const uint64_t a_lo = ptx::umma_desc_k_sw128(sbase + OPERAND_BYTES);
               const uint64_t b_hi = ptx::umma_desc_k_sw128(sbase + 2 * OPERAND_BYTES);
               const uint64_t b_lo = ptx::umma_desc_k_sw128(sbase + 3 * OPERAND_BYTES);
-              for (int ks = 0; ks < ksteps; ++ks) {
+              for (int ks = ks0; ks < ks1; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);   // 8 frames = 32 B = 2 x 16 B
-                const uint32_t acc = (kt > c0 || ks > 0) ? 1u : 0u;
+                const uint32_t acc = (kt > c0 || ks > ks0) ? 1u : 0u;
                 ptx::mma_tf32<CG>(d, a_hi + adv, b_hi + adv, IDESC, acc);
                 ptx::mma_tf32<CG>(d, a_hi + adv, b_lo + adv, IDESC, 1u);
                 ptx::mma_tf32<CG>(d, a_lo + adv, b_hi + adv, IDESC, 1u);
@@ -398,8 +413,10 @@ int pick_cb(int channels_min_max) {
   return 8;
 }
 
-int make_plan(const td_stream* streams, int n_streams, const int64_t* seg_keep, int n_seg,
-              const td_gram_options* opt, GramPlan* pl) {
+inline int64_t first_of(const int64_t* seg_first, int s) { return seg_first ? seg_first[s] : 0; }
+
+int make_plan(const td_stream* streams, int n_streams, const int64_t* seg_first,
+              const int64_t* seg_keep, int n_seg, const td_gram_options* opt, GramPlan* pl) {
   TD_REQUIRE(n_streams == 1 || n_streams == 2, "td_lagged_gram: n_streams must be 1 or 2, not %d",
              n_streams);
   TD_REQUIRE(n_seg > 0, "td_lagged_gram: no segments");
@@ -450,7 +467,9 @@ int make_plan(const td_stream* streams, int n_streams, const int64_t* seg_keep, 
     int64_t len = 0;
     for (int q = 0; q < n_streams; ++q) len = std::max(len, streams[q].seg_len[s]);
     cur = round_up(cur + len + halo, 32);
-    nk += ceil_div(seg_keep[s], BK);
+    const int64_t f = first_of(seg_first, s);
+    TD_REQUIRE(f >= 0, "td_lagged_gram: negative first row at segment %d", s);
+    if (seg_keep[s] > f) nk += ceil_div(seg_keep[s], BK) - f / BK;
   }
   pl->Tp = round_up(cur + BK + halo, 32);
   pl->NK = nk;
@@ -485,6 +504,9 @@ int debug_sync(cudaStream_t st, const char* what) {
   if (e != cudaSuccess) { set_error("%s failed: %s", what, cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }
+
+thread_local cudaEvent_t g_ev_start = nullptr, g_ev_stop = nullptr;
+thread_local bool g_ev_valid = false;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -532,15 +554,23 @@ int make_tmap(CUtensorMap* m, float* planes, int64_t Tp, int Cpad, int CB, int n
 using namespace td;
 
 extern "C" int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_streams,
-                                              const int64_t* seg_keep, int n_seg,
-                                              const td_gram_options* opt, size_t* bytes) {
+                                              const int64_t* seg_first, const int64_t* seg_keep,
+                                              int n_seg, const td_gram_options* opt, size_t* bytes) {
   TD_REQUIRE(streams && seg_keep && bytes, "td_lagged_gram_workspace_bytes: null argument");
   if (opt && opt->method == 1) { *bytes = 0; return TD_OK; }
   GramPlan pl;
-  int rc = make_plan(streams, n_streams, seg_keep, n_seg, opt, &pl);
+  int rc = make_plan(streams, n_streams, seg_first, seg_keep, n_seg, opt, &pl);
   if (rc) return rc;
   *bytes = pl.total;
   return TD_OK;
+}
+
+extern "C" float td_last_gram_kernel_ms(void) {
+  if (!g_ev_valid) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(g_ev_stop) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, g_ev_start, g_ev_stop) != cudaSuccess) return -1.0f;
+  return ms;
 }
 
 extern "C" int td_symmetrize_f32(float* G, int64_t n, int64_t ldg, int from_upper, void* stream) {
@@ -552,9 +582,10 @@ extern "C" int td_symmetrize_f32(float* G, int64_t n, int64_t ldg, int from_uppe
   return TD_OK;
 }
 
-extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const int64_t* seg_keep,
-                                  int n_seg, float* G, int64_t ldg, const td_gram_options* opt,
-                                  void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const int64_t* seg_first,
+                                  const int64_t* seg_keep, int n_seg, float* G, int64_t ldg,
+                                  const td_gram_options* opt, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   TD_REQUIRE(streams && seg_keep && G, "td_lagged_gram_f32: null argument");
   if (opt && opt->method == 1) {
@@ -565,11 +596,11 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       Dz += width_of(streams[q]);
     }
     TD_REQUIRE(ldg >= Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)Dz);
-    return launch_gram_simt(streams, n_streams, nullptr, seg_keep, n_seg, G, ldg, st);
+    return launch_gram_simt(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, st);
   }
   TD_REQUIRE(opt == nullptr || opt->method == 0, "td_lagged_gram_f32: unknown method %d", opt->method);
   GramPlan pl;
-  int rc = make_plan(streams, n_streams, seg_keep, n_seg, opt, &pl);
+  int rc = make_plan(streams, n_streams, seg_first, seg_keep, n_seg, opt, &pl);
   if (rc) return rc;
   TD_REQUIRE(ldg >= pl.Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)pl.Dz);
   if (workspace_bytes < pl.total || !workspace) {
@@ -610,10 +641,14 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
   }
   std::vector<int2> ktiles;
   ktiles.reserve(pl.NK);
-  for (int s = 0; s < n_seg; ++s)
-    for (int64_t j = 0; j * BK < seg_keep[s]; ++j)
-      ktiles.push_back(make_int2((int)(pl.seg_off[s] + j * BK),
-                                 (int)std::min<int64_t>(BK, seg_keep[s] - j * BK)));
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t f = first_of(seg_first, s);
+    for (int64_t j = f / BK; j * BK < seg_keep[s] && seg_keep[s] > f; ++j) {
+      const int begin = (int)std::max<int64_t>(0, f - j * BK);
+      const int end = (int)std::min<int64_t>(BK, seg_keep[s] - j * BK);
+      ktiles.push_back(make_int2((int)(pl.seg_off[s] + j * BK), begin | (end << 8)));
+    }
+  }
   std::vector<int64_t> segtab((size_t)n_seg * 2 * n_streams);
   for (int q = 0; q < n_streams; ++q)
     for (int s = 0; s < n_seg; ++s) {
@@ -671,7 +706,7 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
     P.groups_per_tile = TILE_ROWS / pl.CB;
     P.ntri = pl.ntri;
     P.NK = pl.NK;
-    int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 512;
+    int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 128;
     P.chunk_kt = std::max(1, chunk_rows / BK);
     // Superchunk: the staged frames all tiles sweep together; sized to stay L2 resident (~24 MB).
     int64_t sc_rows = (opt && opt->superchunk_rows > 0) ? opt->superchunk_rows : 0;
@@ -688,8 +723,16 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
     P.total_steps = nsc * pl.ntri * ks;
     int workers = sms / pl.cg;
     if (opt && opt->max_ctas > 0) workers = std::max(1, std::min(workers, opt->max_ctas / pl.cg));
-    // No more workers than there are chunk-sized pieces of work.
-    workers = (int)std::max<int64_t>(1, std::min<int64_t>(workers, ceil_div(P.total_steps, P.chunk_kt)));
+    // No more workers than there are chunk-sized pieces of work in a superchunk.
+    workers = (int)std::max<int64_t>(1, std::min<int64_t>(workers, ceil_div((int64_t)pl.ntri * ks, P.chunk_kt)));
+    const bool timed = opt && opt->reserved[0] == 1;
+    if (timed) {
+      if (!g_ev_start) {
+        TD_CHECK_CUDA(cudaEventCreate(&g_ev_start));
+        TD_CHECK_CUDA(cudaEventCreate(&g_ev_stop));
+      }
+      TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
+    }
     if (pl.cg == 1) {
       TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
       lagged_gram_umma_kernel<1><<<workers, NUM_THREADS, SMEM_BYTES, st>>>(tmaps[0], tmaps[1], P);
@@ -710,6 +753,10 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lagged_gram_umma_kernel<2>, tmaps[0], tmaps[1], P));
     }
     TD_CHECK_CUDA(cudaGetLastError());
+    if (timed) {
+      TD_CHECK_CUDA(cudaEventRecord(g_ev_stop, st));
+      g_ev_valid = true;
+    }
     if (debug_enabled())
       fprintf(stderr, "[tdgram] gram launch: cg=%d workers=%d CB=%d Dz=%lld Dpad=%lld ntri=%d NK=%lld KS=%d chunk_kt=%d total=%lld Tp=%lld\n",
               pl.cg, workers, pl.CB, (long long)pl.Dz, (long long)pl.Dpad, pl.ntri, (long long)pl.NK, P.KS, P.chunk_kt,

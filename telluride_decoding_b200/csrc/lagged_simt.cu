@@ -98,10 +98,12 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(MultiView mv, const int6
 // ---------------------------------------------------------------------------------------------
 constexpr int THIN_TB = 512;   // frames per block
 constexpr int THIN_QMAX = 16;
+constexpr int THIN_SLICES = 64;   // partial-sum copies: blocks add into slice (block % 64) to keep
+                                  // same-address float64 atomics from serialising, then one reduce
 
 __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, int has_v, int Q,
                                                    const int64_t* seg_keep, const int* blk_seg,
-                                                   const int64_t* blk_t0, double* xtv,
+                                                   const int64_t* blk_t0, double* xtv_slices,
                                                    double* vtv) {
   __shared__ float Vs[THIN_TB][THIN_QMAX];
   const int seg = blk_seg[blockIdx.x];
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, i
   const int64_t Dx = (int64_t)x.channels * x.lags;
   const int64_t len = x.seg_len[seg];
   const float* base = x.data + x.seg_start[seg] * x.ld;
+  double* xtv = xtv_slices + (size_t)(blockIdx.x % THIN_SLICES) * Dx * Q;
   for (int64_t j = threadIdx.x; j < Dx; j += blockDim.x) {
     const int k = (int)(j / x.channels);
     const int c = (int)(j - (int64_t)k * x.channels);
@@ -145,6 +148,15 @@ __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, i
     for (int r = 0; r < rows; ++r) s += (double)Vs[r][a] * (double)Vs[r][b];
     atomicAdd(vtv + e, s);
   }
+}
+
+__global__ void thin_reduce_kernel(const double* __restrict__ slices, double* __restrict__ out,
+                                   int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < THIN_SLICES; ++k) s += slices[(size_t)k * n + i];
+  out[i] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -364,8 +376,15 @@ extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const 
   TD_CHECK_CUDA(cudaMemsetAsync(xtv, 0, (size_t)Dx * Q * sizeof(double), st));
   TD_CHECK_CUDA(cudaMemsetAsync(vtv, 0, (size_t)Q * Q * sizeof(double), st));
   if (nblk > 0) {
-    thin_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, xtv, vtv);
+    double* slices = nullptr;
+    const size_t slice_bytes = (size_t)THIN_SLICES * Dx * Q * sizeof(double);
+    TD_CHECK_CUDA(cudaMallocAsync((void**)&slices, slice_bytes, st));
+    TD_CHECK_CUDA(cudaMemsetAsync(slices, 0, slice_bytes, st));
+    thin_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, slices, vtv);
     TD_CHECK_CUDA(cudaGetLastError());
+    thin_reduce_kernel<<<(unsigned)ceil_div(Dx * Q, 256), 256, 0, st>>>(slices, xtv, Dx * Q);
+    TD_CHECK_CUDA(cudaGetLastError());
+    TD_CHECK_CUDA(cudaFreeAsync(slices, st));
   }
   return TD_OK;
 }

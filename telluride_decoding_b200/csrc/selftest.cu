@@ -25,17 +25,18 @@ struct Case {
   std::vector<int64_t> seg_len;
   std::vector<int64_t> seg_keep;   // empty = keep all
   bool host_check;
+  std::vector<int64_t> seg_first;  // empty = 0
 };
 
 static void host_gram(const std::vector<float>& x, int C, int pre, int post, const std::vector<float>& y, int C2, int pre2,
                       int post2, const std::vector<int64_t>& start, const std::vector<int64_t>& len,
-                      const std::vector<int64_t>& keep, std::vector<double>& G) {
+                      const std::vector<int64_t>& keep, std::vector<double>& G, const std::vector<int64_t>& first) {
   const int L1 = pre + 1 + post, L2 = C2 ? pre2 + 1 + post2 : 0;
   const int64_t D1 = (int64_t)L1 * C, D = D1 + (int64_t)L2 * C2;
   G.assign((size_t)D * D, 0.0);
   std::vector<double> row(D);
   for (size_t s = 0; s < len.size(); ++s) {
-    for (int64_t t = 0; t < keep[s]; ++t) {
+    for (int64_t t = first.empty() ? 0 : first[s]; t < keep[s]; ++t) {
       for (int k = 0; k < L1; ++k)
         for (int c = 0; c < C; ++c) {
           int64_t u = t - pre + k;
@@ -82,6 +83,7 @@ int main(int argc, char** argv) {
       {"c8_l1_n50", 8, 0, 0, 0, 0, 0, {50}, {}, true},
       {"c2_l3_n100", 2, 1, 1, 0, 0, 0, {100}, {}, true},
       {"c3_l4_2seg_keep", 3, 1, 2, 0, 0, 0, {333, 217}, {320, 200}, true},
+      {"c3_l4_2seg_range", 3, 1, 2, 0, 0, 0, {333, 217}, {320, 200}, true, {37, 64}},
       {"c64_l4_n4096", 64, 0, 3, 0, 0, 0, {4096}, {}, true},
       {"c32_l33_n3000", 32, 16, 16, 0, 0, 0, {3000}, {}, true},
       {"c20_l5+c6_l3_cca", 20, 0, 4, 6, 1, 1, {1500, 901}, {1500, 890}, true},
@@ -94,6 +96,7 @@ int main(int argc, char** argv) {
     if (filter[0] && !strstr(cs.name, filter)) continue;
     const int n_seg = (int)cs.seg_len.size();
     std::vector<int64_t> start(n_seg), keep = cs.seg_keep.empty() ? cs.seg_len : cs.seg_keep;
+    const std::vector<int64_t>& first = cs.seg_first;
     int64_t rows = 0;
     for (int s = 0; s < n_seg; ++s) { start[s] = rows; rows += cs.seg_len[s]; }
     printf("[case %s] begin\n", cs.name);
@@ -124,7 +127,7 @@ int main(int argc, char** argv) {
     opt.cta_group = cta_group;
     opt.chunk_rows = chunk_rows;
     size_t wsb = 0;
-    if (td_lagged_gram_workspace_bytes(st, ns, keep.data(), n_seg, &opt, &wsb)) { printf("%s: ws: %s\n", cs.name, td_last_error()); return 2; }
+    if (td_lagged_gram_workspace_bytes(st, ns, first.empty() ? nullptr : first.data(), keep.data(), n_seg, &opt, &wsb)) { printf("%s: ws: %s\n", cs.name, td_last_error()); return 2; }
     void* ws;
     CK(cudaMalloc(&ws, wsb ? wsb : 1));
     cudaEvent_t e0, e1;
@@ -133,7 +136,7 @@ int main(int argc, char** argv) {
     int rc = 0;
     for (int rep = 0; rep < 2; ++rep) {
       cudaEventRecord(e0);
-      rc = td_lagged_gram_f32(st, ns, keep.data(), n_seg, Gd, D, &opt, ws, wsb, nullptr);
+      rc = td_lagged_gram_f32(st, ns, first.empty() ? nullptr : first.data(), keep.data(), n_seg, Gd, D, &opt, ws, wsb, nullptr);
       cudaEventRecord(e1);
       if (rc) { printf("%s: gram failed: %s\n", cs.name, td_last_error()); return 2; }
       cudaError_t e = cudaDeviceSynchronize();
@@ -143,7 +146,7 @@ int main(int argc, char** argv) {
     td_gram_options opt1 = {};
     opt1.method = 1;
     cudaEventRecord(e0);
-    rc = td_lagged_gram_f32(st, ns, keep.data(), n_seg, Gs, D, &opt1, nullptr, 0, nullptr);
+    rc = td_lagged_gram_f32(st, ns, first.empty() ? nullptr : first.data(), keep.data(), n_seg, Gs, D, &opt1, nullptr, 0, nullptr);
     cudaEventRecord(e1);
     if (rc) { printf("%s: simt gram failed: %s\n", cs.name, td_last_error()); return 2; }
     CK(cudaDeviceSynchronize());
@@ -154,11 +157,11 @@ int main(int argc, char** argv) {
     double asym = 0;
     for (int64_t i = 0; i < D; ++i) for (int64_t j = 0; j < i; ++j) asym = std::max(asym, (double)std::fabs(g1[i * D + j] - g1[j * D + i]));
     int64_t frames = 0;
-    for (auto k : keep) frames += k;
+    for (size_t i = 0; i < keep.size(); ++i) frames += keep[i] - (first.empty() ? 0 : first[i]);
     double tflops = (double)frames * D * (D + 1) / (ms_umma * 1e-3) / 1e12;
     if (cs.host_check) {
       std::vector<double> G;
-      host_gram(x, cs.C, cs.pre, cs.post, y, cs.C2, cs.pre2, cs.post2, start, cs.seg_len, keep, G);
+      host_gram(x, cs.C, cs.pre, cs.post, y, cs.C2, cs.pre2, cs.post2, start, cs.seg_len, keep, G, first);
       double e_umma = rel_fro(g1, G), e_simt = rel_fro(g2, G);
       bool ok = e_umma < 1e-5 && e_simt < 1e-5;
       if (!ok) ++failures;

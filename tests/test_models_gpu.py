@@ -131,15 +131,18 @@ def test_multi_trial_interleaved_fit_and_evaluate():
   lens = [1300, 900, 1111]
   bd = brain_data.TrialBrainData('eeg', 'intensity', 100.0, pre_context=2, post_context=3,
                                  final_batch_size=200, shuffle_buffer_size=0)
-  files = []
+  by_name = {}
   wt = rng.randn(6 * 5, 1).astype(np.float32)
   for i, n in enumerate(lens):
     x = rng.randn(n, 5).astype(np.float32)
     y = (ora.add_context(x, 2, 3) @ wt + 0.2 * rng.randn(n, 1)).astype(np.float32)
     bd.add_trial('t%d' % i, x, y)
     z = np.zeros((n, 1), np.float32)
-    files.append(ora.file_rows(x, z, y, z, 2, 3))
+    by_name['t%d' % i] = ora.file_rows(x, z, y, z, 2, 3)
   ds = bd.create_dataset('train')
+  # like the reference (brain_data.py:206-207) the file list is shuffled once; the interleave
+  # follows that order
+  files = [by_name[name] for name, _, _ in ds.files]
   assert ds.num_batches == sum(lens) // 200
   model = brain_model.BrainModelLinearRegression(ds, regularization_lambda=0.1)
   model.fit(ds)

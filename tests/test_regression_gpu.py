@@ -25,15 +25,16 @@ def _trials(seed, lens, c, lags, c2=0):
   return out
 
 
-def _oracle_jackknife(trials, names, lambdas, post, batch, cca_dims=0, post2=0):
+def _oracle_jackknife(trials, names, lambdas, post, batch, cca_dims=0, post2=0, file_order=None):
   res = np.zeros((len(lambdas), len(names)))
+  file_order = [names.index(n) for n in (file_order or names)]   # interleave order of the data object
   rows = []
   for x, y, x2 in trials:
     z = np.zeros((x.shape[0], 1), np.float32)
     rows.append(ora.file_rows(x, z if x2 is None else x2, y, z, 0, post, 0, post2))
   order = np.argsort(names)
   for j, f in enumerate(order):
-    train = ora.batches_from_files([rows[i] for i in range(len(names)) if i != f], batch)
+    train = ora.batches_from_files([rows[i] for i in file_order if i != f], batch)
     test = ora.batches_from_files([rows[f]], batch)
     for i, lam in enumerate(lambdas):
       if cca_dims:
@@ -60,7 +61,7 @@ def test_linear_jackknife_matches_reference_loop():
     bd.add_trial(n, x, y)
   lambdas = [1e-4, 1e-2, 1.0, 10.0]
   out = reg.jackknife_over_regularizations(opts, lambdas, brain_data_object=bd)
-  want = _oracle_jackknife(trials, names, lambdas, 4, 100)
+  want = _oracle_jackknife(trials, names, lambdas, 4, 100, file_order=bd.all_files())
   got = reg.all_runs_results
   assert got.shape == want.shape == (4, 5)
   np.testing.assert_allclose(got, want, atol=1e-4)
@@ -86,5 +87,6 @@ def test_cca_jackknife_matches_reference_loop():
     bd.add_trial(n, x, y, x2)
   lambdas = [0.01, 0.1, 1.0]
   got = regression.jackknife_sweep(bd, opts, lambdas)
-  want = _oracle_jackknife(trials, names, lambdas, 3, 100, cca_dims=2, post2=2)
+  want = _oracle_jackknife(trials, names, lambdas, 3, 100, cca_dims=2, post2=2,
+                           file_order=bd.all_files())
   np.testing.assert_allclose(got, want, atol=2e-4)
