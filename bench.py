@@ -147,7 +147,7 @@ class ClockSampler(object):
     try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-           '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+           '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
           stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
