@@ -193,7 +193,8 @@ def main():
   ap.add_argument('--steps', type=int, default=5)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-  ap.add_argument('--solve-method', type=int, default=0, help='0 Cholesky per lambda, 1 one eigh')
+  ap.add_argument('--solve-method', type=int, default=2,
+                  help='2 batched blocked Cholesky sweep, 0 cuSOLVER Cholesky per lambda, 1 one eigh')
   ap.add_argument('--cta-group', type=int, default=0)
   ap.add_argument('--chunk-rows', type=int, default=0)
   ap.add_argument('--skip-cpu-baseline', action='store_true')
@@ -358,7 +359,10 @@ def main():
                gram_pass_s=r['gram_pass_s'], solve_s=r['solve_s'], gram_gflops=r['gram_gflops'],
                single_pass_frames_per_s=frames / (r['gram_pass_s'] + r['solve_s']))
 
-  n_launch = 4 + 2 + 2 * len(my_lambdas)            # stage, gram, symmetrize, thin + solve helpers
+  # stage, gram, symmetrize, thin, thin-reduce + solve: scale, colmajor, build, take_y, store and per
+  # 64-column panel potf2 + copy (factor) and one back-substitution kernel
+  n_panels = (CFG['channels'] * (CFG['pre'] + 1 + CFG['post']) + 1 + 63) // 64
+  n_launch = 5 + 5 + 3 * n_panels
   line = dict(
       metric=METRIC, value=world * frames / (ms_per_step * 1e-3), unit='frames/s', n_gpus=world,
       steps=args.steps, warmup=warmup, ms_per_step=ms_per_step, higher_is_better=True,

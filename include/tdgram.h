@@ -141,8 +141,10 @@ int td_lagged_rows_f32(const td_stream* x, const int64_t* seg_keep, const int64_
  * (bias row included), B = C_aug / n, solution = A^-1 B for every lambda.
  *   G_aug_dev [Da, Da] double (Da = D+1 with the ones column last, or D when no offset)
  *   C_aug_dev [Da, Dy] double;  W_out_dev [n_lambda, Da, Dy] float32.
- *   method 0: Cholesky per lambda (LU if not positive definite); 1: one eigendecomposition
- *   reused for the whole sweep.  Synchronises the stream.
+ *   method 0: cuSOLVER Cholesky per lambda on side streams (LU if not positive definite);
+ *   1: one eigendecomposition reused for the whole sweep; 2: the whole sweep as ONE batched,
+ *   blocked Cholesky (own panel kernels + cublasDgemmStridedBatched; falls back to method 0 for a
+ *   lambda whose matrix is not positive definite).  Synchronises the stream.
  * ------------------------------------------------------------------------------------- */
 int td_ridge_solve(const double* G_aug_dev, const double* C_aug_dev, int Da, int Dy, double n,
                    const double* lambdas, int n_lambda, int method, float* W_out_dev,

@@ -146,8 +146,11 @@ class RegressionStats(object):
     return g, c.contiguous()
 
 
-def solve_regression(stats, lambdas, use_offset=True, method=0):
-  """[(W [D, Dy], b [Dy])] float32 CUDA tensors, one per lambda (brain_model.py:447-479)."""
+def solve_regression(stats, lambdas, use_offset=True, method=2):
+  """[(W [D, Dy], b [Dy])] float32 CUDA tensors, one per lambda (brain_model.py:447-479).
+
+  method 2 (default): the whole sweep as one batched blocked Cholesky; 0: cuSOLVER Cholesky per
+  lambda; 1: one eigendecomposition reused for every lambda."""
   g_aug, c_aug = stats.augmented(use_offset)
   sol = ops.ridge_solve(g_aug, c_aug, stats.n, lambdas, method=method)
   out = []
@@ -312,7 +315,7 @@ class BrainModelLinearRegression(BrainModel):
     self.w_estimate = self._w.cpu().numpy()
     self.b_estimate = self._b.cpu().numpy()
 
-  def fit_from_stats(self, stats, regularization_lambda=None, method=0):
+  def fit_from_stats(self, stats, regularization_lambda=None, method=2):
     lamb = self._regularization_lambda if regularization_lambda is None else regularization_lambda
     (w, b), = solve_regression(stats, [lamb], method=method)
     self._w, self._b = w.contiguous(), b.contiguous()

@@ -96,20 +96,39 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(MultiView mv, const int6
 }
 
 // ---------------------------------------------------------------------------------------------
-constexpr int THIN_TB = 512;   // frames per block
+constexpr int THIN_TB = 256;      // frames per block
+constexpr int THIN_CB = 64;       // channels per block
 constexpr int THIN_QMAX = 16;
+constexpr int THIN_KT = 4;        // lags per thread (register window)
+constexpr int THIN_QFAST = 4;     // target columns handled by the register-tiled path
 constexpr int THIN_SLICES = 64;   // partial-sum copies: blocks add into slice (block % 64) to keep
                                   // same-address float64 atomics from serialising, then one reduce
 
+// Block = (256-frame piece of a segment, 64-channel block).  The raw frames it needs (piece + lag
+// halo) and the targets are staged in shared memory once; thread j = (lag k, channel c) then walks
+// the piece with fp32 FMAs, carried into float64 every 32 frames.
 __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, int has_v, int Q,
                                                    const int64_t* seg_keep, const int* blk_seg,
                                                    const int64_t* blk_t0, double* xtv_slices,
                                                    double* vtv) {
-  __shared__ float Vs[THIN_TB][THIN_QMAX];
+  extern __shared__ float thin_sm[];
   const int seg = blk_seg[blockIdx.x];
   const int64_t t0 = blk_t0[blockIdx.x];
   const int64_t keep = seg_keep[seg];
   const int rows = (int)min((int64_t)THIN_TB, keep - t0);
+  const int L = x.lags;
+  const int halo_rows = rows + L - 1;
+  const int c0 = blockIdx.y * THIN_CB;
+  float* xs = thin_sm;                                   // [halo_rows][THIN_CB]
+  float* vs = thin_sm + (size_t)(THIN_TB + L - 1) * THIN_CB;   // [rows][Q]
+  const int64_t len = x.seg_len[seg];
+  const float* base = x.data + x.seg_start[seg] * x.ld;
+  for (int e = threadIdx.x; e < halo_rows * THIN_CB; e += blockDim.x) {
+    const int r = e / THIN_CB, cl = e % THIN_CB;
+    const int64_t u = t0 + r - x.pre;
+    const int c = c0 + cl;
+    xs[e] = (u >= 0 && u < len && c < x.channels) ? __ldg(base + u * x.ld + c) : 0.0f;
+  }
   for (int e = threadIdx.x; e < rows * Q; e += blockDim.x) {
     const int r = e / Q, q = e % Q;
     float val = 1.0f;
@@ -117,36 +136,95 @@ __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, i
       const int64_t u = t0 + r;
       val = (has_v && u < v.seg_len[seg]) ? __ldg(v.data + (v.seg_start[seg] + u) * v.ld + q) : 0.0f;
     }
-    Vs[r][q] = val;
+    vs[e] = val;
   }
   __syncthreads();
-  const int64_t Dx = (int64_t)x.channels * x.lags;
-  const int64_t len = x.seg_len[seg];
-  const float* base = x.data + x.seg_start[seg] * x.ld;
-  double* xtv = xtv_slices + (size_t)(blockIdx.x % THIN_SLICES) * Dx * Q;
-  for (int64_t j = threadIdx.x; j < Dx; j += blockDim.x) {
-    const int k = (int)(j / x.channels);
-    const int c = (int)(j - (int64_t)k * x.channels);
-    double acc[THIN_QMAX];
+  const int64_t Dx = (int64_t)x.channels * L;
+  double* xtv = xtv_slices + (size_t)((blockIdx.x + blockIdx.y) % THIN_SLICES) * Dx * Q;
+  // Thread = (channel, group of THIN_KT consecutive lags): the frames x[r+k .. r+k+KT) slide
+  // through registers, so one shared-memory load of x and Q of the targets feed KT*Q FMAs.
+  const int n_kg = (L + THIN_KT - 1) / THIN_KT;
+  for (int jj = threadIdx.x; jj < n_kg * THIN_CB; jj += blockDim.x) {
+    const int kg = jj / THIN_CB, cl = jj % THIN_CB;
+    const int c = c0 + cl;
+    if (c >= x.channels) continue;
+    const int k0 = kg * THIN_KT;
+    if (Q <= THIN_QFAST) {
+      double accd[THIN_KT][THIN_QFAST];
 #pragma unroll
-    for (int q = 0; q < THIN_QMAX; ++q) acc[q] = 0.0;
-    for (int r = 0; r < rows; ++r) {
-      const int64_t u = t0 + r - x.pre + k;
-      if (u < 0 || u >= len) continue;
-      const double xv = (double)__ldg(base + u * x.ld + c);
+      for (int i = 0; i < THIN_KT; ++i)
 #pragma unroll
-      for (int q = 0; q < THIN_QMAX; ++q)
-        if (q < Q) acc[q] += xv * (double)Vs[r][q];
+        for (int q = 0; q < THIN_QFAST; ++q) accd[i][q] = 0.0;
+      for (int r0 = 0; r0 < rows; r0 += 32) {
+        float accf[THIN_KT][THIN_QFAST];
+#pragma unroll
+        for (int i = 0; i < THIN_KT; ++i)
+#pragma unroll
+          for (int q = 0; q < THIN_QFAST; ++q) accf[i][q] = 0.0f;
+        const int r1 = min(rows, r0 + 32);
+        float win[THIN_KT];
+#pragma unroll
+        for (int i = 0; i < THIN_KT - 1; ++i)
+          win[i + 1] = (r0 + k0 + i < halo_rows) ? xs[(r0 + k0 + i) * THIN_CB + cl] : 0.0f;
+        for (int r = r0; r < r1; ++r) {
+#pragma unroll
+          for (int i = 0; i < THIN_KT - 1; ++i) win[i] = win[i + 1];
+          // (loaded by frame, not by lag validity: the value slides down to the lower lags)
+          win[THIN_KT - 1] = (r + k0 + THIN_KT - 1 < halo_rows) ? xs[(r + k0 + THIN_KT - 1) * THIN_CB + cl] : 0.0f;
+#pragma unroll
+          for (int q = 0; q < THIN_QFAST; ++q) {
+            const float vv = (q < Q) ? vs[r * Q + q] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < THIN_KT; ++i) accf[i][q] = fmaf(win[i], vv, accf[i][q]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < THIN_KT; ++i)
+#pragma unroll
+          for (int q = 0; q < THIN_QFAST; ++q) accd[i][q] += (double)accf[i][q];
+      }
+#pragma unroll
+      for (int i = 0; i < THIN_KT; ++i) {
+        if (k0 + i >= L) continue;
+        const int64_t j = (int64_t)(k0 + i) * x.channels + c;
+#pragma unroll
+        for (int q = 0; q < THIN_QFAST; ++q)
+          if (q < Q) atomicAdd(xtv + j * Q + q, accd[i][q]);
+      }
+    } else {
+      for (int i = 0; i < THIN_KT && k0 + i < L; ++i) {
+        const int k = k0 + i;
+        double accd[THIN_QMAX];
+#pragma unroll
+        for (int q = 0; q < THIN_QMAX; ++q) accd[q] = 0.0;
+        for (int r0 = 0; r0 < rows; r0 += 32) {
+          float accf[THIN_QMAX];
+#pragma unroll
+          for (int q = 0; q < THIN_QMAX; ++q) accf[q] = 0.0f;
+          const int r1 = min(rows, r0 + 32);
+          for (int r = r0; r < r1; ++r) {
+            const float xv = xs[(r + k) * THIN_CB + cl];
+#pragma unroll
+            for (int q = 0; q < THIN_QMAX; ++q)
+              if (q < Q) accf[q] = fmaf(xv, vs[r * Q + q], accf[q]);
+          }
+#pragma unroll
+          for (int q = 0; q < THIN_QMAX; ++q) accd[q] += (double)accf[q];
+        }
+        const int64_t j = (int64_t)k * x.channels + c;
+#pragma unroll
+        for (int q = 0; q < THIN_QMAX; ++q)
+          if (q < Q) atomicAdd(xtv + j * Q + q, accd[q]);
+      }
     }
-#pragma unroll
-    for (int q = 0; q < THIN_QMAX; ++q)
-      if (q < Q) atomicAdd(xtv + j * Q + q, acc[q]);
   }
-  for (int e = threadIdx.x; e < Q * Q; e += blockDim.x) {
-    const int a = e / Q, b = e % Q;
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += (double)Vs[r][a] * (double)Vs[r][b];
-    atomicAdd(vtv + e, s);
+  if (blockIdx.y == 0) {
+    for (int e = threadIdx.x; e < Q * Q; e += blockDim.x) {
+      const int a = e / Q, b = e % Q;
+      double s = 0.0;
+      for (int r = 0; r < rows; ++r) s += (double)vs[r * Q + a] * (double)vs[r * Q + b];
+      atomicAdd(vtv + e, s);
+    }
   }
 }
 
@@ -380,7 +458,15 @@ extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const 
     const size_t slice_bytes = (size_t)THIN_SLICES * Dx * Q * sizeof(double);
     TD_CHECK_CUDA(cudaMallocAsync((void**)&slices, slice_bytes, st));
     TD_CHECK_CUDA(cudaMemsetAsync(slices, 0, slice_bytes, st));
-    thin_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, slices, vtv);
+    const int L = lags_of(*x);
+    const size_t smem = ((size_t)(THIN_TB + L - 1) * THIN_CB + (size_t)THIN_TB * Q) * sizeof(float);
+    if (smem > 220 * 1024) {
+      set_error("td_lagged_thin_f64: %d lags need %zu bytes of shared memory", L, smem);
+      return TD_ERR_UNSUPPORTED;
+    }
+    TD_CHECK_CUDA(cudaFuncSetAttribute(thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)nblk, (unsigned)ceil_div(x->channels, THIN_CB));
+    thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, slices, vtv);
     TD_CHECK_CUDA(cudaGetLastError());
     thin_reduce_kernel<<<(unsigned)ceil_div(Dx * Q, 256), 256, 0, st>>>(slices, xtv, Dx * Q);
     TD_CHECK_CUDA(cudaGetLastError());

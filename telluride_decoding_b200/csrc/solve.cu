@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -16,17 +18,17 @@
 namespace td {
 namespace {
 
-constexpr int MAX_LANES = 4;    // concurrent factorisations of a lambda sweep
+constexpr int MAX_LANES = 8;    // concurrent factorisations of a lambda sweep
 
 struct Handles {
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;
   // side streams (+ their own cuSOLVER handles) so that the independent Cholesky factorisations of
   // a regularisation sweep overlap: one n ~ 2000 potrf cannot fill 148 SMs
-  cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
-  cusolverDnHandle_t lane_solver[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t lane_stream[MAX_LANES] = {};
+  cusolverDnHandle_t lane_solver[MAX_LANES] = {};
   cudaEvent_t ev_ready = nullptr;
-  cudaEvent_t ev_done[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_done[MAX_LANES] = {};
 };
 
 int get_handles(Handles** out) {
@@ -181,51 +183,228 @@ int eigh(Handles* h, Scratch& sc, double* A, int n, double* w, int* info_dev) {
   return TD_OK;
 }
 
-}  // namespace
-}  // namespace td
+// ---------------------------------------------------------------------------------------------
+// Whole regularisation sweep as ONE batched, blocked Cholesky (float64).
+//
+// Every lambda gets its own copy M_l of the augmented matrix [[A0 + lambda I, .], [B0', .]]
+// (column-major, Nt = Da + Dy rows; the right-hand sides ride along as extra rows, so the forward
+// substitution L^-1 B falls out of the panel solves).  Per 64-column panel, for all lambdas at once:
+//   potf2 of the diagonal block (one CTA per matrix, shared memory)
+//   panel rows below:  P <- P L_jj^-T          (thread per row, L_jj in shared memory)
+//   trailing update:   C <- C - P P'           (cublasDgemmStridedBatched over the batch)
+// then a blocked back substitution.  One n ~ 2000 potrf cannot fill 148 SMs; twenty together can.
+constexpr int CH_NB = 64;
 
-using namespace td;
+__global__ void chol_build(const double* __restrict__ A0, const double* __restrict__ B0, int Da, int Dy,
+                           const double* __restrict__ lambdas_dev, int l0, double* __restrict__ M) {
+  const long long Nt = Da + Dy;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nt * Da) return;                       // columns >= Da are never read
+  const long long c = i / Nt, r = i - c * Nt;
+  double* Ml = M + (size_t)blockIdx.y * Nt * Nt;
+  double v;
+  if (r < Da) v = A0[c * Da + r] + (r == c ? lambdas_dev[l0 + blockIdx.y] : 0.0);   // A0 is symmetric
+  else v = B0[c + (r - Da) * Da];
+  Ml[c * Nt + r] = v;
+}
 
-extern "C" int td_ridge_solve(const double* G_aug, const double* C_aug, int Da, int Dy, double n,
-                              const double* lambdas, int n_lambda, int method, float* W_out, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  TD_REQUIRE(G_aug && C_aug && lambdas && W_out, "td_ridge_solve: null argument");
-  TD_REQUIRE(Da >= 1 && Dy >= 1 && n_lambda >= 1 && n > 0, "td_ridge_solve: Da=%d Dy=%d n_lambda=%d n=%g", Da, Dy, n_lambda, n);
-  TD_REQUIRE(method == 0 || method == 1, "td_ridge_solve: unknown method %d", method);
-  Handles* h;
-  int rc = get_handles(&h);
-  if (rc) return rc;
-  TD_CHECK_SOLVER(cusolverDnSetStream(h->solver, st));
-  TD_CHECK_SOLVER(cublasSetStream(h->blas, st));
-  Scratch sc(st);
-  const long long nn = (long long)Da * Da, nb = (long long)Da * Dy;
-  double *A0, *A, *B0, *X;
-  int* info;
-  if ((rc = sc.get(nn, &A0)) || (rc = sc.get(nn, &A)) || (rc = sc.get(nb, &B0)) || (rc = sc.get(nb, &X)) || (rc = sc.get(1, &info))) return rc;
-  scale_add_diag<<<blocks_for(nn), 256, 0, st>>>(G_aug, A0, Da, 1.0 / n, 0.0);
-  to_colmajor<<<blocks_for(nb), 256, 0, st>>>(C_aug, B0, Da, Dy, 1.0 / n);
-  TD_CHECK_CUDA(cudaGetLastError());
-
-  if (method == 1) {
-    double *w, *Z;
-    if ((rc = sc.get(Da, &w)) || (rc = sc.get(nb, &Z))) return rc;
-    if ((rc = eigh(h, sc, A0, Da, w, info))) return rc;    // A0 now holds V (column-major)
-    int hinfo = 0;
-    TD_CHECK_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
-    TD_CHECK_CUDA(cudaStreamSynchronize(st));
-    if (hinfo != 0) { set_error("td_ridge_solve: syevd did not converge (info %d)", hinfo); return TD_ERR_SOLVER; }
-    const double one = 1.0, zero = 0.0;
-    TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, Da, Dy, Da, &one, A0, Da, B0, Da, &zero, Z, Da));
-    for (int l = 0; l < n_lambda; ++l) {
-      divide_rows<<<blocks_for(nb), 256, 0, st>>>(Z, w, lambdas[l], A /*scratch*/, Da, Dy);
-      TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, Da, Dy, Da, &one, A0, Da, A, Da, &zero, X, Da));
-      to_rowmajor_f32<<<blocks_for(nb), 256, 0, st>>>(X, Da, W_out + (size_t)l * nb, Da, Dy);
-    }
-    TD_CHECK_CUDA(cudaGetLastError());
-    TD_CHECK_CUDA(cudaStreamSynchronize(st));
-    return TD_OK;
+// Factor the jb x jb diagonal block at (j0, j0) of every matrix in place (lower) and write the
+// inverse of the factor, Linv [batch][64][64] column-major (zero padded), for the panel solve.
+// info[l] = first non-positive pivot (1-based, global column) or unchanged.
+__global__ void __launch_bounds__(256) chol_potf2(double* M, long long Nt, int j0, int jb, int* info,
+                                                  double* __restrict__ Linv, long long linv_stride) {
+  extern __shared__ double chol_sm[];
+  double (*T)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chol_sm);
+  double (*X)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chol_sm + CH_NB * (CH_NB + 1));
+  double* Ml = M + (size_t)blockIdx.x * Nt * Nt + (size_t)j0 * Nt + j0;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  for (int e = threadIdx.x; e < CH_NB * CH_NB; e += blockDim.x) {
+    const int c = e >> 6, r = e & 63;
+    T[r][c] = (r >= c && r < jb) ? Ml[(size_t)c * Nt + r] : ((r == c) ? 1.0 : 0.0);   // identity padding
+    X[r][c] = 0.0;
   }
+  __syncthreads();
+  for (int k = 0; k < jb; ++k) {
+    const double d = T[k][k];
+    if (!(d > 0.0) && threadIdx.x == 0 && info[blockIdx.x] == 0) info[blockIdx.x] = j0 + k + 1;
+    const double rpiv = rsqrt(d > 0.0 ? d : 1.0);
+    __syncthreads();
+    if (threadIdx.x >= k && threadIdx.x < CH_NB) T[threadIdx.x][k] *= rpiv;     // T[k][k] = sqrt(d)
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int r = ty + 16 * a;
+#pragma unroll
+      for (int bb = 0; bb < 4; ++bb) {
+        const int c = tx + 16 * bb;
+        if (c > k && r >= c) T[r][c] -= T[r][k] * T[c][k];
+      }
+    }
+    __syncthreads();
+  }
+  // Linv: column j by forward substitution, one thread per column.
+  if (threadIdx.x < CH_NB) {
+    const int j = threadIdx.x;
+    X[j][j] = 1.0 / T[j][j];
+    for (int i = j + 1; i < CH_NB; ++i) {
+      double sacc = 0.0;
+      for (int k = j; k < i; ++k) sacc += T[i][k] * X[k][j];
+      X[i][j] = -sacc / T[i][i];
+    }
+  }
+  __syncthreads();
+  double* Li = Linv + (size_t)blockIdx.x * linv_stride + (size_t)(j0 / CH_NB) * CH_NB * CH_NB;
+  for (int e = threadIdx.x; e < CH_NB * CH_NB; e += blockDim.x) {
+    const int c = e >> 6, r = e & 63;
+    Li[e] = X[r][c];
+    if (r >= c && r < jb && c < jb) Ml[(size_t)c * Nt + r] = T[r][c];
+  }
+}
 
+// tmp[batch][64][Nt] <- the panel rows below the diagonal block (source of the panel GEMM).
+__global__ void chol_copy_panel(const double* __restrict__ M, long long Nt, int j0, int jb,
+                                double* __restrict__ tmp) {
+  const long long below0 = (long long)j0 + jb;
+  const long long rows = Nt - below0;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * jb) return;
+  const long long c = i / rows, r = below0 + (i - c * rows);
+  tmp[(size_t)blockIdx.y * CH_NB * Nt + (size_t)c * Nt + r] =
+      M[(size_t)blockIdx.y * Nt * Nt + (size_t)(j0 + c) * Nt + r];
+}
+
+// Back substitution step for block j: x_j = L_jj^-T y_j (a 64 x 64 product with the stored inverse,
+// recomputed by every CTA), then y[0:j0] -= L[j0:j0+jb, 0:j0]' x_j, one thread per column.
+// Y: [batch][Dy][Da] work vectors.  grid (ceil(max(j0,1)/256), batch, Dy); CTA x == 0 stores x_j.
+__global__ void __launch_bounds__(256) chol_back(const double* __restrict__ M, long long Nt, int Da, int j0,
+                                                 int jb, const double* __restrict__ Linv, long long linv_stride,
+                                                 double* Y, double* __restrict__ Xs) {
+  __shared__ double yv[CH_NB];
+  __shared__ double xv[CH_NB];
+  const double* Ml = M + (size_t)blockIdx.y * Nt * Nt;
+  const double* Li = Linv + (size_t)blockIdx.y * linv_stride + (size_t)(j0 / CH_NB) * CH_NB * CH_NB;
+  double* y = Y + ((size_t)blockIdx.y * gridDim.z + blockIdx.z) * Da;
+  if (threadIdx.x < CH_NB) yv[threadIdx.x] = (threadIdx.x < jb) ? y[j0 + threadIdx.x] : 0.0;
+  __syncthreads();
+  if (threadIdx.x < CH_NB) {             // x_i = sum_r Linv[r][i] y_r   (Linv column-major: Li[i*64 + r])
+    const double* col = Li + (size_t)threadIdx.x * CH_NB;
+    double sacc = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < CH_NB; ++r) sacc += col[r] * yv[r];
+    xv[threadIdx.x] = sacc;
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < j0) {
+    const double* col = Ml + (size_t)c * Nt + j0;
+    double sacc = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < jb; ++r) sacc += col[r] * xv[r];
+    y[c] -= sacc;
+  }
+  // The solution goes to a separate vector: other CTAs of this launch still read y_j.
+  if (blockIdx.x == 0 && threadIdx.x < jb)
+    Xs[((size_t)blockIdx.y * gridDim.z + blockIdx.z) * Da + j0 + threadIdx.x] = xv[threadIdx.x];
+}
+
+__global__ void chol_take_y(const double* __restrict__ M, long long Nt, int Da, int Dy, double* Y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Da * Dy) return;
+  const int q = (int)(i / Da), c = (int)(i - (long long)q * Da);
+  Y[((size_t)blockIdx.y * Dy + q) * Da + c] = M[(size_t)blockIdx.y * Nt * Nt + (size_t)c * Nt + Da + q];
+}
+
+__global__ void chol_store(const double* __restrict__ Y, int Da, int Dy, float* W) {   // W [batch][Da][Dy]
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Da * Dy) return;
+  const int r = (int)(i / Dy), q = (int)(i - (long long)r * Dy);
+  W[(size_t)blockIdx.y * Da * Dy + i] = (float)Y[((size_t)blockIdx.y * Dy + q) * Da + r];
+}
+
+int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const double* A0, const double* B0,
+                           int Da, int Dy, const double* lambdas, int n_lambda, float* W_out,
+                           std::vector<int>* failed) {
+  int rc;
+  const long long Nt = (long long)Da + Dy;
+  const size_t per = (size_t)Nt * Nt * sizeof(double);
+  const int batch_max = (int)std::max<size_t>(1, std::min<size_t>(n_lambda, ((size_t)6 << 30) / per));
+  const long long n_panels = (Da + CH_NB - 1) / CH_NB;
+  const long long linv_stride = n_panels * CH_NB * CH_NB;
+  double *M, *Y, *Xs, *lam_dev, *Linv, *tmp;
+  int* info;
+  if ((rc = sc.get((size_t)Nt * Nt * batch_max, &M)) || (rc = sc.get((size_t)Da * Dy * batch_max, &Y)) || (rc = sc.get((size_t)Da * Dy * batch_max, &Xs)) ||
+      (rc = sc.get(n_lambda, &lam_dev)) || (rc = sc.get(n_lambda, &info)) ||
+      (rc = sc.get((size_t)linv_stride * batch_max, &Linv)) || (rc = sc.get((size_t)CH_NB * Nt * batch_max, &tmp)))
+    return rc;
+  TD_CHECK_CUDA(cudaMemcpyAsync(lam_dev, lambdas, n_lambda * sizeof(double), cudaMemcpyHostToDevice, st));
+  TD_CHECK_CUDA(cudaMemsetAsync(info, 0, n_lambda * sizeof(int), st));
+  const double minus_one = -1.0, one = 1.0, zero = 0.0;
+  const int potf2_smem = 2 * CH_NB * (CH_NB + 1) * (int)sizeof(double);
+  TD_CHECK_CUDA(cudaFuncSetAttribute(chol_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem));
+  const char* dbg_env = getenv("TD_DEBUG");
+  const bool dbg = dbg_env && dbg_env[0] == '2';
+  cudaEvent_t ev[4];
+  if (dbg) for (auto& e : ev) cudaEventCreate(&e);
+  for (int l0 = 0; l0 < n_lambda; l0 += batch_max) {
+    const int nbat = std::min(batch_max, n_lambda - l0);
+    if (dbg) cudaEventRecord(ev[0], st);
+    chol_build<<<dim3(blocks_for(Nt * Da), nbat), 256, 0, st>>>(A0, B0, Da, Dy, lam_dev, l0, M);
+    if (dbg) cudaEventRecord(ev[1], st);
+    for (int j0 = 0; j0 < Da; j0 += CH_NB) {
+      const int jb = std::min(CH_NB, Da - j0);
+      chol_potf2<<<nbat, 256, potf2_smem, st>>>(M, Nt, j0, jb, info + l0, Linv, linv_stride);
+      const long long below = Nt - j0 - jb;
+      if (below > 0) {
+        // panel solve P <- P L_jj^-T as a GEMM with the explicit 64 x 64 inverse
+        chol_copy_panel<<<dim3(blocks_for(below * jb), nbat), 256, 0, st>>>(M, Nt, j0, jb, tmp);
+        TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)below, jb, jb, &one,
+                                                  tmp + j0 + jb, (int)Nt, (long long)CH_NB * Nt,
+                                                  Linv + (size_t)(j0 / CH_NB) * CH_NB * CH_NB, CH_NB,
+                                                  linv_stride, &zero, M + (size_t)j0 * Nt + j0 + jb,
+                                                  (int)Nt, Nt * Nt, nbat));
+        // trailing update C <- C - P P' on the lower block-triangle only (512-column blocks)
+        const long long t0 = (long long)j0 + jb;
+        for (long long cb = t0; cb < Da; cb += 512) {
+          const long long ncb = std::min<long long>(512, Da - cb);
+          const double* Prow = M + (size_t)j0 * Nt + cb;      // P[cb:, :]   [Nt - cb, jb], ld Nt
+          double* C = M + (size_t)cb * Nt + cb;               // C[cb:, cb:cb+ncb]
+          TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)(Nt - cb), (int)ncb, jb,
+                                                    &minus_one, Prow, (int)Nt, Nt * Nt, Prow, (int)Nt, Nt * Nt, &one,
+                                                    C, (int)Nt, Nt * Nt, nbat));
+        }
+      }
+    }
+    if (dbg) cudaEventRecord(ev[2], st);
+    chol_take_y<<<dim3(blocks_for((long long)Da * Dy), nbat), 256, 0, st>>>(M, Nt, Da, Dy, Y);
+    for (int j0 = ((Da - 1) / CH_NB) * CH_NB; j0 >= 0; j0 -= CH_NB) {
+      const int jb = std::min(CH_NB, Da - j0);
+      chol_back<<<dim3(blocks_for(std::max(j0, 1)), nbat, Dy), 256, 0, st>>>(M, Nt, Da, j0, jb, Linv, linv_stride, Y, Xs);
+    }
+    chol_store<<<dim3(blocks_for((long long)Da * Dy), nbat), 256, 0, st>>>(Xs, Da, Dy, W_out + (size_t)l0 * Da * Dy);
+    TD_CHECK_CUDA(cudaGetLastError());
+    if (dbg) {
+      cudaEventRecord(ev[3], st);
+      cudaEventSynchronize(ev[3]);
+      float a, b, c;
+      cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
+      fprintf(stderr, "[tdgram] batched cholesky: build %.3f ms, factor %.3f ms, back-substitution %.3f ms (batch %d, n %d)\n", a, b, c, nbat, Da);
+    }
+  }
+  std::vector<int> hinfo(n_lambda, 0);
+  TD_CHECK_CUDA(cudaMemcpyAsync(hinfo.data(), info, n_lambda * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TD_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (int l = 0; l < n_lambda; ++l)
+    if (hinfo[l] != 0) failed->push_back(l);
+  return TD_OK;
+}
+
+// Cholesky per lambda on already normalised A0 [Da, Da], B0 (column-major [Da, Dy]).
+int td_ridge_solve_scaled(Handles* h, Scratch& sc, cudaStream_t st, const double* A0, const double* B0,
+                          int Da, int Dy, const double* lambdas, int n_lambda, float* W_out) {
+  int rc;
+  const long long nn = (long long)Da * Da, nb = (long long)Da * Dy;
+  double* A;
+  if ((rc = sc.get(nn, &A))) return rc;
   // Cholesky per lambda.  The factorisations are independent: they run on up to MAX_LANES side
   // streams, nothing synchronises with the host until all are queued, and only a lambda whose
   // matrix turned out not to be positive definite is redone with LU (like np.linalg.solve).
@@ -281,6 +460,75 @@ extern "C" int td_ridge_solve(const double* G_aug, const double* C_aug, int Da, 
     to_rowmajor_f32<<<blocks_for(nb), 256, 0, st>>>(Xl, Da, W_out + (size_t)l * nb, Da, Dy);
     TD_CHECK_CUDA(cudaGetLastError());
   }
+  TD_CHECK_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
+}  // namespace
+}  // namespace td
+
+using namespace td;
+
+extern "C" int td_ridge_solve(const double* G_aug, const double* C_aug, int Da, int Dy, double n,
+                              const double* lambdas, int n_lambda, int method, float* W_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_REQUIRE(G_aug && C_aug && lambdas && W_out, "td_ridge_solve: null argument");
+  TD_REQUIRE(Da >= 1 && Dy >= 1 && n_lambda >= 1 && n > 0, "td_ridge_solve: Da=%d Dy=%d n_lambda=%d n=%g", Da, Dy, n_lambda, n);
+  TD_REQUIRE(method >= 0 && method <= 2, "td_ridge_solve: unknown method %d", method);
+  Handles* h;
+  int rc = get_handles(&h);
+  if (rc) return rc;
+  TD_CHECK_SOLVER(cusolverDnSetStream(h->solver, st));
+  TD_CHECK_SOLVER(cublasSetStream(h->blas, st));
+  Scratch sc(st);
+  const long long nn = (long long)Da * Da, nb = (long long)Da * Dy;
+  double *A0, *A, *B0, *X;
+  int* info;
+  if ((rc = sc.get(nn, &A0)) || (rc = sc.get(nn, &A)) || (rc = sc.get(nb, &B0)) || (rc = sc.get(nb, &X)) || (rc = sc.get(1, &info))) return rc;
+  scale_add_diag<<<blocks_for(nn), 256, 0, st>>>(G_aug, A0, Da, 1.0 / n, 0.0);
+  to_colmajor<<<blocks_for(nb), 256, 0, st>>>(C_aug, B0, Da, Dy, 1.0 / n);
+  TD_CHECK_CUDA(cudaGetLastError());
+
+  if (method == 1) {
+    double *w, *Z;
+    if ((rc = sc.get(Da, &w)) || (rc = sc.get(nb, &Z))) return rc;
+    if ((rc = eigh(h, sc, A0, Da, w, info))) return rc;    // A0 now holds V (column-major)
+    int hinfo = 0;
+    TD_CHECK_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TD_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (hinfo != 0) { set_error("td_ridge_solve: syevd did not converge (info %d)", hinfo); return TD_ERR_SOLVER; }
+    const double one = 1.0, zero = 0.0;
+    TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, Da, Dy, Da, &one, A0, Da, B0, Da, &zero, Z, Da));
+    for (int l = 0; l < n_lambda; ++l) {
+      divide_rows<<<blocks_for(nb), 256, 0, st>>>(Z, w, lambdas[l], A /*scratch*/, Da, Dy);
+      TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, Da, Dy, Da, &one, A0, Da, A, Da, &zero, X, Da));
+      to_rowmajor_f32<<<blocks_for(nb), 256, 0, st>>>(X, Da, W_out + (size_t)l * nb, Da, Dy);
+    }
+    TD_CHECK_CUDA(cudaGetLastError());
+    TD_CHECK_CUDA(cudaStreamSynchronize(st));
+    return TD_OK;
+  }
+
+  if (method == 2) {
+    std::vector<int> failed;
+    rc = batched_cholesky_sweep(h, sc, st, A0, B0, Da, Dy, lambdas, n_lambda, W_out, &failed);
+    if (rc) return rc;
+    if (failed.empty()) return TD_OK;
+    // Not positive definite for some lambda: those go through the per-lambda path below (LU).
+    std::vector<double> lam2;
+    for (int l : failed) lam2.push_back(lambdas[l]);
+    float* W2;
+    if ((rc = sc.get((size_t)nb * failed.size(), &W2))) return rc;
+    // (A0 / B0 are already normalised: pass n = 1 through a recursive call on the scaled data.)
+    rc = td_ridge_solve_scaled(h, sc, st, A0, B0, Da, Dy, lam2.data(), (int)lam2.size(), W2);
+    if (rc) return rc;
+    for (size_t i = 0; i < failed.size(); ++i)
+      TD_CHECK_CUDA(cudaMemcpyAsync(W_out + (size_t)failed[i] * nb, W2 + i * nb, nb * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TD_CHECK_CUDA(cudaStreamSynchronize(st));
+    return TD_OK;
+  }
+  rc = td_ridge_solve_scaled(h, sc, st, A0, B0, Da, Dy, lambdas, n_lambda, W_out);
+  if (rc) return rc;
   TD_CHECK_CUDA(cudaStreamSynchronize(st));
   return TD_OK;
 }

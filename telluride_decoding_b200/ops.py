@@ -149,7 +149,7 @@ def lagged_rows(x, seg_keep, out_row, total_rows):
   return out
 
 
-def ridge_solve(g_aug, c_aug, n, lambdas, method=0):
+def ridge_solve(g_aug, c_aug, n, lambdas, method=2):
   """[n_lambda, Da, Dy] float32 solutions of (G/n + lambda I) W = C/n  (brain_model.py:447-479)."""
   _lib.require_cuda()
   lib = _lib.load()

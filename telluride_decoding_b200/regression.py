@@ -101,7 +101,7 @@ def _dropped_rows_stats(train_dataset, is_cca):
 
 
 def jackknife_sweep(test_brain_data, my_flags, regularization_list, test_files=None,
-                    solve_method=1):
+                    solve_method=2):
   """[n_lambda, n_files] matrix of test metrics: one sweep over the data for all folds and
   lambdas.  Fold f trains on `allbut` {f} and tests on f, files in sorted order
   (regression.py:197)."""

@@ -82,7 +82,8 @@ def test_thin_products_and_rows_and_predict():
   x64 = gpu_util.design64(batches)
   y64 = np.concatenate([np.asarray(b[1], dtype=np.float64) for b in batches], axis=0)
   v = np.concatenate([y64, np.ones((y64.shape[0], 1))], axis=1)
-  np.testing.assert_allclose(xtv.cpu().numpy(), x64.T @ v, rtol=1e-10, atol=1e-9)
+  # fp32 products carried into float64 every 32 frames
+  np.testing.assert_allclose(xtv.cpu().numpy(), x64.T @ v, rtol=2e-6, atol=2e-4)
   np.testing.assert_allclose(vtv.cpu().numpy(), v.T @ v, rtol=1e-10, atol=1e-9)
   assert vtv[-1, -1].item() == 1500
   # the lagged rows are bit-identical to the reference's tf.signal.frame layout

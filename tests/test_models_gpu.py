@@ -114,13 +114,34 @@ def test_lambda_sweep_one_factorisation_equals_per_lambda_solves():
   lambdas = np.logspace(-6, 3, 20)
   chol = brain_model.solve_regression(stats, lambdas, method=0)
   eigh = brain_model.solve_regression(stats, lambdas, method=1)
+  sweep = brain_model.solve_regression(stats, lambdas, method=2)     # batched blocked Cholesky
   batches = gpu_util.oracle_batches(x, y, post=post, batch=500)
-  for lam, (w0, b0), (w1, b1) in zip(lambdas, chol, eigh):
+  for lam, (w0, b0), (w1, b1), (w2, b2) in zip(lambdas, chol, eigh, sweep):
     assert gpu_util.rel_fro(w1.cpu().numpy(), w0.cpu().numpy()) < 1e-5
+    assert gpu_util.rel_fro(w2.cpu().numpy(), w0.cpu().numpy()) < 1e-6
+    assert abs(float(b2[0]) - float(b0[0])) < 1e-6
     if lam >= 1e-3:      # the reference's own float32 LU is only trustworthy when conditioned
       w, b, _, _, _ = ora.linear_regressor_from_batches(batches, float(lam))
       assert gpu_util.rel_fro(w0.cpu().numpy(), w) < W_TOL, lam
       assert abs(float(b0[0]) - float(b[0, 0])) < W_TOL
+
+
+def test_batched_sweep_multi_rhs_and_singular_fallback():
+  """Several targets through the batched sweep; lambda = 0 on a rank-deficient design falls back to
+  LU for that lambda only (np.linalg.solve semantics) or reports a singular matrix."""
+  rng = np.random.RandomState(17)
+  n, c = 3000, 70                 # 141 columns: panels of 64 + a ragged last panel
+  x = rng.randn(n, c).astype(np.float32)
+  y = (x[:, :3] @ rng.randn(3, 3) + 0.1 * rng.randn(n, 3)).astype(np.float32)
+  bd = gpu_util.make_test_data(x, y, post_context=1, final_batch_size=300)
+  stats = brain_model.RegressionStats.from_dataset(bd.create_dataset('train'))
+  lambdas = [1e-3, 0.1, 5.0]
+  a = brain_model.solve_regression(stats, lambdas, method=0)
+  b = brain_model.solve_regression(stats, lambdas, method=2)
+  for (w0, b0), (w2, b2) in zip(a, b):
+    assert w2.shape == (140, 3)
+    assert gpu_util.rel_fro(w2.cpu().numpy(), w0.cpu().numpy()) < 1e-6
+    np.testing.assert_allclose(b2.cpu().numpy(), b0.cpu().numpy(), atol=1e-6)
 
 
 def test_multi_trial_interleaved_fit_and_evaluate():
