@@ -79,7 +79,8 @@ typedef struct td_gram_options {
   int32_t chunk_rows;    /* TMEM flush period in frames (0 = default 128) */
   int32_t superchunk_rows; /* L2 working-set period in frames (0 = auto) */
   int32_t max_ctas;      /* 0 = all SMs */
-  int32_t reserved[3];   /* reserved[0] = 1: record CUDA events around the Gram kernel */
+  int32_t reserved[3];   /* reserved[0] = 1: record CUDA events around the Gram kernel;
+                            reserved[1]: operand multicast, 0 auto, 1 off, 2 clusters of two CTA pairs */
 } td_gram_options;
 
 int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_streams,

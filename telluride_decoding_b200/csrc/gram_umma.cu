@@ -61,6 +61,8 @@ struct GramParams {
   long long NK;           // k-tiles in total
   int KS;                 // k-tiles per superchunk
   int chunk_kt;           // k-tiles per TMEM flush
+  int mc;                 // CTA pairs per cluster sharing the A operand by TMA multicast (1 or 2)
+  int experiment;         // development: 1 = skip lo*hi, 2 = hi*hi only (timing experiments, wrong results)
   long long total_steps;  // NSC * ntri * KS
 };
 
@@ -100,11 +102,19 @@ struct WorkIter {
       const long long e = min(b + len, P.NK);
       p += len;
       if (b < e) {
-        int tm = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-        while ((long long)(tm + 1) * (tm + 2) / 2 <= tile) ++tm;
-        while ((long long)tm * (tm + 1) / 2 > tile) --tm;
-        it.tm = tm;
-        it.tn = tile - tm * (tm + 1) / 2;
+        if (P.mc == 1) {
+          int tm = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+          while ((long long)(tm + 1) * (tm + 2) / 2 <= tile) ++tm;
+          while ((long long)tm * (tm + 1) / 2 > tile) --tm;
+          it.tm = tm;
+          it.tn = tile - tm * (tm + 1) / 2;
+        } else {
+          // row tm holds ceil((tm+1)/2) tile pairs (tn0, tn0+1); it.tn = pair index within the row
+          int tm = 0, left = tile;
+          while (left >= (tm + 2) / 2) { left -= (tm + 2) / 2; ++tm; }
+          it.tm = tm;
+          it.tn = left;
+        }
         it.kt_begin = b;
         it.kt_end = e;
         return true;
@@ -131,7 +141,11 @@ __device__ __forceinline__ void zero_outside_frames(uint32_t sbase, int begin, i
 
 // CG = 1: one CTA per 128x128 tile.  CG = 2: a CTA pair (cluster of 2) per 256x256 tile, each CTA
 // staging 128 rows of A and 128 rows of B; the pair leader issues tcgen05.mma.cta_group::2.
-template <int CG>
+// MC = 2: a cluster of two CTA pairs works on the tiles (tm, 2j) and (tm, 2j+1): they need the same
+// A operand, so pair 0 fetches its hi plane and pair 1 its lo plane, each multicast to both pairs.
+// That removes a quarter of the L2 -> SM traffic, which is what bounds the kernel (measured: dropping
+// two of the three MMAs per k-step does not change its duration).
+template <int CG, int MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
                         const __grid_constant__ CUtensorMap tmap1, const GramParams P) {
@@ -154,16 +168,20 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
-  const int worker = blockIdx.x / CG;
-  const int n_workers = gridDim.x / CG;
+  static_assert(MC == 1 || CG == 2, "operand multicast needs CTA pairs");
+  const uint32_t crank = (CG * MC > 1) ? ptx::cluster_ctarank() : 0u;
+  const uint32_t rank = crank & (uint32_t)(CG - 1);      // rank inside the CTA pair
+  const uint32_t pair = crank >> 1;                      // pair inside the cluster (0 if MC == 1)
+  const uint32_t leader = crank & ~1u;                   // cluster rank of this pair's leader
+  const int worker = blockIdx.x / (CG * MC);
+  const int n_workers = gridDim.x / (CG * MC);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap0);
     ptx::prefetch_tmap(&tmap1);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), MC);       // one commit per pair that writes into this stage
       ptx::mbar_init(pready_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -174,7 +192,7 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
   }
   if (warp == 1) ptx::tmem_alloc<CG>(tmem_slot, TMEM_COLS);
   ptx::tc_fence_before();
-  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if constexpr (CG * MC > 1) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -186,13 +204,15 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
       int stage = 0;
       uint32_t phase = 0;
       while (wi.next(P, it)) {
+        const int tile_n = it.tn * MC + (int)pair;
         const int ga = (it.tm * CG + (int)rank) * P.groups_per_tile;
-        const int gb = (it.tn * CG + (int)rank) * P.groups_per_tile;
+        const int gb = (tile_n * CG + (int)rank) * P.groups_per_tile;
+        const uint16_t a_mask = (uint16_t)(0x5u << rank);      // this rank of both pairs
         for (long long kt = it.kt_begin; kt < it.kt_end; ++kt) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const int2 kti = __ldg(&P.ktiles[kt]);
           const uint32_t fb = full_bar(stage);
-          ptx::mbar_expect_tx(fb, STAGE_BYTES);
+          ptx::mbar_expect_tx(fb, P.experiment == 3 ? STAGE_BYTES / 2 : STAGE_BYTES);
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
 #pragma unroll 1
           for (int op = 0; op < 2; ++op) {
@@ -203,8 +223,15 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
               const int4 gd = __ldg(&P.groups[g0 + g]);
               const CUtensorMap* tm = gd.x ? &tmap1 : &tmap0;
               const uint32_t dst = obase + g * P.CB * (BK * 4);
-              ptx::tma_load_3d(dst, tm, fb, kti.x + gd.y, gd.z, 2 * gd.w);                      // hi plane
-              ptx::tma_load_3d(dst + OPERAND_BYTES, tm, fb, kti.x + gd.y, gd.z, 2 * gd.w + 1);  // lo plane
+              if (MC == 2 && op == 0) {
+                // A operand: pair 0 fetches the hi plane, pair 1 the lo plane, both multicast
+                ptx::tma_load_3d_mcast(dst + pair * OPERAND_BYTES, tm, fb, kti.x + gd.y, gd.z,
+                                       2 * gd.w + (int)pair, a_mask);
+              } else {
+                ptx::tma_load_3d(dst, tm, fb, kti.x + gd.y, gd.z, 2 * gd.w);                      // hi plane
+                if (P.experiment != 3)   // (experiment 3: half the ingest, timing only)
+                  ptx::tma_load_3d(dst + OPERAND_BYTES, tm, fb, kti.x + gd.y, gd.z, 2 * gd.w + 1);  // lo plane
+              }
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -222,7 +249,9 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
     int buf = 0;
     uint32_t tphase[2] = {0u, 0u};
     const bool issuer = (CG == 1 || rank == 0);
-    const uint32_t pready_leader0 = (CG == 2) ? ptx::mapa(pready_bar(0), 0) : 0u;
+    const uint32_t pready_leader0 = (CG == 2) ? ptx::mapa(pready_bar(0), leader) : 0u;
+    const uint16_t all_mask = (uint16_t)((1u << (CG * MC)) - 1u);
+    const uint16_t pair_mask = (uint16_t)(0x3u << (2 * pair));
     while (wi.next(P, it)) {
       for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
         const long long c1 = min(it.kt_end, c0 + (long long)P.chunk_kt);
@@ -259,11 +288,11 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
                 const uint64_t adv = (uint64_t)(ks * 2);   // 8 frames = 32 B = 2 x 16 B
                 const uint32_t acc = (kt > c0 || ks > ks0) ? 1u : 0u;
                 ptx::mma_tf32<CG>(d, a_hi + adv, b_hi + adv, IDESC, acc);
-                ptx::mma_tf32<CG>(d, a_hi + adv, b_lo + adv, IDESC, 1u);
-                ptx::mma_tf32<CG>(d, a_lo + adv, b_hi + adv, IDESC, 1u);
+                if (P.experiment < 2) ptx::mma_tf32<CG>(d, a_hi + adv, b_lo + adv, IDESC, 1u);
+                if (P.experiment < 1) ptx::mma_tf32<CG>(d, a_lo + adv, b_hi + adv, IDESC, 1u);
               }
-              ptx::mma_commit<CG>(empty_bar(stage));          // stage reusable once these retire
-              if (kt == c1 - 1) ptx::mma_commit<CG>(tfull_bar(buf));
+              ptx::mma_commit<CG>(empty_bar(stage), all_mask);   // stage reusable once these retire
+              if (kt == c1 - 1) ptx::mma_commit<CG>(tfull_bar(buf), pair_mask);
             }
             __syncwarp();
           }
@@ -282,7 +311,7 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
     WorkItem it;
     int buf = 0;
     uint32_t fphase[2] = {0u, 0u};
-    const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+    const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), leader) : tempty_bar(0);
     float acc[NACC];
     while (wi.next(P, it)) {
 #pragma unroll
@@ -311,9 +340,11 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
       }
       // Tile (tm, tn), tm >= tn: element (m, n) is stored at G[n][m] (upper triangle) so that the
       // 32 lanes of a warp (consecutive m) write consecutive addresses.
+      const int tile_n = it.tn * MC + (int)pair;
+      if (tile_n > it.tm) continue;              // the odd tile of a row's last pair: nothing to store
       const int m_row = (it.tm * CG + (int)rank) * TILE_ROWS + quad * 32 + lane;
       const int m_out = __ldg(&P.out_idx[m_row]);
-      const int n_row0 = it.tn * BN + half * NACC;
+      const int n_row0 = tile_n * BN + half * NACC;
 #pragma unroll
       for (int i = 0; i < NACC; ++i) {
         const int n_row = n_row0 + i;
@@ -325,7 +356,7 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
   }
 
   ptx::tc_fence_before();
-  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if constexpr (CG * MC > 1) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);
 }
 
@@ -336,7 +367,8 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
 // d is read from pair (d mod 4) at the 16-byte aligned coordinate d - (d mod 4): TMA box origins
 // must be 16-byte aligned along the contiguous dimension.
 __global__ void stage_split_kernel(StreamView s, const int64_t* __restrict__ seg_off, int seg0,
-                                   float* __restrict__ planes, int64_t Tp, int Cpad, int n_shift) {
+                                   float* __restrict__ planes, int64_t Tp, int Cpad, int n_shift,
+                                   int raw_hi) {
   __shared__ float tile[32][33];
   const int seg = seg0 + blockIdx.y;
   const int64_t len = s.seg_len[seg];
@@ -358,12 +390,20 @@ __global__ void stage_split_kernel(StreamView s, const int64_t* __restrict__ seg
     if (c < s.channels && t < len) {
       const float v = tile[threadIdx.x][r];
       uint32_t hb, lb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-      const float hi = __uint_as_float(hb);
+      float hi;
+      if (raw_hi) {
+        // experiment: hi plane = raw fp32 (the tensor core is expected to ignore the 13 low mantissa
+        // bits, i.e. truncate), lo = tf32(x - trunc(x))
+        hb = __float_as_uint(v);
+        hi = __uint_as_float(hb & 0xFFFFE000u);
+      } else {
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+        hi = __uint_as_float(hb);
+      }
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
       const int64_t o = (int64_t)c * Tp + seg_off[seg] + t;
       for (int sh = 0; sh < n_shift; ++sh) {
-        planes[(2 * sh) * plane + o - sh] = hi;
+        planes[(2 * sh) * plane + o - sh] = __uint_as_float(hb);
         planes[(2 * sh + 1) * plane + o - sh] = __uint_as_float(lb);
       }
     }
@@ -394,7 +434,7 @@ __global__ void symmetrize_kernel(float* __restrict__ G, int64_t n, int64_t ldg,
 // Host-side plan.
 // ---------------------------------------------------------------------------------------------
 struct GramPlan {
-  int n_streams = 0, CB = 0, cg = 1, n_seg = 0, n_shift = 4;
+  int n_streams = 0, CB = 0, cg = 1, mc = 1, n_seg = 0, n_shift = 4;
   int L[2] = {0, 0}, C[2] = {0, 0}, Cpad[2] = {0, 0}, pre[2] = {0, 0};
   int64_t Tp = 0, Dz = 0, Dpad = 0, NK = 0;
   int nt = 0, ntri = 0, n_groups = 0, tile = 0;
@@ -453,9 +493,21 @@ int make_plan(const td_stream* streams, int n_streams, const int64_t* seg_first,
   pl->cg = cg;
   pl->tile = TILE_ROWS * cg;
   pl->Dpad = round_up(n_groups * cb, pl->tile);
-  pl->n_groups = (int)(pl->Dpad / cb);
   pl->nt = (int)(pl->Dpad / pl->tile);
-  pl->ntri = pl->nt * (pl->nt + 1) / 2;
+  // Two CTA pairs per cluster share the A operand by multicast once there are enough tiles.
+  int mc = opt ? opt->reserved[1] : 0;          // 0 = auto, 1 = off, 2 = on
+  if (mc == 0) mc = (cg == 2 && pl->nt >= 4) ? 2 : 1;
+  { const char* e = getenv("TD_GRAM_MC"); if (e && (e[0] == '1' || e[0] == '2')) mc = e[0] - '0'; }
+  if (cg != 2) mc = 1;
+  pl->mc = mc;
+  // tables carry one extra (all padding) tile: the odd tile of a row's last pair reads it
+  pl->n_groups = (int)((pl->Dpad + pl->tile) / cb);
+  if (mc == 1) {
+    pl->ntri = pl->nt * (pl->nt + 1) / 2;
+  } else {
+    pl->ntri = 0;                                // tile PAIRS in the lower triangle
+    for (int tm = 0; tm < pl->nt; ++tm) pl->ntri += (tm + 2) / 2;
+  }
   TD_REQUIRE(pl->Dpad < (1LL << 30), "td_lagged_gram: design too wide");
 
   // Segment placement in staged time: zero gap >= halo between segments, 32-frame aligned starts.
@@ -483,7 +535,7 @@ int make_plan(const td_stream* streams, int n_streams, const int64_t* seg_first,
   }
   pl->off_groups = off;  off += (size_t)round_up((int64_t)pl->n_groups * sizeof(int4), 1024);
   pl->off_ktiles = off;  off += (size_t)round_up(std::max<int64_t>(nk, 1) * sizeof(int2), 1024);
-  pl->off_outidx = off;  off += (size_t)round_up(pl->Dpad * sizeof(int), 1024);
+  pl->off_outidx = off;  off += (size_t)round_up((pl->Dpad + pl->tile) * sizeof(int), 1024);
   pl->off_segoff = off;  off += (size_t)round_up((int64_t)n_seg * sizeof(int64_t), 1024);
   pl->off_segtab = off;  off += (size_t)round_up((int64_t)n_seg * 2 * n_streams * sizeof(int64_t), 1024);
   pl->total = off;
@@ -619,7 +671,7 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
 
   // ---- tables -------------------------------------------------------------------------------
   std::vector<int4> groups(pl.n_groups);
-  std::vector<int> out_idx(pl.Dpad, -1);
+  std::vector<int> out_idx(pl.Dpad + pl.tile, -1);
   {
     int g = 0;
     int64_t col0 = 0;
@@ -683,7 +735,8 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
         dim3 grid((unsigned)ceil_div(maxlen, 32), (unsigned)std::min(32768, n_seg - s0),
                   (unsigned)ceil_div(pl.C[q], 32));
         stage_split_kernel<<<grid, dim3(32, 8), 0, st>>>(
-            sv, reinterpret_cast<const int64_t*>(ws + pl.off_segoff), s0, planes, pl.Tp, pl.Cpad[q], pl.n_shift);
+            sv, reinterpret_cast<const int64_t*>(ws + pl.off_segoff), s0, planes, pl.Tp, pl.Cpad[q], pl.n_shift,
+            getenv("TD_RAW_HI") ? 1 : 0);
         TD_CHECK_CUDA(cudaGetLastError());
       }
     }
@@ -708,6 +761,7 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
     P.NK = pl.NK;
     int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 128;
     P.chunk_kt = std::max(1, chunk_rows / BK);
+    { const char* e = getenv("TD_EXPERIMENT"); P.experiment = e ? atoi(e) : 0; }
     // Superchunk: the staged frames all tiles sweep together; sized to stay L2 resident (~24 MB).
     int64_t sc_rows = (opt && opt->superchunk_rows > 0) ? opt->superchunk_rows : 0;
     if (sc_rows == 0) {
@@ -733,24 +787,38 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       }
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
+    P.mc = pl.mc;
     if (pl.cg == 1) {
-      TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-      lagged_gram_umma_kernel<1><<<workers, NUM_THREADS, SMEM_BYTES, st>>>(tmaps[0], tmaps[1], P);
+      TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      lagged_gram_umma_kernel<1, 1><<<workers, NUM_THREADS, SMEM_BYTES, st>>>(tmaps[0], tmaps[1], P);
     } else {
-      TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      const int csize = 2 * pl.mc;
+      auto kern = (pl.mc == 2) ? lagged_gram_umma_kernel<2, 2> : lagged_gram_umma_kernel<2, 1>;
+      TD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(workers * 2);
       cfg.blockDim = dim3(NUM_THREADS);
       cfg.dynamicSmemBytes = SMEM_BYTES;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.x = csize;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lagged_gram_umma_kernel<2>, tmaps[0], tmaps[1], P));
+      int n_clusters = sms / csize;
+      if (csize > 2) {
+        // clusters of 4 cannot use every SM (GPC sizes): ask how many are co-resident
+        cfg.gridDim = dim3(sms / csize * csize);
+        int max_clusters = 0;
+        TD_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+        n_clusters = std::max(1, std::min(n_clusters, max_clusters));
+      }
+      if (opt && opt->max_ctas > 0) n_clusters = std::max(1, std::min(n_clusters, opt->max_ctas / csize));
+      n_clusters = (int)std::max<int64_t>(1, std::min<int64_t>(n_clusters, ceil_div((int64_t)pl.ntri * ks, P.chunk_kt)));
+      workers = n_clusters;
+      cfg.gridDim = dim3(n_clusters * csize);
+      TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmaps[0], tmaps[1], P));
     }
     TD_CHECK_CUDA(cudaGetLastError());
     if (timed) {
@@ -758,8 +826,8 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       g_ev_valid = true;
     }
     if (debug_enabled())
-      fprintf(stderr, "[tdgram] gram launch: cg=%d workers=%d CB=%d Dz=%lld Dpad=%lld ntri=%d NK=%lld KS=%d chunk_kt=%d total=%lld Tp=%lld\n",
-              pl.cg, workers, pl.CB, (long long)pl.Dz, (long long)pl.Dpad, pl.ntri, (long long)pl.NK, P.KS, P.chunk_kt,
+      fprintf(stderr, "[tdgram] gram launch: mc=%d cg=%d workers=%d CB=%d Dz=%lld Dpad=%lld ntri=%d NK=%lld KS=%d chunk_kt=%d total=%lld Tp=%lld\n",
+              pl.mc, pl.cg, workers, pl.CB, (long long)pl.Dz, (long long)pl.Dpad, pl.ntri, (long long)pl.NK, P.KS, P.chunk_kt,
               (long long)P.total_steps, (long long)pl.Tp);
     if ((rc = debug_sync(st, "gram kernel"))) return rc;
   }

@@ -108,6 +108,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Multicast form: the box lands at the same shared-memory offset of every CTA in cta_mask and
+// completes on the barrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_3d_mcast(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                  int c0, int c1, int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
 // Same, CTA-pair form: data lands in this CTA, completion may signal the pair leader's barrier.
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* m,
                                                  uint32_t cluster_bar, int c0, int c1, int c2) {
@@ -172,16 +182,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
 
 // All previously issued MMAs of this thread arrive (once) on `bar` when they retire.
 template <int CG>
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
+__device__ __forceinline__ void mma_commit(uint32_t bar, uint16_t cta_mask = 3) {
   if constexpr (CG == 1) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
   } else {
-    // Same barrier offset in both CTAs of the pair.
+    // Same barrier offset in every CTA of the cluster named by cta_mask.
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
         " [%0], %1;" ::"r"(bar),
-        "h"((uint16_t)3)
+        "h"(cta_mask)
         : "memory");
   }
 }
