@@ -68,8 +68,9 @@ int td_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *
  * The design is Z = [X_0 | X_1 | ...] over n_streams (1 or 2) lagged streams sharing the
  * segment table; G = Z'Z, [Dz, Dz] with Dz = sum_q channels_q * (pre_q+1+post_q), full
- * symmetric, row stride ldg.  method 0: tcgen05 3xTF32 implicit-Hankel kernel (TMA-staged,
- * TMEM fp32 accumulation flushed every `chunk_rows` frames into fp32 registers);
+ * symmetric, row stride ldg.  method 0: tcgen05 3xTF32 implicit-Hankel kernel (raw tiles TMA-staged,
+ * hi/lo split built in shared memory, TMEM fp32 accumulation flushed every `chunk_rows` frames
+ * into fp32 registers);
  * method 1: fp32 CUDA-core kernel kept as an on-device cross-check.
  * Workspace: td_lagged_gram_workspace_bytes bytes of device memory.
  * ------------------------------------------------------------------------------------- */
@@ -79,8 +80,7 @@ typedef struct td_gram_options {
   int32_t chunk_rows;    /* TMEM flush period in frames (0 = default 128) */
   int32_t superchunk_rows; /* L2 working-set period in frames (0 = auto) */
   int32_t max_ctas;      /* 0 = all SMs */
-  int32_t reserved[3];   /* reserved[0] = 1: record CUDA events around the Gram kernel;
-                            reserved[1]: operand multicast, 0 auto, 1 off, 2 clusters of two CTA pairs */
+  int32_t reserved[3];   /* reserved[0] = 1: record CUDA events around the Gram kernel */
 } td_gram_options;
 
 int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_streams,

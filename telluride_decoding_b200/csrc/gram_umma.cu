@@ -4,20 +4,27 @@
 // lagged design (telluride_decoding/brain_model.py:429-444, cca.py:311-332; the design itself is
 // built by brain_data.py:446-455).  Here the design Z = [X_0 | X_1] never exists:
 //
-//   1. stage:  every raw stream [T, C] (time-major) is rewritten once as two channel-major
-//      planes hi = tf32(x), lo = tf32(x - hi), segments separated by >= (pre+post) zero frames.
-//      Row (stream q, lag k, channel c) of Z' is then the staged row c read at a time shift of
-//      (k - pre): a plain TMA box at a shifted coordinate.  Zero padding at segment edges comes
-//      from the zero gaps / TMA out-of-bounds fill.
+//   1. stage:  every raw stream [T, C] (time-major) is rewritten once channel-major (4 copies,
+//      advanced by 0..3 frames, so that every lag is a 16-byte aligned TMA box origin), segments
+//      separated by >= (pre+post) zero frames.  Row (stream q, lag k, channel c) of Z' is then the
+//      staged row c read at a time shift of (k - pre): a plain TMA box at a shifted coordinate.
+//      Zero padding at segment edges comes from the zero gaps / TMA out-of-bounds fill.
 //   2. gram:   persistent warp-specialised kernel.  K dimension = time, cut into 32-frame
 //      k-tiles; M/N = rows of Z' in 128-row operand tiles made of CB-channel TMA boxes.
-//      Per k-tile and operand the producer lands hi and lo tiles (K-major, 128B swizzle) and one
-//      thread issues hi*hi + hi*lo + lo*hi tcgen05.mma (kind::tf32) into a TMEM accumulator.
-//      Every `chunk` k-tiles the accumulator is drained by the epilogue warps into fp32
-//      registers (round-to-nearest adds; bounds the tensor-core accumulation length), while the
-//      MMA warp continues in the second TMEM buffer.  Work = (superchunk, lower-triangle tile,
-//      k-range) linearised and split evenly over CTAs (stream-K); partial tiles are combined with
-//      fp32 red.add into G.  Rows >= keep of a segment tail k-tile are zeroed in shared memory.
+//        warp 0      TMA producer: lands the RAW fp32 tiles (K-major, 128B swizzle), 3-stage ring
+//        warps 10-11 converters: build the 3xTF32 split in shared memory once per staged tile --
+//                    hi is the raw tile itself (kind::tf32 ignores the 13 low mantissa bits, i.e.
+//                    truncates; verified on B200), lo = tf32_rna(x - trunc(x)) goes to a second
+//                    tile; they also zero the frames of a k-tile that are not design rows of this
+//                    call.  Only half of the operand bytes cross L2 -> SM this way; with both
+//                    planes staged in HBM the kernel was bound by that ingest (measured: dropping
+//                    two of three MMAs did not change its duration, halving the TMA bytes did).
+//        warp 1      issues hi*hi + hi*lo + lo*hi tcgen05.mma (kind::tf32) into a TMEM accumulator
+//        warps 2-9   epilogue: every `chunk` k-tiles the accumulator is drained into fp32 registers
+//                    (round-to-nearest adds; bounds the tensor-core accumulation length), while the
+//                    MMA warp continues in the second TMEM buffer.
+//      Work = (superchunk, lower-triangle tile, k-range) split evenly over CTAs (stream-K); partial
+//      tiles are combined with fp32 red.add into G.
 //   3. the computed triangle is mirrored by td_symmetrize_f32.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -43,14 +50,19 @@ constexpr int BK = 32;                       // frames per k-tile (one 128-byte 
 constexpr int TILE_ROWS = 128;               // operand rows per CTA
 constexpr int STAGES = 3;
 constexpr int OPERAND_BYTES = TILE_ROWS * BK * 4;       // 16 KiB
-constexpr int STAGE_BYTES = 4 * OPERAND_BYTES;          // A_hi, A_lo, B_hi, B_lo
-constexpr int NUM_THREADS = 320;             // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue
+constexpr int STAGE_BYTES = 4 * OPERAND_BYTES;          // A_raw(hi), A_lo, B_raw(hi), B_lo
+constexpr int TMA_BYTES = 2 * OPERAND_BYTES;            // what the producer lands per stage
+#ifndef TD_CONV_WARPS
+#define TD_CONV_WARPS 2
+#endif
+constexpr int NUM_CONV_WARPS = TD_CONV_WARPS;     // converter warps (half of them per operand)
+constexpr int NUM_THREADS = 320 + 32 * NUM_CONV_WARPS;   // warp 0 TMA, warp 1 MMA/TMEM, warps 2..9 epilogue, 10.. converters
 constexpr int NUM_EPI_WARPS = 8;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-static_assert(8 * (3 * STAGES + 4) + 8 <= 256, "barrier block too small");
+static_assert(8 * (4 * STAGES + 4) + 8 <= 256, "barrier block too small");
 
 struct GramParams {
-  const int4* groups;     // [n_groups_pad] {stream, aligned time shift, first channel, shift plane}
+  const int4* groups;     // [n_groups] {stream, aligned time shift, first channel, shift plane}
   const int2* ktiles;     // [NK] {staged time of design row 0 of the tile, begin | end << 8}: rows [begin, end) exist
   const int* out_idx;     // [Dpad] tile-space row -> row/col of G, -1 for padding
   float* G;
@@ -61,8 +73,6 @@ struct GramParams {
   long long NK;           // k-tiles in total
   int KS;                 // k-tiles per superchunk
   int chunk_kt;           // k-tiles per TMEM flush
-  int mc;                 // CTA pairs per cluster sharing the A operand by TMA multicast (1 or 2)
-  int experiment;         // development: 1 = skip lo*hi, 2 = hi*hi only (timing experiments, wrong results)
   long long total_steps;  // NSC * ntri * KS
 };
 
@@ -102,19 +112,11 @@ struct WorkIter {
       const long long e = min(b + len, P.NK);
       p += len;
       if (b < e) {
-        if (P.mc == 1) {
-          int tm = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-          while ((long long)(tm + 1) * (tm + 2) / 2 <= tile) ++tm;
-          while ((long long)tm * (tm + 1) / 2 > tile) --tm;
-          it.tm = tm;
-          it.tn = tile - tm * (tm + 1) / 2;
-        } else {
-          // row tm holds ceil((tm+1)/2) tile pairs (tn0, tn0+1); it.tn = pair index within the row
-          int tm = 0, left = tile;
-          while (left >= (tm + 2) / 2) { left -= (tm + 2) / 2; ++tm; }
-          it.tm = tm;
-          it.tn = left;
-        }
+        int tm = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+        while ((long long)(tm + 1) * (tm + 2) / 2 <= tile) ++tm;
+        while ((long long)tm * (tm + 1) / 2 > tile) --tm;
+        it.tm = tm;
+        it.tn = tile - tm * (tm + 1) / 2;
         it.kt_begin = b;
         it.kt_end = e;
         return true;
@@ -123,17 +125,47 @@ struct WorkIter {
   }
 };
 
-// Zero the frames outside [begin, end) of every row of the four operand tiles of one stage
-// (K-major, 128-byte swizzle: element t of row r sits in 16-byte chunk (t/4) ^ (r%8)).  One warp.
-__device__ __forceinline__ void zero_outside_frames(uint32_t sbase, int begin, int end, int lane) {
-  for (int r = lane; r < 4 * TILE_ROWS; r += 32) {
-    const uint32_t rowaddr = sbase + r * (BK * 4);
-    for (int t = 0; t < BK; ++t) {
-      if (t >= begin && t < end) continue;
-      const uint32_t a = rowaddr + ((((uint32_t)t >> 2) ^ ((uint32_t)r & 7u)) << 4) +
-                         (((uint32_t)t & 3u) << 2);
-      asm volatile("st.shared::cta.b32 [%0], %1;" ::"r"(a), "r"(0u) : "memory");
+// One converter warp turns the raw tile of one operand (16 KiB, K-major, 128-byte swizzle: frame t
+// of row r sits in 16-byte chunk (t/4) ^ (r%8)) into its lo tile, lo = tf32_rna(x - trunc_tf32(x)),
+// at the same offsets.  The raw tile doubles as the hi operand: kind::tf32 reads only the upper 19
+// bits.  Frames outside [begin, end) are not design rows of this call (end of trial, rows lost to
+// drop_remainder, brain_data.py:369-370, or another rank's share): they are zeroed in both tiles.
+__device__ __forceinline__ void split_tile(uint32_t raw, uint32_t lo, int begin, int end, int lane,
+                                           int part, int n_parts) {
+  const bool partial = begin > 0 || end < BK;
+  const int per_part = OPERAND_BYTES / 16 / 32 / n_parts;
+#pragma unroll 4
+  for (int i = part * per_part; i < (part + 1) * per_part; ++i) {
+    const uint32_t off = (uint32_t)(i * 32 + lane) * 16u;
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(raw + off));
+    if (partial) {
+      const uint32_t r = off >> 7;
+      const int t0 = (int)((((off >> 4) & 7u) ^ (r & 7u)) << 2);
+      const bool k0 = t0 >= begin && t0 < end, k1 = t0 + 1 >= begin && t0 + 1 < end;
+      const bool k2 = t0 + 2 >= begin && t0 + 2 < end, k3 = t0 + 3 >= begin && t0 + 3 < end;
+      if (!(k0 && k1 && k2 && k3)) {
+        v.x = k0 ? v.x : 0.0f; v.y = k1 ? v.y : 0.0f; v.z = k2 ? v.z : 0.0f; v.w = k3 ? v.w : 0.0f;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raw + off), "f"(v.x), "f"(v.y),
+                     "f"(v.z), "f"(v.w) : "memory");
+      }
     }
+    float4 l;
+    {
+      // x - trunc(x) is exact in fp32; adding half an ulp of tf32 to the magnitude bits and
+      // clearing the 13 low bits is round-to-nearest (ties away), i.e. cvt.rna.tf32.f32.
+      const float dx = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+      const float dy = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+      const float dz = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+      const float dw = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+      l.x = __uint_as_float((__float_as_uint(dx) + 0x1000u) & 0xFFFFE000u);
+      l.y = __uint_as_float((__float_as_uint(dy) + 0x1000u) & 0xFFFFE000u);
+      l.z = __uint_as_float((__float_as_uint(dz) + 0x1000u) & 0xFFFFE000u);
+      l.w = __uint_as_float((__float_as_uint(dw) + 0x1000u) & 0xFFFFE000u);
+    }
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + off), "f"(l.x), "f"(l.y),
+                 "f"(l.z), "f"(l.w) : "memory");
   }
   ptx::fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor-core proxy
   __syncwarp();
@@ -141,11 +173,7 @@ __device__ __forceinline__ void zero_outside_frames(uint32_t sbase, int begin, i
 
 // CG = 1: one CTA per 128x128 tile.  CG = 2: a CTA pair (cluster of 2) per 256x256 tile, each CTA
 // staging 128 rows of A and 128 rows of B; the pair leader issues tcgen05.mma.cta_group::2.
-// MC = 2: a cluster of two CTA pairs works on the tiles (tm, 2j) and (tm, 2j+1): they need the same
-// A operand, so pair 0 fetches its hi plane and pair 1 its lo plane, each multicast to both pairs.
-// That removes a quarter of the L2 -> SM traffic, which is what bounds the kernel (measured: dropping
-// two of the three MMAs per k-step does not change its duration).
-template <int CG, int MC>
+template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
                         const __grid_constant__ CUtensorMap tmap1, const GramParams P) {
@@ -157,31 +185,29 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // TMA bytes of this CTA
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };     // MMAs of the stage retired
-  auto pready_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };  // leader: peer stage ready
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (3 * STAGES + 4);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // raw tiles landed (TMA)
+  auto conv_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };      // lo tiles built
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); }; // MMAs of the stage retired
+  auto pready_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + s); };  // leader: peer stage ready
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (4 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (4 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (4 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
       smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  static_assert(MC == 1 || CG == 2, "operand multicast needs CTA pairs");
-  const uint32_t crank = (CG * MC > 1) ? ptx::cluster_ctarank() : 0u;
-  const uint32_t rank = crank & (uint32_t)(CG - 1);      // rank inside the CTA pair
-  const uint32_t pair = crank >> 1;                      // pair inside the cluster (0 if MC == 1)
-  const uint32_t leader = crank & ~1u;                   // cluster rank of this pair's leader
-  const int worker = blockIdx.x / (CG * MC);
-  const int n_workers = gridDim.x / (CG * MC);
+  const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+  const int worker = blockIdx.x / CG;
+  const int n_workers = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap0);
     ptx::prefetch_tmap(&tmap1);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), MC);       // one commit per pair that writes into this stage
+      ptx::mbar_init(conv_bar(s), NUM_CONV_WARPS);
+      ptx::mbar_init(empty_bar(s), 1);
       ptx::mbar_init(pready_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -192,7 +218,7 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
   }
   if (warp == 1) ptx::tmem_alloc<CG>(tmem_slot, TMEM_COLS);
   ptx::tc_fence_before();
-  if constexpr (CG * MC > 1) ptx::cluster_sync(); else __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -204,15 +230,13 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
       int stage = 0;
       uint32_t phase = 0;
       while (wi.next(P, it)) {
-        const int tile_n = it.tn * MC + (int)pair;
         const int ga = (it.tm * CG + (int)rank) * P.groups_per_tile;
-        const int gb = (tile_n * CG + (int)rank) * P.groups_per_tile;
-        const uint16_t a_mask = (uint16_t)(0x5u << rank);      // this rank of both pairs
+        const int gb = (it.tn * CG + (int)rank) * P.groups_per_tile;
         for (long long kt = it.kt_begin; kt < it.kt_end; ++kt) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const int2 kti = __ldg(&P.ktiles[kt]);
           const uint32_t fb = full_bar(stage);
-          ptx::mbar_expect_tx(fb, P.experiment == 3 ? STAGE_BYTES / 2 : STAGE_BYTES);
+          ptx::mbar_expect_tx(fb, TMA_BYTES);
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
 #pragma unroll 1
           for (int op = 0; op < 2; ++op) {
@@ -221,27 +245,38 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
 #pragma unroll 1
             for (int g = 0; g < P.groups_per_tile; ++g) {
               const int4 gd = __ldg(&P.groups[g0 + g]);
-              const CUtensorMap* tm = gd.x ? &tmap1 : &tmap0;
-              const uint32_t dst = obase + g * P.CB * (BK * 4);
-              if (MC == 2 && op == 0) {
-                // A operand: pair 0 fetches the hi plane, pair 1 the lo plane, both multicast
-                ptx::tma_load_3d_mcast(dst + pair * OPERAND_BYTES, tm, fb, kti.x + gd.y, gd.z,
-                                       2 * gd.w + (int)pair, a_mask);
-              } else {
-                ptx::tma_load_3d(dst, tm, fb, kti.x + gd.y, gd.z, 2 * gd.w);                      // hi plane
-                if (P.experiment != 3)   // (experiment 3: half the ingest, timing only)
-                  ptx::tma_load_3d(dst + OPERAND_BYTES, tm, fb, kti.x + gd.y, gd.z, 2 * gd.w + 1);  // lo plane
-              }
+              ptx::tma_load_3d(obase + g * P.CB * (BK * 4), gd.x ? &tmap1 : &tmap0, fb, kti.x + gd.y,
+                               gd.z, gd.w);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
+  } else if (warp >= 2 + NUM_EPI_WARPS) {
+    // ===================== converters: raw tile -> lo tile (+ row masking) =====================
+    constexpr int PER_OP = NUM_CONV_WARPS / 2;
+    const int cw = warp - (2 + NUM_EPI_WARPS);
+    const int op = cw / PER_OP;                         // 0: A operand, 1: B operand
+    const int part = cw % PER_OP;
+    WorkIter wi(P, worker, n_workers);
+    WorkItem it;
+    int stage = 0;
+    uint32_t phase = 0;
+    while (wi.next(P, it)) {
+      for (long long kt = it.kt_begin; kt < it.kt_end; ++kt) {
+        const int range = __ldg(&P.ktiles[kt]).y;
+        const uint32_t raw = smem_base + stage * STAGE_BYTES + op * 2 * OPERAND_BYTES;
+        ptx::mbar_wait(full_bar(stage), phase);
+        split_tile(raw, raw + OPERAND_BYTES, range & 0xff, range >> 8, lane, part, PER_OP);
+        if (lane == 0) ptx::mbar_arrive(conv_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
   } else if (warp == 1) {
     // ===================== MMA warp =====================
-    // Every CTA waits for its own stage and zeroes segment-tail frames; with CG == 2 the peer then
-    // reports the stage to the leader (remote mbarrier arrive) and only the leader issues MMAs.
+    // With CG == 2 the peer reports each converted stage to the leader (remote mbarrier arrive) and
+    // only the leader issues MMAs.
     WorkIter wi(P, worker, n_workers);
     WorkItem it;
     int stage = 0;
@@ -249,9 +284,7 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
     int buf = 0;
     uint32_t tphase[2] = {0u, 0u};
     const bool issuer = (CG == 1 || rank == 0);
-    const uint32_t pready_leader0 = (CG == 2) ? ptx::mapa(pready_bar(0), leader) : 0u;
-    const uint16_t all_mask = (uint16_t)((1u << (CG * MC)) - 1u);
-    const uint16_t pair_mask = (uint16_t)(0x3u << (2 * pair));
+    const uint32_t pready_leader0 = (CG == 2) ? ptx::mapa(pready_bar(0), 0) : 0u;
     while (wi.next(P, it)) {
       for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
         const long long c1 = min(it.kt_end, c0 + (long long)P.chunk_kt);
@@ -263,11 +296,7 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
           const int range = __ldg(&P.ktiles[kt]).y;
           const int begin = range & 0xff, end = range >> 8;
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
-          ptx::mbar_wait(full_bar(stage), phase);
-          // Frames outside [begin, end) of a k-tile are not design rows of this call (end of
-          // trial, rows lost to drop_remainder, brain_data.py:369-370, or another rank's share
-          // of the trial): zero them in both operands.
-          if (begin > 0 || end < BK) zero_outside_frames(sbase, begin, end, lane);
+          ptx::mbar_wait(conv_bar(stage), phase);
           if constexpr (CG == 2) {
             if (!issuer) {
               if (lane == 0) ptx::mbar_arrive_cluster(pready_leader0 + 8u * stage);
@@ -288,11 +317,11 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
                 const uint64_t adv = (uint64_t)(ks * 2);   // 8 frames = 32 B = 2 x 16 B
                 const uint32_t acc = (kt > c0 || ks > ks0) ? 1u : 0u;
                 ptx::mma_tf32<CG>(d, a_hi + adv, b_hi + adv, IDESC, acc);
-                if (P.experiment < 2) ptx::mma_tf32<CG>(d, a_hi + adv, b_lo + adv, IDESC, 1u);
-                if (P.experiment < 1) ptx::mma_tf32<CG>(d, a_lo + adv, b_hi + adv, IDESC, 1u);
+                ptx::mma_tf32<CG>(d, a_hi + adv, b_lo + adv, IDESC, 1u);
+                ptx::mma_tf32<CG>(d, a_lo + adv, b_hi + adv, IDESC, 1u);
               }
-              ptx::mma_commit<CG>(empty_bar(stage), all_mask);   // stage reusable once these retire
-              if (kt == c1 - 1) ptx::mma_commit<CG>(tfull_bar(buf), pair_mask);
+              ptx::mma_commit<CG>(empty_bar(stage));          // stage reusable once these retire
+              if (kt == c1 - 1) ptx::mma_commit<CG>(tfull_bar(buf));
             }
             __syncwarp();
           }
@@ -311,7 +340,7 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
     WorkItem it;
     int buf = 0;
     uint32_t fphase[2] = {0u, 0u};
-    const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), leader) : tempty_bar(0);
+    const uint32_t tempty_leader0 = (CG == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
     float acc[NACC];
     while (wi.next(P, it)) {
 #pragma unroll
@@ -340,11 +369,9 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
       }
       // Tile (tm, tn), tm >= tn: element (m, n) is stored at G[n][m] (upper triangle) so that the
       // 32 lanes of a warp (consecutive m) write consecutive addresses.
-      const int tile_n = it.tn * MC + (int)pair;
-      if (tile_n > it.tm) continue;              // the odd tile of a row's last pair: nothing to store
       const int m_row = (it.tm * CG + (int)rank) * TILE_ROWS + quad * 32 + lane;
       const int m_out = __ldg(&P.out_idx[m_row]);
-      const int n_row0 = tile_n * BN + half * NACC;
+      const int n_row0 = it.tn * BN + half * NACC;
 #pragma unroll
       for (int i = 0; i < NACC; ++i) {
         const int n_row = n_row0 + i;
@@ -356,19 +383,18 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
   }
 
   ptx::tc_fence_before();
-  if constexpr (CG * MC > 1) ptx::cluster_sync(); else __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage: raw [T, C] time-major  ->  planes[2][Cpad][Tp] channel-major, hi / lo tf32 split.
+// Stage: raw [T, C] time-major  ->  planes[n_shift][Cpad][Tp] channel-major (raw fp32).
 // ---------------------------------------------------------------------------------------------
-// With n_shift = 4 every plane pair s holds the stream advanced by s frames, so that a lag shift
-// d is read from pair (d mod 4) at the 16-byte aligned coordinate d - (d mod 4): TMA box origins
-// must be 16-byte aligned along the contiguous dimension.
-__global__ void stage_split_kernel(StreamView s, const int64_t* __restrict__ seg_off, int seg0,
-                                   float* __restrict__ planes, int64_t Tp, int Cpad, int n_shift,
-                                   int raw_hi) {
+// Plane s holds the stream advanced by s frames, so that a lag shift d is read from plane (d mod 4)
+// at the 16-byte aligned coordinate d - (d mod 4): TMA box origins must be 16-byte aligned along
+// the contiguous dimension (measured: an unaligned origin raises "illegal instruction").
+__global__ void stage_kernel(StreamView s, const int64_t* __restrict__ seg_off, int seg0,
+                             float* __restrict__ planes, int64_t Tp, int Cpad, int n_shift) {
   __shared__ float tile[32][33];
   const int seg = seg0 + blockIdx.y;
   const int64_t len = s.seg_len[seg];
@@ -389,23 +415,8 @@ __global__ void stage_split_kernel(StreamView s, const int64_t* __restrict__ seg
     const int64_t t = t0 + threadIdx.x;
     if (c < s.channels && t < len) {
       const float v = tile[threadIdx.x][r];
-      uint32_t hb, lb;
-      float hi;
-      if (raw_hi) {
-        // experiment: hi plane = raw fp32 (the tensor core is expected to ignore the 13 low mantissa
-        // bits, i.e. truncate), lo = tf32(x - trunc(x))
-        hb = __float_as_uint(v);
-        hi = __uint_as_float(hb & 0xFFFFE000u);
-      } else {
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-        hi = __uint_as_float(hb);
-      }
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
       const int64_t o = (int64_t)c * Tp + seg_off[seg] + t;
-      for (int sh = 0; sh < n_shift; ++sh) {
-        planes[(2 * sh) * plane + o - sh] = __uint_as_float(hb);
-        planes[(2 * sh + 1) * plane + o - sh] = __uint_as_float(lb);
-      }
+      for (int sh = 0; sh < n_shift; ++sh) planes[sh * plane + o - sh] = v;
     }
   }
 }
@@ -434,7 +445,7 @@ __global__ void symmetrize_kernel(float* __restrict__ G, int64_t n, int64_t ldg,
 // Host-side plan.
 // ---------------------------------------------------------------------------------------------
 struct GramPlan {
-  int n_streams = 0, CB = 0, cg = 1, mc = 1, n_seg = 0, n_shift = 4;
+  int n_streams = 0, CB = 0, cg = 1, n_seg = 0, n_shift = 4;
   int L[2] = {0, 0}, C[2] = {0, 0}, Cpad[2] = {0, 0}, pre[2] = {0, 0};
   int64_t Tp = 0, Dz = 0, Dpad = 0, NK = 0;
   int nt = 0, ntri = 0, n_groups = 0, tile = 0;
@@ -466,10 +477,7 @@ int make_plan(const td_stream* streams, int n_streams, const int64_t* seg_first,
   }
   pl->n_streams = n_streams;
   pl->n_seg = n_seg;
-  {
-    const char* e = getenv("TD_STAGE_SHIFTS");     // development switch: 1 = unaligned TMA origins
-    pl->n_shift = (e && e[0] == '1') ? 1 : 4;
-  }
+  pl->n_shift = 4;
   int cg = opt ? opt->cta_group : 0;
   int cb = 64;
   int halo = 0;
@@ -494,20 +502,8 @@ int make_plan(const td_stream* streams, int n_streams, const int64_t* seg_first,
   pl->tile = TILE_ROWS * cg;
   pl->Dpad = round_up(n_groups * cb, pl->tile);
   pl->nt = (int)(pl->Dpad / pl->tile);
-  // Two CTA pairs per cluster share the A operand by multicast once there are enough tiles.
-  int mc = opt ? opt->reserved[1] : 0;          // 0 = auto, 1 = off, 2 = on
-  if (mc == 0) mc = (cg == 2 && pl->nt >= 4) ? 2 : 1;
-  { const char* e = getenv("TD_GRAM_MC"); if (e && (e[0] == '1' || e[0] == '2')) mc = e[0] - '0'; }
-  if (cg != 2) mc = 1;
-  pl->mc = mc;
-  // tables carry one extra (all padding) tile: the odd tile of a row's last pair reads it
-  pl->n_groups = (int)((pl->Dpad + pl->tile) / cb);
-  if (mc == 1) {
-    pl->ntri = pl->nt * (pl->nt + 1) / 2;
-  } else {
-    pl->ntri = 0;                                // tile PAIRS in the lower triangle
-    for (int tm = 0; tm < pl->nt; ++tm) pl->ntri += (tm + 2) / 2;
-  }
+  pl->n_groups = (int)(pl->Dpad / cb);
+  pl->ntri = pl->nt * (pl->nt + 1) / 2;
   TD_REQUIRE(pl->Dpad < (1LL << 30), "td_lagged_gram: design too wide");
 
   // Segment placement in staged time: zero gap >= halo between segments, 32-frame aligned starts.
@@ -530,12 +526,12 @@ int make_plan(const td_stream* streams, int n_streams, const int64_t* seg_first,
   size_t off = 0;
   for (int q = 0; q < n_streams; ++q) {
     pl->off_stage[q] = off;
-    off += (size_t)2 * pl->n_shift * pl->Cpad[q] * pl->Tp * sizeof(float);
+    off += (size_t)pl->n_shift * pl->Cpad[q] * pl->Tp * sizeof(float);
     off = (size_t)round_up((int64_t)off, 1024);
   }
   pl->off_groups = off;  off += (size_t)round_up((int64_t)pl->n_groups * sizeof(int4), 1024);
   pl->off_ktiles = off;  off += (size_t)round_up(std::max<int64_t>(nk, 1) * sizeof(int2), 1024);
-  pl->off_outidx = off;  off += (size_t)round_up((pl->Dpad + pl->tile) * sizeof(int), 1024);
+  pl->off_outidx = off;  off += (size_t)round_up(pl->Dpad * sizeof(int), 1024);
   pl->off_segoff = off;  off += (size_t)round_up((int64_t)n_seg * sizeof(int64_t), 1024);
   pl->off_segtab = off;  off += (size_t)round_up((int64_t)n_seg * 2 * n_streams * sizeof(int64_t), 1024);
   pl->total = off;
@@ -585,7 +581,7 @@ int make_tmap(CUtensorMap* m, float* planes, int64_t Tp, int Cpad, int CB, int n
   EncodeTiledFn enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
-  cuuint64_t dims[3] = {(cuuint64_t)Tp, (cuuint64_t)Cpad, (cuuint64_t)(2 * n_shift)};
+  cuuint64_t dims[3] = {(cuuint64_t)Tp, (cuuint64_t)Cpad, (cuuint64_t)n_shift};
   cuuint64_t strides[2] = {(cuuint64_t)Tp * 4, (cuuint64_t)Tp * 4 * (cuuint64_t)Cpad};
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)CB, 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -671,7 +667,7 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
 
   // ---- tables -------------------------------------------------------------------------------
   std::vector<int4> groups(pl.n_groups);
-  std::vector<int> out_idx(pl.Dpad + pl.tile, -1);
+  std::vector<int> out_idx(pl.Dpad, -1);
   {
     int g = 0;
     int64_t col0 = 0;
@@ -718,7 +714,7 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
   CUtensorMap tmaps[2];
   for (int q = 0; q < n_streams; ++q) {
     float* planes = reinterpret_cast<float*>(ws + pl.off_stage[q]);
-    TD_CHECK_CUDA(cudaMemsetAsync(planes, 0, (size_t)2 * pl.n_shift * pl.Cpad[q] * pl.Tp * sizeof(float), st));
+    TD_CHECK_CUDA(cudaMemsetAsync(planes, 0, (size_t)pl.n_shift * pl.Cpad[q] * pl.Tp * sizeof(float), st));
     StreamView sv;
     sv.data = streams[q].data_dev;
     sv.ld = streams[q].ld;
@@ -734,9 +730,8 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       for (int s0 = 0; s0 < n_seg; s0 += 32768) {
         dim3 grid((unsigned)ceil_div(maxlen, 32), (unsigned)std::min(32768, n_seg - s0),
                   (unsigned)ceil_div(pl.C[q], 32));
-        stage_split_kernel<<<grid, dim3(32, 8), 0, st>>>(
-            sv, reinterpret_cast<const int64_t*>(ws + pl.off_segoff), s0, planes, pl.Tp, pl.Cpad[q], pl.n_shift,
-            getenv("TD_RAW_HI") ? 1 : 0);
+        stage_kernel<<<grid, dim3(32, 8), 0, st>>>(
+            sv, reinterpret_cast<const int64_t*>(ws + pl.off_segoff), s0, planes, pl.Tp, pl.Cpad[q], pl.n_shift);
         TD_CHECK_CUDA(cudaGetLastError());
       }
     }
@@ -761,13 +756,12 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
     P.NK = pl.NK;
     int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 128;
     P.chunk_kt = std::max(1, chunk_rows / BK);
-    { const char* e = getenv("TD_EXPERIMENT"); P.experiment = e ? atoi(e) : 0; }
     // Superchunk: the staged frames all tiles sweep together; sized to stay L2 resident (~24 MB).
     int64_t sc_rows = (opt && opt->superchunk_rows > 0) ? opt->superchunk_rows : 0;
     if (sc_rows == 0) {
       int64_t cpad_sum = 0;
       for (int q = 0; q < n_streams; ++q) cpad_sum += pl.Cpad[q];
-      sc_rows = (24LL << 20) / (cpad_sum * 8 * pl.n_shift);
+      sc_rows = (24LL << 20) / (cpad_sum * 4 * pl.n_shift);
       sc_rows = std::max<int64_t>(sc_rows, 4096);
     }
     int64_t ks = std::max<int64_t>(P.chunk_kt, round_up(ceil_div(sc_rows, BK), P.chunk_kt));
@@ -787,38 +781,24 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       }
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
-    P.mc = pl.mc;
     if (pl.cg == 1) {
-      TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-      lagged_gram_umma_kernel<1, 1><<<workers, NUM_THREADS, SMEM_BYTES, st>>>(tmaps[0], tmaps[1], P);
+      TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      lagged_gram_umma_kernel<1><<<workers, NUM_THREADS, SMEM_BYTES, st>>>(tmaps[0], tmaps[1], P);
     } else {
-      const int csize = 2 * pl.mc;
-      auto kern = (pl.mc == 2) ? lagged_gram_umma_kernel<2, 2> : lagged_gram_umma_kernel<2, 1>;
-      TD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
       cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(workers * 2);
       cfg.blockDim = dim3(NUM_THREADS);
       cfg.dynamicSmemBytes = SMEM_BYTES;
       cfg.stream = st;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = csize;
+      attr[0].val.clusterDim.x = 2;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      int n_clusters = sms / csize;
-      if (csize > 2) {
-        // clusters of 4 cannot use every SM (GPC sizes): ask how many are co-resident
-        cfg.gridDim = dim3(sms / csize * csize);
-        int max_clusters = 0;
-        TD_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-        n_clusters = std::max(1, std::min(n_clusters, max_clusters));
-      }
-      if (opt && opt->max_ctas > 0) n_clusters = std::max(1, std::min(n_clusters, opt->max_ctas / csize));
-      n_clusters = (int)std::max<int64_t>(1, std::min<int64_t>(n_clusters, ceil_div((int64_t)pl.ntri * ks, P.chunk_kt)));
-      workers = n_clusters;
-      cfg.gridDim = dim3(n_clusters * csize);
-      TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmaps[0], tmaps[1], P));
+      TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lagged_gram_umma_kernel<2>, tmaps[0], tmaps[1], P));
     }
     TD_CHECK_CUDA(cudaGetLastError());
     if (timed) {
@@ -826,8 +806,8 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       g_ev_valid = true;
     }
     if (debug_enabled())
-      fprintf(stderr, "[tdgram] gram launch: mc=%d cg=%d workers=%d CB=%d Dz=%lld Dpad=%lld ntri=%d NK=%lld KS=%d chunk_kt=%d total=%lld Tp=%lld\n",
-              pl.mc, pl.cg, workers, pl.CB, (long long)pl.Dz, (long long)pl.Dpad, pl.ntri, (long long)pl.NK, P.KS, P.chunk_kt,
+      fprintf(stderr, "[tdgram] gram launch: cg=%d workers=%d CB=%d Dz=%lld Dpad=%lld ntri=%d NK=%lld KS=%d chunk_kt=%d total=%lld Tp=%lld\n",
+              pl.cg, workers, pl.CB, (long long)pl.Dz, (long long)pl.Dpad, pl.ntri, (long long)pl.NK, P.KS, P.chunk_kt,
               (long long)P.total_steps, (long long)pl.Tp);
     if ((rc = debug_sync(st, "gram kernel"))) return rc;
   }

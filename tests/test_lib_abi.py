@@ -54,8 +54,8 @@ def test_workspace_plan_and_argument_errors():
   opt = _lib.TdGramOptions(0, 0, 0, 0, 0)
   assert lib.td_lagged_gram_workspace_bytes(arr, 1, None, keep, 60, ctypes.byref(opt),
                                             ctypes.byref(nbytes)) == 0
-  # 4 shifted hi/lo plane pairs of 64 channels x ~463k staged frames
-  assert 8 * 64 * 4 * 460800 < nbytes.value < 2 * 8 * 64 * 4 * 460800
+  # 4 shifted raw planes of 64 channels x ~463k staged frames
+  assert 4 * 64 * 4 * 460800 < nbytes.value < 2 * 4 * 64 * 4 * 460800
   # three streams are rejected with a message
   rc = lib.td_lagged_gram_workspace_bytes(arr, 3, None, keep, 60, ctypes.byref(opt), ctypes.byref(nbytes))
   assert rc == -1 and b'n_streams' in lib.td_last_error()
