@@ -228,8 +228,7 @@ def main():
     bd = brain_data.TrialBrainData('eeg', 'envelope', 128.0, pre_context=CFG['pre'],
                                    post_context=CFG['post'], final_batch_size=CFG['batch'],
                                    shuffle_buffer_size=0)
-    for i in range(trials):
-      bd.add_trial('trial_%02d' % i, xd[i * fpt:(i + 1) * fpt], yd[i * fpt:(i + 1) * fpt])
+    bd.set_trials(['trial_%02d' % i for i in range(trials)], [fpt] * trials, xd, yd)
     return bd
 
   gopt = ops.gram_options(cta_group=args.cta_group, chunk_rows=args.chunk_rows, timed=True)

@@ -490,9 +490,48 @@ class TrialBrainData(BrainData):
     if self.attended_field:
       self.features[self.attended_field] = FixedLenFeature([int(a.shape[1]),])
 
+  def set_trials(self, names, lengths, input_data, output_data, input2_data=None,
+                 attention_data=None):
+    """All trials at once from arrays that already hold them back to back (no per-trial copies):
+    trial i is rows [sum(lengths[:i]), sum(lengths[:i+1])) of every array."""
+    x = _check_2d('input_data', _lib.as_device_f32(input_data))
+    y = _check_2d('output_data', _lib.as_device_f32(output_data))
+    n = int(x.shape[0])
+    if sum(int(l) for l in lengths) != n or len(names) != len(lengths):
+      raise ValueError('lengths must sum to the %d frames of input_data, one per name' % n)
+    if y.shape[0] != n:
+      raise ValueError('input shape (%s) and output shape (%s) are not equal.' %
+                       (tuple(x.shape), tuple(y.shape)))
+    x2 = (torch.zeros((n, 1), dtype=torch.float32, device=x.device) if input2_data is None
+          else _check_2d('input2_data', _lib.as_device_f32(input2_data)))
+    a = (torch.zeros((n, 1), dtype=torch.float32, device=x.device) if attention_data is None
+         else _check_2d('attention_data', _lib.as_device_f32(attention_data)))
+    if x2.shape[0] != n or a.shape[0] != n:
+      raise ValueError('all streams must have %d frames' % n)
+    self._x, self._x2, self._y, self._a = x, x2, y, a
+    self._offsets, self._trials, cur = {}, {}, 0
+    for name, length in zip(names, lengths):
+      self._offsets[str(name)] = (cur, int(length))
+      self._trials[str(name)] = None          # data lives in the packed arrays
+      cur += int(length)
+    self._cached_file_names = []
+    self._dirty = False
+    self.features = {'input_1': FixedLenFeature([int(x.shape[1]),]),
+                     'output': FixedLenFeature([int(y.shape[1]),]),
+                     'input_2': FixedLenFeature([int(x2.shape[1]),]),
+                     'attention': FixedLenFeature([int(a.shape[1]),])}
+    self.features[self.in1_fields[0]] = FixedLenFeature([int(x.shape[1]),])
+    self.features[self.out_field] = FixedLenFeature([int(y.shape[1]),])
+    if self.in2_fields:
+      self.features[self.in2_fields[0]] = FixedLenFeature([int(x2.shape[1]),])
+    if self.attended_field:
+      self.features[self.attended_field] = FixedLenFeature([int(a.shape[1]),])
+
   def _pack(self):
     if not self._dirty:
       return
+    if any(v is None for v in self._trials.values()):
+      raise ValueError('add_trial cannot be mixed with set_trials; call set_trials again.')
     names = sorted(self._trials.keys())
     self._offsets = {}
     cur = 0

@@ -23,6 +23,9 @@ constexpr int MAX_LANES = 8;    // concurrent factorisations of a lambda sweep
 struct Handles {
   cusolverDnHandle_t solver = nullptr;
   cublasHandle_t blas = nullptr;
+  cublasHandle_t blas_side = nullptr;     // bound to lane_stream[0]: look-ahead trailing updates
+  cudaEvent_t ev_panel[8] = {};
+  cudaEvent_t ev_wide[8] = {};
   // side streams (+ their own cuSOLVER handles) so that the independent Cholesky factorisations of
   // a regularisation sweep overlap: one n ~ 2000 potrf cannot fill 148 SMs
   cudaStream_t lane_stream[MAX_LANES] = {};
@@ -46,6 +49,10 @@ int get_handles(Handles** out) {
       return TD_ERR_SOLVER;
     }
     TD_CHECK_CUDA(cudaEventCreateWithFlags(&h.ev_ready, cudaEventDisableTiming));
+    for (int i = 0; i < 8; ++i) {
+      TD_CHECK_CUDA(cudaEventCreateWithFlags(&h.ev_panel[i], cudaEventDisableTiming));
+      TD_CHECK_CUDA(cudaEventCreateWithFlags(&h.ev_wide[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < MAX_LANES; ++i) {
       TD_CHECK_CUDA(cudaStreamCreateWithFlags(&h.lane_stream[i], cudaStreamNonBlocking));
       TD_CHECK_CUDA(cudaEventCreateWithFlags(&h.ev_done[i], cudaEventDisableTiming));
@@ -54,6 +61,11 @@ int get_handles(Handles** out) {
         set_error("cusolverDnCreate (lane) failed");
         return TD_ERR_SOLVER;
       }
+    }
+    if (cublasCreate(&h.blas_side) != CUBLAS_STATUS_SUCCESS ||
+        cublasSetStream(h.blas_side, h.lane_stream[0]) != CUBLAS_STATUS_SUCCESS) {
+      set_error("cublasCreate (side) failed");
+      return TD_ERR_SOLVER;
     }
   }
   *out = &h;
@@ -224,33 +236,61 @@ __global__ void __launch_bounds__(256) chol_potf2(double* M, long long Nt, int j
     X[r][c] = 0.0;
   }
   __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = 0; k < jb; ++k) {
     const double d = T[k][k];
     if (!(d > 0.0) && threadIdx.x == 0 && info[blockIdx.x] == 0) info[blockIdx.x] = j0 + k + 1;
-    const double rpiv = rsqrt(d > 0.0 ? d : 1.0);
+    // 1/sqrt(d): float seed + two Newton steps in double (relative error ~1e-16)
+    const double dd = d > 0.0 ? d : 1.0;
+    double rp = (double)rsqrtf((float)dd);
+    rp = rp * (1.5 - 0.5 * dd * rp * rp);
+    rp = rp * (1.5 - 0.5 * dd * rp * rp);
     __syncthreads();
-    if (threadIdx.x >= k && threadIdx.x < CH_NB) T[threadIdx.x][k] *= rpiv;     // T[k][k] = sqrt(d)
+    if (threadIdx.x >= k && threadIdx.x < CH_NB) T[threadIdx.x][k] *= rp;     // T[k][k] = sqrt(d)
     __syncthreads();
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int r = ty + 16 * a;
-#pragma unroll
-      for (int bb = 0; bb < 4; ++bb) {
-        const int c = tx + 16 * bb;
-        if (c > k && r >= c) T[r][c] -= T[r][k] * T[c][k];
-      }
+    // rank-1 update of the remaining lower triangle: warp -> rows, lanes -> columns
+    for (int r = k + 1 + warp; r < CH_NB; r += 8) {
+      const double lr = T[r][k];
+      for (int c = k + 1 + lane; c <= r; c += 32) T[r][c] -= lr * T[c][k];
     }
     __syncthreads();
   }
-  // Linv: column j by forward substitution, one thread per column.
+  // Linv by 32 x 32 blocks: inv([[A,0],[B,C]]) = [[inv A, 0], [-inv C * B * inv A, inv C]].
+  // The two diagonal inverses: one thread per column, forward substitution.
   if (threadIdx.x < CH_NB) {
-    const int j = threadIdx.x;
+    const int blk = threadIdx.x >> 5, j = (threadIdx.x & 31) + 32 * blk, lim = 32 * (blk + 1);
     X[j][j] = 1.0 / T[j][j];
-    for (int i = j + 1; i < CH_NB; ++i) {
+    for (int i = j + 1; i < lim; ++i) {
       double sacc = 0.0;
-      for (int k = j; k < i; ++k) sacc += T[i][k] * X[k][j];
+      for (int kk = j; kk < i; ++kk) sacc += T[i][kk] * X[kk][j];
       X[i][j] = -sacc / T[i][i];
     }
+  }
+  __syncthreads();
+  // W = B * inv A  (into the upper-right corner of X as scratch), then X21 = -inv C * W.
+  for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+    const int i = e >> 5, j = e & 31;
+    double sacc = 0.0;
+    for (int kk = j; kk < 32; ++kk) sacc += T[32 + i][kk] * X[kk][j];
+    X[i][32 + j] = sacc;                       // scratch (upper-right block is otherwise zero)
+  }
+  __syncthreads();
+  double keep[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = threadIdx.x + q * 256;
+    const int i = e >> 5, j = e & 31;
+    double sacc = 0.0;
+    for (int kk = 0; kk <= i; ++kk) sacc += X[32 + i][32 + kk] * X[kk][32 + j];
+    keep[q] = -sacc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = threadIdx.x + q * 256;
+    const int i = e >> 5, j = e & 31;
+    X[32 + i][j] = keep[q];
+    X[i][32 + j] = 0.0;
   }
   __syncthreads();
   double* Li = Linv + (size_t)blockIdx.x * linv_stride + (size_t)(j0 / CH_NB) * CH_NB * CH_NB;
@@ -350,30 +390,55 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
     if (dbg) cudaEventRecord(ev[0], st);
     chol_build<<<dim3(blocks_for(Nt * Da), nbat), 256, 0, st>>>(A0, B0, Da, Dy, lam_dev, l0, M);
     if (dbg) cudaEventRecord(ev[1], st);
-    for (int j0 = 0; j0 < Da; j0 += CH_NB) {
+    // Look-ahead: the serial chain potf2 -> panel solve -> update of the NEXT panel's columns runs
+    // on the caller's stream; the wide trailing update of panel j runs on a side stream and overlaps
+    // the chain of panel j + 1.
+    cudaStream_t side = h->lane_stream[0];
+    int panel = 0;
+    for (int j0 = 0; j0 < Da; j0 += CH_NB, ++panel) {
       const int jb = std::min(CH_NB, Da - j0);
+      // panel j's columns got their last update from narrow(j-1) (this stream); the wide updates that
+      // touched them finished with wide(j-2), which narrow(j-1) already waited for.
       chol_potf2<<<nbat, 256, potf2_smem, st>>>(M, Nt, j0, jb, info + l0, Linv, linv_stride);
       const long long below = Nt - j0 - jb;
-      if (below > 0) {
-        // panel solve P <- P L_jj^-T as a GEMM with the explicit 64 x 64 inverse
-        chol_copy_panel<<<dim3(blocks_for(below * jb), nbat), 256, 0, st>>>(M, Nt, j0, jb, tmp);
-        TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)below, jb, jb, &one,
-                                                  tmp + j0 + jb, (int)Nt, (long long)CH_NB * Nt,
-                                                  Linv + (size_t)(j0 / CH_NB) * CH_NB * CH_NB, CH_NB,
-                                                  linv_stride, &zero, M + (size_t)j0 * Nt + j0 + jb,
-                                                  (int)Nt, Nt * Nt, nbat));
-        // trailing update C <- C - P P' on the lower block-triangle only (512-column blocks)
-        const long long t0 = (long long)j0 + jb;
-        for (long long cb = t0; cb < Da; cb += 512) {
-          const long long ncb = std::min<long long>(512, Da - cb);
-          const double* Prow = M + (size_t)j0 * Nt + cb;      // P[cb:, :]   [Nt - cb, jb], ld Nt
-          double* C = M + (size_t)cb * Nt + cb;               // C[cb:, cb:cb+ncb]
-          TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)(Nt - cb), (int)ncb, jb,
-                                                    &minus_one, Prow, (int)Nt, Nt * Nt, Prow, (int)Nt, Nt * Nt, &one,
-                                                    C, (int)Nt, Nt * Nt, nbat));
-        }
+      if (below <= 0) continue;
+      // panel solve P <- P L_jj^-T as a GEMM with the explicit 64 x 64 inverse
+      chol_copy_panel<<<dim3(blocks_for(below * jb), nbat), 256, 0, st>>>(M, Nt, j0, jb, tmp);
+      TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)below, jb, jb, &one,
+                                                tmp + j0 + jb, (int)Nt, (long long)CH_NB * Nt,
+                                                Linv + (size_t)(j0 / CH_NB) * CH_NB * CH_NB, CH_NB,
+                                                linv_stride, &zero, M + (size_t)j0 * Nt + j0 + jb,
+                                                (int)Nt, Nt * Nt, nbat));
+      TD_CHECK_CUDA(cudaEventRecord(h->ev_panel[panel & 7], st));
+      const long long t0 = (long long)j0 + jb;
+      if (t0 >= Da) continue;
+      // narrow update: the next panel's columns [t0, t0 + 64), after the previous wide update
+      // (which also wrote them) has finished
+      if (panel > 0) TD_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_wide[(panel - 1) & 7], 0));
+      const long long nnar = std::min<long long>(CH_NB, Da - t0);
+      {
+        const double* Prow = M + (size_t)j0 * Nt + t0;
+        double* C = M + (size_t)t0 * Nt + t0;
+        TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)(Nt - t0), (int)nnar, jb,
+                                                  &minus_one, Prow, (int)Nt, Nt * Nt, Prow, (int)Nt, Nt * Nt, &one,
+                                                  C, (int)Nt, Nt * Nt, nbat));
       }
+      // wide update on the side stream: columns [t0 + 64, Da), lower block-triangle, 512-column blocks
+      TD_CHECK_CUDA(cudaStreamWaitEvent(side, h->ev_panel[panel & 7], 0));
+      for (long long cb = t0 + nnar; cb < Da; cb += 512) {
+        const long long ncb = std::min<long long>(512, Da - cb);
+        const double* Prow = M + (size_t)j0 * Nt + cb;      // P[cb:, :]   [Nt - cb, jb], ld Nt
+        double* C = M + (size_t)cb * Nt + cb;               // C[cb:, cb:cb+ncb]
+        TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas_side, CUBLAS_OP_N, CUBLAS_OP_T, (int)(Nt - cb), (int)ncb, jb,
+                                                  &minus_one, Prow, (int)Nt, Nt * Nt, Prow, (int)Nt, Nt * Nt, &one,
+                                                  C, (int)Nt, Nt * Nt, nbat));
+      }
+      TD_CHECK_CUDA(cudaEventRecord(h->ev_wide[panel & 7], side));
     }
+    // everything the side stream did must be visible before the back substitution
+    if (panel > 0) TD_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_wide[(panel - 1) & 7], 0));
+    TD_CHECK_CUDA(cudaEventRecord(h->ev_ready, side));
+    TD_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_ready, 0));
     if (dbg) cudaEventRecord(ev[2], st);
     chol_take_y<<<dim3(blocks_for((long long)Da * Dy), nbat), 256, 0, st>>>(M, Nt, Da, Dy, Y);
     for (int j0 = ((Da - 1) / CH_NB) * CH_NB; j0 >= 0; j0 -= CH_NB) {
