@@ -177,9 +177,13 @@ int td_column_moments_f64(const float* a_dev, int64_t lda, const float* b_dev, i
  *   mode 1  global:  c[t,d] = (a-mu_a)(b-mu_b)/power in float32 (infer_decoder.py:327-328),
  *                    reduced over d by `reduction` (0 first, 1 second, 2 mean, 3 mean-squared;
  *                    infer_decoder.py:441-450), then float64 window mean
+ *                    reduction 5 ('lda'): slope * sum_d c[t,d] w[d] + intercept in float64
+ *                    (scaled_lda.py:197-212, :345-355), lda_params_dev = [w (dims), slope, intercept]
  *   mode 2  local:   Pearson r per window and column from the five sums
  *                    (brain_model.py:62-79); out has `dims` columns, and a window whose
  *                    product of powers over columns is <= 0 yields zeros
+ *   mode 3  global, every column: window means of c[t,d] for each d ('all' reduction, and
+ *                    average_data of the training pass, infer_decoder.py:377-400, :748-783)
  * seg_start/seg_len HOST arrays (rows of a/b); n_sizes window shapes (W[j], S[j]) are evaluated
  * in ONE pass over the data.  out_dev is double [total_windows, out_cols]; windows are ordered
  * size-major, then segment, then window index; out_offset (HOST, n_sizes+1 entries, may be
@@ -188,7 +192,8 @@ int td_windowed_corr_f32(const float* a_dev, int64_t lda, const float* b_dev, in
                          int dims, const int64_t* seg_start, const int64_t* seg_len, int n_seg,
                          const int64_t* W, const int64_t* S, int n_sizes, int mode, int reduction,
                          const float* mu_a_dev, const float* mu_b_dev, const float* power_dev,
-                         double* out_dev, int64_t* out_offset, void* cuda_stream);
+                         const double* lda_params_dev, double* out_dev, int64_t* out_offset,
+                         void* cuda_stream);
 int64_t td_window_count(int64_t n_frames, int64_t W, int64_t S);
 
 /* Winner-take-all: out[i] = r1[i] > r2[i] (attention_decoder.py:134). */

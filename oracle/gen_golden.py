@@ -26,6 +26,7 @@ from telluride_decoding import brain_model                    # noqa: E402
 from telluride_decoding import cca                            # noqa: E402
 from telluride_decoding import infer_decoder                  # noqa: E402
 from telluride_decoding import result_store                   # noqa: E402
+from telluride_decoding import scaled_lda                     # noqa: E402
 
 from oracle import ref_numpy as ora                           # noqa: E402
 
@@ -169,6 +170,41 @@ def decoder_case():
   print('wrote decoder', len(out), 'arrays; windows@201/100:', len(firsts))
 
 
+def lda_case():
+  """Reference scaled LDA on the decoder fixture's correlation signals: class 0 = unattended
+  speaker (s2), class 1 = attended (s1), averaged over 7-frame windows like Decoder.train."""
+  g = np.load(os.path.join(OUT, 'decoder.npz'))
+  c0, c1 = g['s2_corr'].astype(np.float64), g['s1_corr'].astype(np.float64)
+  dec = infer_decoder.Decoder(lambda d: None, reduction='lda')
+  a0, a1 = infer_decoder.average_data(c0, 7), infer_decoder.average_data(c1, 7)
+  dprime = dec.compute_lda_model(a0, a1)
+  params = dec.lda_params
+  out = dict(dprime=np.asarray(dprime), w_real=np.asarray(params.w_real), w_imag=np.asarray(params.w_imag),
+             slope=np.asarray(params.slope), intercept=np.asarray(params.intercept),
+             mean_vectors=np.asarray(params.mean_vectors), avg0=a0, avg1=a1,
+             transform_s1=dec.reduce_with_lda(g['s1_corr']))
+  label = g['label']
+  sig = dec.reduce_with_lda(g['s1_corr'])[:, 0]
+  for width in (10, 100, 200, 400, 700, 1000):
+    store = result_store.TwoResultStore(window_width=width, window_step=width // 2)
+    res = []
+    for s in range(0, sig.shape[0], 200):
+      store.add_data(sig[s:s + 200], label[s:s + 200])
+      for r, _ in store.next_window():
+        res.append(np.mean(r))
+    out['lda_w%d_res' % width] = np.asarray(res)
+  lda = scaled_lda.ScaledLinearDiscriminantAnalysis()
+  rng = np.random.RandomState(5)
+  x = np.concatenate((rng.randn(200, 3) + [1, 2, 3], rng.randn(150, 3) + [1.5, 1, 3.5]))
+  y = np.concatenate((np.full(200, 4.0), np.full(150, 9.0)))
+  out['toy_x'], out['toy_y'] = x, y
+  out['toy_transform'] = lda.fit_transform(x, y)
+  out['toy_slope'], out['toy_intercept'] = np.asarray(lda.model_parameters.slope), np.asarray(lda.model_parameters.intercept)
+  out['toy_evr'] = lda.explained_variance_ratio()
+  np.savez_compressed(os.path.join(OUT, 'lda.npz'), **out)
+  print('wrote lda: dprime', dprime, 'slope', params.slope)
+
+
 def main():
   os.makedirs(OUT, exist_ok=True)
   ridge_case('ridge_small', seed=11, n_frames=1000, channels=3, pre=1, post=2, dy=2,
@@ -179,6 +215,7 @@ def main():
            reg=0.1, batch=250)
   cca_test42()
   decoder_case()
+  lda_case()
 
 
 if __name__ == '__main__':

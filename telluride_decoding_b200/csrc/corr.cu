@@ -37,13 +37,21 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Per-frame scalar of mode 0 / mode 1 (float32 arithmetic in the reference's operation order).
-__device__ __forceinline__ float frame_signal(const float* a, const float* b, int dims, int mode,
-                                              int reduction, const float* mu_a, const float* mu_b,
-                                              const float* power) {
-  if (mode == 0) return a[0];
+// reduction 5 ('lda'): slope * sum_d c[d] * w[d] + intercept in float64 (ScaledLDA.transform,
+// scaled_lda.py:197-212, :345-355, column 0); lda = [w_0 .. w_{dims-1}, slope, intercept].
+__device__ __forceinline__ double frame_signal(const float* a, const float* b, int dims, int mode,
+                                               int reduction, const float* mu_a, const float* mu_b,
+                                               const float* power, const double* lda) {
+  if (mode == 0) return (double)a[0];
   if (reduction == 0 || reduction == 1) {
     const int d = reduction;
-    return ((a[d] - mu_a[d]) * (b[d] - mu_b[d])) / power[d];
+    return (double)(((a[d] - mu_a[d]) * (b[d] - mu_b[d])) / power[d]);
+  }
+  if (reduction == 5) {
+    double acc = 0.0;
+    for (int d = 0; d < dims; ++d)
+      acc += (double)(((a[d] - mu_a[d]) * (b[d] - mu_b[d])) / power[d]) * lda[d];
+    return lda[dims] * acc + lda[dims + 1];
   }
   // mean (2) and mean-squared (3): numpy float32 mean over the (contiguous) feature axis.
   // numpy sums < 8 values left to right and 8..128 values with eight interleaved accumulators
@@ -64,43 +72,52 @@ __device__ __forceinline__ float frame_signal(const float* a, const float* b, in
       s += c;
     }
   }
-  return s / (float)dims;
+  return (double)(s / (float)dims);
 }
 
 // One block per segment.  ncol partial columns per g-frame chunk:
 //   mode 0/1: 1 (the reduced signal)     mode 2: 5*dims (a, b, aa, bb, ab per column)
 __global__ void __launch_bounds__(CORR_THREADS)
-windowed_corr_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b,
+windowed_corr_kernel(const float* __restrict__ a, long long lda_a, const float* __restrict__ b,
                      long long ldb, int dims, const long long* __restrict__ seg_start,
                      const long long* __restrict__ seg_len, WinSpec ws, int mode, int reduction,
                      const float* __restrict__ mu_a, const float* __restrict__ mu_b,
-                     const float* __restrict__ power, const long long* __restrict__ win_base,
-                     int n_seg, double* __restrict__ out, int out_cols) {
+                     const float* __restrict__ power, const double* __restrict__ lda,
+                     const long long* __restrict__ win_base, int n_seg, double* __restrict__ out,
+                     int out_cols) {
   extern __shared__ double part[];
   const int seg = blockIdx.x;
   const long long n = seg_len[seg];
   const long long g = ws.g;
   const long long nchunk = n / g;
-  const int ncol = (mode == 2) ? 5 * dims : 1;
-  const float* A = a + seg_start[seg] * lda;
+  const int ncol = (mode == 2) ? 5 * dims : (mode == 3 ? dims : 1);
+  const float* A = a + seg_start[seg] * lda_a;
   const float* B = b ? b + seg_start[seg] * ldb : nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
 
   // ---- phase 1: partial sums per chunk ------------------------------------------------------
   if (g >= 32) {
     for (long long ch = warp; ch < nchunk; ch += nwarp) {
-      if (mode != 2) {
+      if (mode < 2) {
         double s = 0.0;
         for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32)
-          s += (double)frame_signal(A + t * lda, B ? B + t * ldb : nullptr, dims, mode, reduction,
-                                    mu_a, mu_b, power);
+          s += frame_signal(A + t * lda_a, B ? B + t * ldb : nullptr, dims, mode, reduction,
+                            mu_a, mu_b, power, lda);
         s = warp_sum(s);
         if (lane == 0) part[ch] = s;
+      } else if (mode == 3) {          // every column of the global-statistics signal
+        for (int d = 0; d < dims; ++d) {
+          double s = 0.0;
+          for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32)
+            s += (double)(((A[t * lda_a + d] - mu_a[d]) * (B[t * ldb + d] - mu_b[d])) / power[d]);
+          s = warp_sum(s);
+          if (lane == 0) part[ch * ncol + d] = s;
+        }
       } else {
         for (int d = 0; d < dims; ++d) {
           double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
           for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32) {
-            const double x = (double)A[t * lda + d], y = (double)B[t * ldb + d];
+            const double x = (double)A[t * lda_a + d], y = (double)B[t * ldb + d];
             sa += x; sb += y; saa += x * x; sbb += y * y; sab += x * y;
           }
           sa = warp_sum(sa); sb = warp_sum(sb); saa = warp_sum(saa); sbb = warp_sum(sbb);
@@ -114,17 +131,24 @@ windowed_corr_kernel(const float* __restrict__ a, long long lda, const float* __
     }
   } else {
     for (long long ch = threadIdx.x; ch < nchunk; ch += blockDim.x) {
-      if (mode != 2) {
+      if (mode < 2) {
         double s = 0.0;
         for (long long t = ch * g; t < (ch + 1) * g; ++t)
-          s += (double)frame_signal(A + t * lda, B ? B + t * ldb : nullptr, dims, mode, reduction,
-                                    mu_a, mu_b, power);
+          s += frame_signal(A + t * lda_a, B ? B + t * ldb : nullptr, dims, mode, reduction,
+                            mu_a, mu_b, power, lda);
         part[ch] = s;
+      } else if (mode == 3) {
+        for (int d = 0; d < dims; ++d) {
+          double s = 0.0;
+          for (long long t = ch * g; t < (ch + 1) * g; ++t)
+            s += (double)(((A[t * lda_a + d] - mu_a[d]) * (B[t * ldb + d] - mu_b[d])) / power[d]);
+          part[ch * ncol + d] = s;
+        }
       } else {
         for (int d = 0; d < dims; ++d) {
           double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
           for (long long t = ch * g; t < (ch + 1) * g; ++t) {
-            const double x = (double)A[t * lda + d], y = (double)B[t * ldb + d];
+            const double x = (double)A[t * lda_a + d], y = (double)B[t * ldb + d];
             sa += x; sb += y; saa += x * x; sbb += y * y; sab += x * y;
           }
           double* p = part + ch * ncol + 5 * d;
@@ -142,11 +166,19 @@ windowed_corr_kernel(const float* __restrict__ a, long long lda, const float* __
     const long long nwin = (n - W) / S + 1;
     const long long cw = W / g, cs = S / g;
     const long long base = win_base[(long long)j * n_seg + seg];
-    if (mode != 2) {
+    if (mode < 2) {
       for (long long i = threadIdx.x; i < nwin; i += blockDim.x) {
         double s = 0.0;
         for (long long c = i * cs; c < i * cs + cw; ++c) s += part[c];
         out[(base + i) * out_cols] = s / (double)W;
+      }
+    } else if (mode == 3) {
+      for (long long e = threadIdx.x; e < nwin * dims; e += blockDim.x) {
+        const long long i = e / dims;
+        const int d = (int)(e - i * dims);
+        double s = 0.0;
+        for (long long c = i * cs; c < i * cs + cw; ++c) s += part[c * ncol + d];
+        out[(base + i) * out_cols + d] = s / (double)W;
       }
     } else {
       // one warp per window: lanes over columns, then the all-columns zero rule
@@ -249,16 +281,18 @@ extern "C" int td_windowed_corr_f32(const float* a, int64_t lda, const float* b,
                                     const int64_t* seg_start, const int64_t* seg_len, int n_seg,
                                     const int64_t* W, const int64_t* S, int n_sizes, int mode,
                                     int reduction, const float* mu_a, const float* mu_b,
-                                    const float* power, double* out, int64_t* out_offset, void* stream) {
+                                    const float* power, const double* lda_params, double* out,
+                                    int64_t* out_offset, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   TD_REQUIRE(a && seg_start && seg_len && W && S && n_seg > 0, "td_windowed_corr_f32: null argument");
   TD_REQUIRE(n_sizes >= 1 && n_sizes <= MAX_SIZES, "td_windowed_corr_f32: n_sizes must be in [1, %d]", MAX_SIZES);
-  TD_REQUIRE(mode >= 0 && mode <= 2, "td_windowed_corr_f32: unknown mode %d", mode);
+  TD_REQUIRE(mode >= 0 && mode <= 3, "td_windowed_corr_f32: unknown mode %d", mode);
   TD_REQUIRE(dims >= 1 && lda >= (mode == 0 ? 1 : dims), "td_windowed_corr_f32: bad dims/lda");
   if (mode != 0) TD_REQUIRE(b && ldb >= dims, "td_windowed_corr_f32: second signal missing");
-  if (mode == 1) {
+  if (mode == 1 || mode == 3) {
     TD_REQUIRE(mu_a && mu_b && power, "td_windowed_corr_f32: global statistics missing");
-    TD_REQUIRE(reduction >= 0 && reduction <= 3, "td_windowed_corr_f32: unknown reduction %d", reduction);
+    TD_REQUIRE((reduction >= 0 && reduction <= 3) || reduction == 5, "td_windowed_corr_f32: unknown reduction %d", reduction);
+    TD_REQUIRE(reduction != 5 || lda_params, "td_windowed_corr_f32: LDA parameters missing");
     TD_REQUIRE(reduction != 1 || dims >= 2, "td_windowed_corr_f32: 'second' needs >= 2 columns");
     TD_REQUIRE(dims <= 128, "td_windowed_corr_f32: at most 128 correlation columns");
   }
@@ -274,8 +308,8 @@ extern "C" int td_windowed_corr_f32(const float* a, int64_t lda, const float* b,
     g = std::gcd(g, (long long)S[j]);
   }
   ws.g = g;
-  const int ncol = (mode == 2) ? 5 * dims : 1;
-  const int out_cols = (mode == 2) ? dims : 1;
+  const int ncol = (mode == 2) ? 5 * dims : (mode == 3 ? dims : 1);
+  const int out_cols = (mode >= 2) ? dims : 1;
   int64_t max_chunks = 0;
   std::vector<long long> win_base((size_t)n_sizes * n_seg);
   int64_t total = 0;
@@ -302,7 +336,7 @@ extern "C" int td_windowed_corr_f32(const float* a, int64_t lda, const float* b,
   rc = upload(win_base, &wb_d, st); if (rc) return rc;
   const size_t smem = (size_t)std::max<int64_t>(1, max_chunks * ncol) * sizeof(double);
   TD_CHECK_CUDA(cudaFuncSetAttribute(windowed_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_PARTIALS * sizeof(double))));
-  windowed_corr_kernel<<<n_seg, CORR_THREADS, smem, st>>>(a, lda, b, ldb, dims, ss_d, sl_d, ws, mode, reduction, mu_a, mu_b, power, wb_d, n_seg, out, out_cols);
+  windowed_corr_kernel<<<n_seg, CORR_THREADS, smem, st>>>(a, lda, b, ldb, dims, ss_d, sl_d, ws, mode, reduction, mu_a, mu_b, power, lda_params, wb_d, n_seg, out, out_cols);
   TD_CHECK_CUDA(cudaGetLastError());
   cudaFreeAsync(ss_d, st);
   cudaFreeAsync(sl_d, st);

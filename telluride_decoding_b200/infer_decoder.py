@@ -7,8 +7,8 @@ callers that feed minibatches, and adds the whole-dataset forms the B200 path us
 `train_statistics(dataset)` (one pass: lagged forward kernel + column-moment kernel) and
 `windowed_results(dataset, window_sizes)` (forward kernel, then ONE pass of the windowed
 correlation kernel for every window size).  `average_data` (:748-783) and `calculate_dprime`
-(:717-745) are here too.  The LDA reducer and SavedModel loading are outside the hot path
-(SURVEY.md section 8f).
+(:717-745) are here too; `train` / `compute_lda_model` / `reduce_with_lda` give the `lda` reducer
+(scaled_lda.py).  SavedModel loading is outside the hot path.
 """
 
 import collections
@@ -19,10 +19,14 @@ import torch
 from telluride_decoding_b200 import brain_model
 from telluride_decoding_b200 import ops
 from telluride_decoding_b200 import result_store
+from telluride_decoding_b200 import scaled_lda
 
 CorrelationParamsTuple = collections.namedtuple('CorrelationParamsTuple', [
     'count', 'sum_x', 'sum_y', 'sum_x2', 'sum_y2', 'mean_x', 'mean_y', 'power'
 ])
+
+ModelParamsTuple = collections.namedtuple('ModelParamsTuple',
+                                          ['correlation_params', 'lda_params'])
 
 _REDUCTIONS = ('mean-squared', 'first', 'second', 'lda', 'all', 'mean')
 
@@ -46,6 +50,7 @@ class Decoder(object):
       raise ValueError('Unknown reduction technique: %s' % reduction)
     self._decoding_model = decoding_model
     self._reduction = reduction
+    self._lda = None
     self.reset_correlation_statistics()
 
   @property
@@ -56,6 +61,32 @@ class Decoder(object):
   def correlation_params(self):
     return CorrelationParamsTuple(self._count, self._sum_x, self._sum_y, self._sum_x2,
                                   self._sum_y2, self._mean_x, self._mean_y, self._power)
+
+  def _set_correlation_params(self, values):
+    values = CorrelationParamsTuple(*values)
+    (self._count, self._sum_x, self._sum_y, self._sum_x2, self._sum_y2, self._mean_x, self._mean_y,
+     self._power) = values
+
+  @property
+  def lda_params(self):
+    if self._lda is None:
+      self._lda = scaled_lda.ScaledLinearDiscriminantAnalysis()
+    return self._lda.model_parameters
+
+  def _set_lda_params(self, values):
+    if self._lda is None:
+      self._lda = scaled_lda.ScaledLinearDiscriminantAnalysis()
+    self._lda.model_parameters = values
+
+  @property
+  def model_params(self):
+    """Correlation statistics and LDA parameters (infer_decoder.py:197-219)."""
+    return ModelParamsTuple(self.correlation_params, self.lda_params)
+
+  @model_params.setter
+  def model_params(self, values):
+    self._set_correlation_params(values.correlation_params)
+    self._set_lda_params(values.lda_params)
 
   def reset_correlation_statistics(self):
     self._count = 0
@@ -104,7 +135,7 @@ class Decoder(object):
     elif self._reduction == 'mean-squared':
       return np.mean(np.sign(correlations) * correlations ** 2, axis=1)
     elif self._reduction == 'lda':
-      raise NotImplementedError('The LDA reducer is outside the B200 hot path.')
+      return self.reduce_with_lda(correlations)[:, 0]
     elif self._reduction == 'all':
       return correlations
     raise ValueError('Unknown reduction technique: %s.' % self._reduction)
@@ -133,6 +164,28 @@ class Decoder(object):
       for r1, r2 in storage.next_window():
         yield r1, r2
 
+  def compute_lda_model(self, d1, d2):
+    """Fits the scaled LDA separating class-0 data d1 from class-1 data d2; returns d'
+    (infer_decoder.py:506-532)."""
+    if not isinstance(d1, np.ndarray):
+      raise TypeError('Input d1 must be an numpy array, not %s.' % type(d1))
+    if not isinstance(d2, np.ndarray):
+      raise TypeError('Input d2 must be an numpy array, not %s.' % type(d2))
+    data = np.concatenate((d1, d2), axis=0)
+    labels = np.concatenate((1 * np.ones(d1.shape[0],), 2 * np.ones(d2.shape[0],)))
+    self._lda = scaled_lda.ScaledLinearDiscriminantAnalysis()
+    predictions = self._lda.fit_transform(data, labels)
+    return calculate_dprime(predictions[labels == 1, 0], predictions[labels == 2, 0])
+
+  def reduce_with_lda(self, d1):
+    """Rotates the data so as to get the maximal separation in dimension 0
+    (infer_decoder.py:534-550)."""
+    if self._lda is None or self._lda.coef_array is None:
+      raise ValueError('Must compute the LDA model before reducing data.')
+    if not isinstance(d1, np.ndarray):
+      raise TypeError('Input data must be an numpy array, not %s.' % type(d1))
+    return self._lda.transform(d1)
+
   # ------------------------------------------------------------- whole-dataset (B200) interface
   def decode_dataset(self, dataset):
     """(result1, result2) float32 CUDA [kept rows, dims] in stream order for a whole dataset."""
@@ -154,6 +207,28 @@ class Decoder(object):
     self._sum_y2 = self._sum_y2 + s[3]
     self._finish_statistics()
 
+  def train(self, data0, data1, window_size=0):
+    """Trains the classification part of the decoder: global statistics, then the scaled LDA on
+    window-averaged correlations; data0 = class 0 (unattended / mixed-up), data1 = class 1.
+    Returns d' (infer_decoder.py:330-400).  Two passes over the data, both on the GPU."""
+    for d in (data0, data1):
+      if not brain_model.is_dataset(d):
+        raise TypeError('Must feed training routine data0 with a tf.data.Dataset'
+                        ' not a %s.' % type(d))
+    self.train_statistics(data0, data1)
+    averaged = []
+    for ds in (data0, data1):
+      r1, r2 = self.decode_dataset(ds)
+      n, dims = int(r1.shape[0]), int(r1.shape[1])
+      if n == 0:
+        raise ValueError('No data for class %d' % len(averaged))
+      mu_a, mu_b, power = self._device_statistics(dims, r1.device)
+      w = max(int(window_size), 1)             # average_data: 0 or 1 means no averaging
+      vals, _ = ops.windowed_corr(r1, r2, [0], [n], [w], [w], 'global_all', mu_a=mu_a, mu_b=mu_b,
+                                  power=power)
+      averaged.append(vals.cpu().numpy())
+    return self.compute_lda_model(averaged[0], averaged[1])
+
   def _device_statistics(self, dims, device):
     f = lambda v: torch.as_tensor(np.broadcast_to(np.asarray(v, dtype=np.float32), (dims,)).copy(),
                                   device=device)
@@ -174,8 +249,14 @@ class Decoder(object):
     r1, r2 = self.decode_dataset(dataset)
     n, dims = int(r1.shape[0]), int(r1.shape[1])
     mu_a, mu_b, power = self._device_statistics(dims, r1.device)
+    lda_params = None
+    if self._reduction == 'lda':
+      if self._lda is None:
+        raise ValueError('Must compute the LDA model before reducing data.')
+      lda_params = torch.as_tensor(self._lda.kernel_parameters(), device=r1.device)
     vals, off = ops.windowed_corr(r1, r2, [0], [n], window_sizes, window_steps, 'global',
-                                  reduction=self._reduction, mu_a=mu_a, mu_b=mu_b, power=power)
+                                  reduction=self._reduction, mu_a=mu_a, mu_b=mu_b, power=power,
+                                  lda_params=lda_params)
     labels = brain_model._stream_order(dataset, dataset.unlagged_rows('a')).contiguous()   # pylint: disable=protected-access
     labs, _ = ops.windowed_corr(labels, None, [0], [n], window_sizes, window_steps, 'plain')
     vals, labs = vals.cpu().numpy()[:, 0], labs.cpu().numpy()[:, 0]

@@ -12,7 +12,7 @@ import torch
 from telluride_decoding_b200 import _lib
 from telluride_decoding_b200._lib import Stream  # re-export  pylint: disable=unused-import
 
-REDUCTIONS = {'first': 0, 'second': 1, 'mean': 2, 'mean-squared': 3}
+REDUCTIONS = {'first': 0, 'second': 1, 'mean': 2, 'mean-squared': 3, 'lda': 5}
 
 
 def _streams_array(streams):
@@ -207,17 +207,18 @@ def window_count(n_frames, width, step):
 
 
 def windowed_corr(a, b, seg_start, seg_len, widths, steps, mode, reduction='first', mu_a=None,
-                  mu_b=None, power=None):
+                  mu_b=None, power=None, lda_params=None):
   """Sliding-window values for every (width, step) shape in one pass over the data.
 
-  mode 'plain' | 'global' | 'local' (see tdgram.h).  Returns (values float64 [windows, cols],
+  mode 'plain' | 'global' | 'local' | 'global_all' (see tdgram.h); reduction 'lda' takes
+  lda_params = float64 CUDA [w_0..w_{dims-1}, slope, intercept].  Returns (values float64 [windows, cols],
   offsets list with n_sizes+1 entries); rows are ordered size, segment, window."""
   _lib.require_cuda()
   lib = _lib.load()
-  mode_id = {'plain': 0, 'global': 1, 'local': 2}[mode]
+  mode_id = {'plain': 0, 'global': 1, 'local': 2, 'global_all': 3}[mode]
   dims = int(a.shape[1]) if mode_id else 1
   total = sum(window_count(n, w, s) for w, s in zip(widths, steps) for n in seg_len)
-  cols = dims if mode_id == 2 else 1
+  cols = dims if mode_id >= 2 else 1
   out = torch.empty((max(total, 1), cols), dtype=torch.float64, device=a.device)
   offsets = (ctypes.c_int64 * (len(widths) + 1))()
   with torch.cuda.device(a.device):
@@ -226,7 +227,7 @@ def windowed_corr(a, b, seg_start, seg_len, widths, steps, mode, reduction='firs
         ctypes.c_int64(b.stride(0) if b is not None else 0), dims, _lib.i64_array(seg_start),
         _lib.i64_array(seg_len), len(seg_len), _lib.i64_array(widths), _lib.i64_array(steps),
         len(widths), mode_id, REDUCTIONS.get(reduction, 0), _lib.ptr(mu_a), _lib.ptr(mu_b),
-        _lib.ptr(power), _lib.ptr(out), offsets, _lib.current_stream_ptr()))
+        _lib.ptr(power), _lib.ptr(lda_params), _lib.ptr(out), offsets, _lib.current_stream_ptr()))
   return out[:total], [int(o) for o in offsets]
 
 

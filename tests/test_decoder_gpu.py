@@ -154,3 +154,63 @@ def test_decoder_end_to_end_attention_accuracy():
   want, want_lab = ora.windowed_means(sig, label, 200)
   np.testing.assert_allclose(res[0], want, rtol=1e-3, atol=1e-5)
   np.testing.assert_array_equal(res[1], want_lab)
+
+
+def test_lda_training_and_windows_match_reference(golden_dir):
+  """Decoder.train (global statistics + scaled LDA on 7-frame averages) and the 'lda' reducer in
+  the window kernel against the reference's Decoder / scaled_lda run on the same signals."""
+  g = _golden(golden_dir)
+  lg = np.load(os.path.join(golden_dir, 'lda.npz'))
+  t = lambda v: torch.as_tensor(np.ascontiguousarray(v), device='cuda')
+  n = g['truth'].shape[0]
+
+  class FixedDecoder(infer_decoder.Decoder):
+    """decode_dataset returns prepared model outputs; each class uses its own statistics like the
+    fixture (the reference fixture trained one correlator per speaker)."""
+    def decode_dataset(self, dataset):
+      return dataset
+
+  # class-wise correlation signals with the fixture's per-speaker statistics, all columns
+  avg = []
+  for which, p in (('s2', g['pred2']), ('s1', g['pred'])):
+    cor = _stats(g['truth'], p)
+    vals, _ = ops.windowed_corr(t(g['truth']), t(p), [0], [n], [7], [7], 'global_all',
+                                mu_a=t(cor.mean_x), mu_b=t(cor.mean_y), power=t(cor.power))
+    avg.append(vals.cpu().numpy())
+  np.testing.assert_allclose(avg[0], lg['avg0'], rtol=1e-12, atol=1e-14)
+  np.testing.assert_allclose(avg[1], lg['avg1'], rtol=1e-12, atol=1e-14)
+  dec = FixedDecoder(lambda d: None, reduction='lda')
+  dprime = dec.compute_lda_model(avg[0], avg[1])
+  assert abs(dprime - float(lg['dprime'])) < 1e-8
+  # 'lda' windows of speaker 1 through the kernel
+  cor = _stats(g['truth'], g['pred'])
+  dec._set_correlation_params([cor.count, cor.sum_x, cor.sum_y, cor.sum_x2, cor.sum_y2,
+                               cor.mean_x, cor.mean_y, cor.power])
+  bd = gpu_util.make_test_data(g['truth'], g['truth'][:, :1], a=g['label'], final_batch_size=200)
+  ds = bd.create_dataset('test')
+  dec.decode_dataset = lambda dataset: (t(g['truth']), t(g['pred']))
+  res = dec.windowed_results(ds, WINDOWS)
+  for w in WINDOWS:
+    np.testing.assert_allclose(res[w][0], lg['lda_w%d_res' % w], rtol=1e-9, atol=1e-11)
+    np.testing.assert_array_equal(res[w][1], g['s1_first_w%d_lab' % w])
+  # the whole-dataset train(): statistics pooled over both classes, then LDA; d' is large
+  dec2 = FixedDecoder(lambda d: None, reduction='lda')
+  dec2.decode_dataset = lambda dataset: dataset
+  class _DS(tuple):
+    pass
+  import telluride_decoding_b200.brain_model as bm
+  orig = bm.is_dataset
+  bm.is_dataset = lambda o: True
+  try:
+    d2 = dec2.train((t(g['truth']), t(g['pred2'])), (t(g['truth']), t(g['pred'])), window_size=7)
+  finally:
+    bm.is_dataset = orig
+  pooled = ora.Correlator()
+  for p in (g['pred2'], g['pred']):
+    for s in range(0, n, 200):
+      pooled.add(g['truth'][s:s + 200], p[s:s + 200])
+  c0 = ora.average_data(pooled.correlate(g['truth'], g['pred2']).astype(np.float64), 7)
+  c1 = ora.average_data(pooled.correlate(g['truth'], g['pred']).astype(np.float64), 7)
+  ref = infer_decoder.Decoder(lambda d: None, reduction='lda')
+  want = ref.compute_lda_model(c0, c1)
+  assert abs(d2 - want) < 1e-3 * abs(want) and d2 > 1.0

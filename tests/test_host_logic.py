@@ -195,3 +195,38 @@ def test_regularization_parsing_and_options():
   assert 'batch_size=100' in opts.experiment_parameters()
   with pytest.raises(TypeError, match='DecodingOptions'):
     decoding.create_brain_model({}, None)
+
+
+def test_scaled_lda_matches_reference(golden_dir):
+  """Host-side LDA (float64 numpy) against the unmodified reference's scaled_lda / Decoder."""
+  from telluride_decoding_b200 import scaled_lda
+  g = np.load(os.path.join(golden_dir, 'lda.npz'))
+  lda = scaled_lda.ScaledLinearDiscriminantAnalysis()
+  got = lda.fit_transform(g['toy_x'], g['toy_y'])
+  # two classes: inv(Sw) Sb has rank one, so only the first axis is determined (the second is an
+  # arbitrary null-space vector that depends on summation order)
+  np.testing.assert_allclose(got[:, 0], g['toy_transform'][:, 0], rtol=1e-9, atol=1e-10)
+  np.testing.assert_allclose(lda.model_parameters.slope, g['toy_slope'], rtol=1e-9)
+  np.testing.assert_allclose(lda.explained_variance_ratio()[0], g['toy_evr'][0], rtol=1e-7)
+  assert lda.labels == [4.0, 9.0]
+  with pytest.raises(ValueError, match='two-class data'):
+    scaled_lda.ScaledLinearDiscriminantAnalysis().fit(g['toy_x'], np.arange(350) % 3)
+  with pytest.raises(ValueError, match='Must fit the model'):
+    scaled_lda.LinearDiscriminantAnalysis().transform(g['toy_x'])
+  # Decoder.compute_lda_model / reduce_with_lda on the averaged correlation signals
+  dec = infer_decoder.Decoder(lambda d: None, reduction='lda')
+  dprime = dec.compute_lda_model(g['avg0'], g['avg1'])
+  assert abs(dprime - float(g['dprime'])) < 1e-9
+  p = dec.lda_params
+  np.testing.assert_allclose(p.w_real[:, 0], g['w_real'][:, 0], rtol=1e-8, atol=1e-12)
+  np.testing.assert_allclose(p.slope, g['slope'], rtol=1e-9)
+  d = np.load(os.path.join(golden_dir, 'decoder.npz'))
+  np.testing.assert_allclose(dec.reduce_with_lda(d['s1_corr'])[:, 0], g['transform_s1'][:, 0],
+                             rtol=1e-9, atol=1e-12)
+  with pytest.raises(ValueError, match='Must compute the LDA model'):
+    infer_decoder.Decoder(lambda d: None, reduction='lda').reduce_with_lda(d['s1_corr'])
+  # parameters survive a round trip through model_params
+  other = infer_decoder.Decoder(lambda d: None, reduction='lda')
+  other.model_params = dec.model_params
+  np.testing.assert_allclose(other.reduce_with_lda(d['s1_corr'])[:, 0], g['transform_s1'][:, 0],
+                             rtol=1e-9, atol=1e-12)
