@@ -187,6 +187,12 @@ class ClockSampler(object):
 # This framework
 # ----------------------------------------------------------------------------------------------
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one Gram launch on the bench workload (ncu --set
+# full capture, profiles/r01_ncu_gram_kernel_summary.txt): 533.2 MB + 35.3 MB.  The staged planes are
+# 4 x 118 MB and are read once (L2 hit rate 86 %), the Gram is written once.
+GRAM_DRAM_TRAFFIC_BYTES = 568439552
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -362,6 +368,40 @@ def main():
   # 64-column panel potf2 + copy (factor) and one back-substitution kernel
   n_panels = (CFG['channels'] * (CFG['pre'] + 1 + CFG['post']) + 1 + 63) // 64
   n_launch = 5 + 5 + 3 * n_panels
+
+  # ---- AAD leg (BASELINE.json configs[4]): sliding-window correlation + winner-take-all ----------
+  aad = None
+  if world == 1:
+    trials_a, frames_a = 1000, 7680                     # 60 s @128 Hz per trial
+    na = trials_a * frames_a
+    gen = torch.Generator(device=dev); gen.manual_seed(5)
+    env = torch.randn((na, 1), generator=gen, device=dev)
+    p1 = (0.3 * env + torch.randn((na, 1), generator=gen, device=dev)).contiguous()   # attended
+    p2 = torch.randn((na, 1), generator=gen, device=dev)                             # unattended
+    mu = torch.zeros(1, device=dev); pw = torch.ones(1, device=dev)
+    widths = [128, 256, 640, 1280, 2560, 3840]          # 1, 2, 5, 10, 20, 30 s windows
+    steps_w = [w // 2 for w in widths]
+    starts = [i * frames_a for i in range(trials_a)]
+    lens = [frames_a] * trials_a
+    def aad_step():
+      r1, _ = ops.windowed_corr(env, p1, starts, lens, widths, steps_w, 'global', reduction='first',
+                                mu_a=mu, mu_b=mu, power=pw)
+      r2, _ = ops.windowed_corr(env, p2, starts, lens, widths, steps_w, 'global', reduction='first',
+                                mu_a=mu, mu_b=mu, power=pw)
+      return ops.wta_decide(r1, r2)
+    for _ in range(3):
+      dec = aad_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+      dec = aad_step()
+    torch.cuda.synchronize()
+    aad_ms = (time.perf_counter() - t0) / 5 * 1e3
+    aad = dict(workload='cfg5: 1000 trials x 7680 frames, 2 speakers, windows 1/2/5/10/20/30 s (step W/2), '
+                        'global-statistics correlation, reduction first, winner-take-all',
+               windows_per_s=2 * int(dec.numel()) / (aad_ms * 1e-3), decisions=int(dec.numel()),
+               ms=aad_ms, accuracy=float(dec.float().mean().item()),
+               note='wall clock of the public ops incl. host-side table building; kernel-only numbers in profiles/')
   line = dict(
       metric=METRIC, value=world * frames / (ms_per_step * 1e-3), unit='frames/s', n_gpus=world,
       steps=args.steps, warmup=warmup, ms_per_step=ms_per_step, higher_is_better=True,
@@ -374,13 +414,15 @@ def main():
       tflops_alg=world * f_alg / (ms_per_step * 1e-3) / 1e12,
       gram_kernel_ms=gram_kernel_ms, step_wall_ms=wall / args.steps * 1e3,
       roofline=dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s',
-                    frac=achieved / peak, traffic=None, kernel='lagged_gram_umma_kernel',
+                    frac=achieved / peak, traffic=GRAM_DRAM_TRAFFIC_BYTES if world == 1 else None,
+                    traffic_source='profiles/r01_ncu_gram_kernel_summary.txt (ncu --set full, same workload)',
+                    kernel='lagged_gram_umma_kernel',
                     flops_per_launch=f_alg, peak_source=peak_note, tf32_dense_live_tflops=tf32_live,
                     frac_of_live_tf32_over_3=achieved / (tf32_live / 3.0)),
       e2e=dict(value=world * frames / (e2e_ms * 1e-3), unit='frames/s',
                h2d_bytes_per_step=int(x_pin.numel() * 4 + y_pin.numel() * 4),
                d2h_bytes_per_step=int(w_host.numel() * 4), ms_per_step=e2e_ms),
-      clocks=clocks, cpu_baseline=cpu)
+      clocks=clocks, cpu_baseline=cpu, aad=aad)
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()

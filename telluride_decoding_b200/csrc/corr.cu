@@ -75,6 +75,90 @@ __device__ __forceinline__ double frame_signal(const float* a, const float* b, i
   return (double)(s / (float)dims);
 }
 
+// Same per-frame scalar from rows already held in registers (float4-loaded), DIMS known at compile
+// time.  mu / power / lda point to shared memory.
+template <int DIMS>
+__device__ __forceinline__ double frame_signal_regs(const float (&a)[DIMS], const float (&b)[DIMS],
+                                                    int reduction, const float* mu_a,
+                                                    const float* mu_b, const float* power,
+                                                    const double* lda) {
+  float c[DIMS];
+#pragma unroll
+  for (int d = 0; d < DIMS; ++d) c[d] = ((a[d] - mu_a[d]) * (b[d] - mu_b[d])) / power[d];
+  if (reduction == 0) return (double)c[0];
+  if (reduction == 1) return (double)c[1];
+  if (reduction == 5) {
+    double acc = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) acc += (double)c[d] * lda[d];
+    return lda[DIMS] * acc + lda[DIMS + 1];
+  }
+  if (reduction == 3) {
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) {
+      const float sg = (c[d] > 0.0f) ? 1.0f : ((c[d] < 0.0f) ? -1.0f : 0.0f);
+      c[d] = sg * (c[d] * c[d]);
+    }
+  }
+  float s;
+  if (DIMS < 8) {                      // numpy: plain left-to-right sum below 8 values
+    s = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) s += c[d];
+  } else {                             // numpy: eight interleaved accumulators, pairwise combine
+    float r[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) r[d] = c[d];
+#pragma unroll
+    for (int d = 8; d < DIMS; ++d) r[d & 7] += c[d];
+    s = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  }
+  return (double)(s / (float)DIMS);
+}
+
+// Phase-1 fast path: rows of DIMS floats (DIMS % 4 == 0) fetched with 16-byte loads.
+template <int DIMS>
+__device__ __forceinline__ void chunk_sums_vec(const float* A, long long lda_a, const float* B,
+                                               long long ldb, long long nchunk, long long g, int mode,
+                                               int reduction, const float* mu_a, const float* mu_b,
+                                               const float* power, const double* lda, double* part,
+                                               int warp, int lane, int nwarp) {
+  for (long long ch = warp; ch < nchunk; ch += nwarp) {
+    double s = 0.0;
+    double sd[DIMS];
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) sd[d] = 0.0;
+    for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32) {
+      float av[DIMS], bv[DIMS];
+      const float4* pa = reinterpret_cast<const float4*>(A + t * lda_a);
+      const float4* pb = reinterpret_cast<const float4*>(B + t * ldb);
+#pragma unroll
+      for (int v = 0; v < DIMS / 4; ++v) {
+        const float4 x = __ldg(pa + v), y = __ldg(pb + v);
+        av[4 * v] = x.x; av[4 * v + 1] = x.y; av[4 * v + 2] = x.z; av[4 * v + 3] = x.w;
+        bv[4 * v] = y.x; bv[4 * v + 1] = y.y; bv[4 * v + 2] = y.z; bv[4 * v + 3] = y.w;
+      }
+      if (mode == 1) {
+        s += frame_signal_regs<DIMS>(av, bv, reduction, mu_a, mu_b, power, lda);
+      } else {
+#pragma unroll
+        for (int d = 0; d < DIMS; ++d)
+          sd[d] += (double)(((av[d] - mu_a[d]) * (bv[d] - mu_b[d])) / power[d]);
+      }
+    }
+    if (mode == 1) {
+      s = warp_sum(s);
+      if (lane == 0) part[ch] = s;
+    } else {
+#pragma unroll
+      for (int d = 0; d < DIMS; ++d) {
+        const double v = warp_sum(sd[d]);
+        if (lane == 0) part[ch * DIMS + d] = v;
+      }
+    }
+  }
+}
+
 // One block per segment.  ncol partial columns per g-frame chunk:
 //   mode 0/1: 1 (the reduced signal)     mode 2: 5*dims (a, b, aa, bb, ab per column)
 __global__ void __launch_bounds__(CORR_THREADS)
@@ -95,8 +179,28 @@ windowed_corr_kernel(const float* __restrict__ a, long long lda_a, const float* 
   const float* B = b ? b + seg_start[seg] * ldb : nullptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
 
+  // Global statistics (and LDA axis) staged once per block.
+  __shared__ float s_mu_a[128], s_mu_b[128], s_power[128];
+  __shared__ double s_lda[130];
+  if (mode == 1 || mode == 3) {
+    for (int d = threadIdx.x; d < dims; d += blockDim.x) {
+      s_mu_a[d] = mu_a[d]; s_mu_b[d] = mu_b[d]; s_power[d] = power[d];
+    }
+    if (lda) for (int d = threadIdx.x; d < dims + 2; d += blockDim.x) s_lda[d] = lda[d];
+    __syncthreads();
+    mu_a = s_mu_a; mu_b = s_mu_b; power = s_power;
+    if (lda) lda = s_lda;
+  }
+
   // ---- phase 1: partial sums per chunk ------------------------------------------------------
-  if (g >= 32) {
+  const bool vec_ok = (mode == 1 || mode == 3) && g >= 32 && (dims == 4 || dims == 8 || dims == 16) &&
+                      (lda_a % 4 == 0) && (ldb % 4 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0);
+  if (vec_ok) {
+    if (dims == 4) chunk_sums_vec<4>(A, lda_a, B, ldb, nchunk, g, mode, reduction, mu_a, mu_b, power, lda, part, warp, lane, nwarp);
+    else if (dims == 8) chunk_sums_vec<8>(A, lda_a, B, ldb, nchunk, g, mode, reduction, mu_a, mu_b, power, lda, part, warp, lane, nwarp);
+    else chunk_sums_vec<16>(A, lda_a, B, ldb, nchunk, g, mode, reduction, mu_a, mu_b, power, lda, part, warp, lane, nwarp);
+  } else if (g >= 32) {
     for (long long ch = warp; ch < nchunk; ch += nwarp) {
       if (mode < 2) {
         double s = 0.0;

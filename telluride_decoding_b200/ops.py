@@ -217,7 +217,8 @@ def windowed_corr(a, b, seg_start, seg_len, widths, steps, mode, reduction='firs
   lib = _lib.load()
   mode_id = {'plain': 0, 'global': 1, 'local': 2, 'global_all': 3}[mode]
   dims = int(a.shape[1]) if mode_id else 1
-  total = sum(window_count(n, w, s) for w, s in zip(widths, steps) for n in seg_len)
+  total = sum(((n - w) // s + 1) for w, s in zip(widths, steps) for n in seg_len
+              if w > 0 and s > 0 and n >= w)
   cols = dims if mode_id >= 2 else 1
   out = torch.empty((max(total, 1), cols), dtype=torch.float64, device=a.device)
   offsets = (ctypes.c_int64 * (len(widths) + 1))()
