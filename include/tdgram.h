@@ -69,13 +69,15 @@ int td_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * The design is Z = [X_0 | X_1 | ...] over n_streams (1 or 2) lagged streams sharing the
  * segment table; G = Z'Z, [Dz, Dz] with Dz = sum_q channels_q * (pre_q+1+post_q), full
  * symmetric, row stride ldg.  method 0: tcgen05 3xTF32 implicit-Hankel kernel (raw tiles TMA-staged,
- * hi/lo split built in shared memory, TMEM fp32 accumulation flushed every `chunk_rows` frames
- * into fp32 registers);
+ * hi/lo split built on chip, TMEM fp32 accumulation flushed every `chunk_rows` frames into fp32
+ * registers); it picks between the two flavours that can also be forced: method 2 = both operands
+ * from shared memory (the only one for cta_group 1), method 3 = A operand in tensor memory (CTA pairs
+ * only; the default whenever the plan uses CTA pairs).
  * method 1: fp32 CUDA-core kernel kept as an on-device cross-check.
  * Workspace: td_lagged_gram_workspace_bytes bytes of device memory.
  * ------------------------------------------------------------------------------------- */
 typedef struct td_gram_options {
-  int32_t method;        /* 0 = tcgen05 3xTF32 (default), 1 = fp32 SIMT cross-check */
+  int32_t method;        /* 0 = tcgen05 3xTF32 (default), 1 = fp32 SIMT cross-check, 2 / 3 = force a tcgen05 flavour */
   int32_t cta_group;     /* 0 = auto, 1 = 128x128 tiles per CTA, 2 = CTA-pair 256x256 tiles */
   int32_t chunk_rows;    /* TMEM flush period in frames (0 = default 128) */
   int32_t superchunk_rows; /* L2 working-set period in frames (0 = auto) */

@@ -74,6 +74,7 @@ struct GramParams {
   int KS;                 // k-tiles per superchunk
   int chunk_kt;           // k-tiles per TMEM flush
   long long total_steps;  // NSC * ntri * KS
+  long long* prof;        // development: per-CTA stall clocks of the TS kernel (null in production)
 };
 
 struct WorkItem {
@@ -171,6 +172,8 @@ __device__ __forceinline__ void split_tile(uint32_t raw, uint32_t lo, int begin,
   __syncwarp();
 }
 
+#include "gram_ts.cuh"
+
 // CG = 1: one CTA per 128x128 tile.  CG = 2: a CTA pair (cluster of 2) per 256x256 tile, each CTA
 // staging 128 rows of A and 128 rows of B; the pair leader issues tcgen05.mma.cta_group::2.
 template <int CG>
@@ -223,18 +226,22 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane) =====================
-    if (lane == 0) {
-      WorkIter wi(P, worker, n_workers);
-      WorkItem it;
-      int stage = 0;
-      uint32_t phase = 0;
-      while (wi.next(P, it)) {
-        const int ga = (it.tm * CG + (int)rank) * P.groups_per_tile;
-        const int gb = (it.tn * CG + (int)rank) * P.groups_per_tile;
-        for (long long kt = it.kt_begin; kt < it.kt_end; ++kt) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          const int2 kti = __ldg(&P.ktiles[kt]);
+    // ===================== TMA producer (whole warp loops, one elected lane issues) ==============
+    // (Issuing under `if (lane == 0)` makes ptxas wrap every TMA / MMA in an elect + R2UR.BROADCAST
+    // loop, ~80 clocks per instruction; under elect.sync the operands go straight to uniform registers.)
+    WorkIter wi(P, worker, n_workers);
+    WorkItem it;
+    int stage = 0;
+    uint32_t phase = 0;
+    while (wi.next(P, it)) {
+      const int ga = (it.tm * CG + (int)rank) * P.groups_per_tile;
+      const int gb = (it.tn * CG + (int)rank) * P.groups_per_tile;
+      int kt_time = __ldg(&P.ktiles[it.kt_begin]).x;
+      for (long long kt = it.kt_begin; kt < it.kt_end; ++kt) {
+        const int t0 = kt_time;
+        if (kt + 1 < it.kt_end) kt_time = __ldg(&P.ktiles[kt + 1]).x;
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (ptx::elect_one()) {
           const uint32_t fb = full_bar(stage);
           ptx::mbar_expect_tx(fb, TMA_BYTES);
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
@@ -245,12 +252,13 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
 #pragma unroll 1
             for (int g = 0; g < P.groups_per_tile; ++g) {
               const int4 gd = __ldg(&P.groups[g0 + g]);
-              ptx::tma_load_3d(obase + g * P.CB * (BK * 4), gd.x ? &tmap1 : &tmap0, fb, kti.x + gd.y,
+              ptx::tma_load_3d(obase + g * P.CB * (BK * 4), gd.x ? &tmap1 : &tmap0, fb, t0 + gd.y,
                                gd.z, gd.w);
             }
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp >= 2 + NUM_EPI_WARPS) {
@@ -286,6 +294,7 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
     const bool issuer = (CG == 1 || rank == 0);
     const uint32_t pready_leader0 = (CG == 2) ? ptx::mapa(pready_bar(0), 0) : 0u;
     while (wi.next(P, it)) {
+      int next_range = __ldg(&P.ktiles[it.kt_begin]).y;
       for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
         const long long c1 = min(it.kt_end, c0 + (long long)P.chunk_kt);
         if (issuer) {
@@ -293,20 +302,21 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
           ptx::tc_fence_after();
         }
         for (long long kt = c0; kt < c1; ++kt) {
-          const int range = __ldg(&P.ktiles[kt]).y;
+          const int range = next_range;
+          if (kt + 1 < it.kt_end) next_range = __ldg(&P.ktiles[kt + 1]).y;
           const int begin = range & 0xff, end = range >> 8;
           const uint32_t sbase = smem_base + stage * STAGE_BYTES;
           ptx::mbar_wait(conv_bar(stage), phase);
           if constexpr (CG == 2) {
             if (!issuer) {
-              if (lane == 0) ptx::mbar_arrive_cluster(pready_leader0 + 8u * stage);
+              if (lane == 0) ptx::mbar_arrive_remote(pready_leader0 + 8u * stage);
             } else {
               ptx::mbar_wait(pready_bar(stage), phase);
             }
           }
           if (issuer) {
             ptx::tc_fence_after();
-            if (lane == 0) {
+            if (ptx::elect_one()) {
               const int ks0 = begin >> 3, ks1 = (end + 7) >> 3;
               const uint32_t d = tmem_base + (uint32_t)(buf * BN);
               const uint64_t a_hi = ptx::umma_desc_k_sw128(sbase);
@@ -362,7 +372,7 @@ lagged_gram_umma_kernel(const __grid_constant__ CUtensorMap tmap0,
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CG == 2) ptx::mbar_arrive_cluster(tempty_leader0 + 8u * buf);
+          if constexpr (CG == 2) ptx::mbar_arrive_remote(tempty_leader0 + 8u * buf);
           else ptx::mbar_arrive(tempty_bar(buf));
         }
         buf ^= 1;
@@ -606,6 +616,8 @@ extern "C" int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_st
                                               int n_seg, const td_gram_options* opt, size_t* bytes) {
   TD_REQUIRE(streams && seg_keep && bytes, "td_lagged_gram_workspace_bytes: null argument");
   if (opt && opt->method == 1) { *bytes = 0; return TD_OK; }
+  TD_REQUIRE(opt == nullptr || (opt->method >= 0 && opt->method <= 3),
+             "td_lagged_gram_workspace_bytes: unknown method %d", opt->method);
   GramPlan pl;
   int rc = make_plan(streams, n_streams, seg_first, seg_keep, n_seg, opt, &pl);
   if (rc) return rc;
@@ -646,10 +658,22 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
     TD_REQUIRE(ldg >= Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)Dz);
     return launch_gram_simt(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, st);
   }
-  TD_REQUIRE(opt == nullptr || opt->method == 0, "td_lagged_gram_f32: unknown method %d", opt->method);
+  TD_REQUIRE(opt == nullptr || (opt->method >= 0 && opt->method <= 3),
+             "td_lagged_gram_f32: unknown method %d", opt->method);
   GramPlan pl;
   int rc = make_plan(streams, n_streams, seg_first, seg_keep, n_seg, opt, &pl);
   if (rc) return rc;
+  // Kernel flavour: 2 = operands from shared memory, 3 = A operand from tensor memory (CTA pairs
+  // only); 0 picks 3 whenever the plan uses CTA pairs.  TD_GRAM_METHOD overrides 0 (experiments).
+  int flavour = opt ? opt->method : 0;
+  if (flavour == 0) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("TD_GRAM_METHOD"); env = e ? atoi(e) : 0; }
+    flavour = (env == 2 || env == 3) ? env : 0;
+  }
+  if (flavour == 0) flavour = (pl.cg == 2) ? 3 : 2;
+  TD_REQUIRE(flavour == 2 || pl.cg == 2,
+             "td_lagged_gram_f32: method 3 (A operand in tensor memory) needs cta_group 2");
   TD_REQUIRE(ldg >= pl.Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)pl.Dz);
   if (workspace_bytes < pl.total || !workspace) {
     set_error("td_lagged_gram_f32: workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
@@ -773,6 +797,13 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
     if (opt && opt->max_ctas > 0) workers = std::max(1, std::min(workers, opt->max_ctas / pl.cg));
     // No more workers than there are chunk-sized pieces of work in a superchunk.
     workers = (int)std::max<int64_t>(1, std::min<int64_t>(workers, ceil_div((int64_t)pl.ntri * ks, P.chunk_kt)));
+    P.prof = nullptr;
+#ifdef TD_TS_PROFILE
+    long long* prof_dev = nullptr;
+    TD_CHECK_CUDA(cudaMalloc(&prof_dev, (size_t)sms * 24 * sizeof(long long)));
+    TD_CHECK_CUDA(cudaMemsetAsync(prof_dev, 0, (size_t)sms * 24 * sizeof(long long), st));
+    P.prof = prof_dev;
+#endif
     const bool timed = opt && opt->reserved[0] == 1;
     if (timed) {
       if (!g_ev_start) {
@@ -781,7 +812,22 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       }
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
-    if (pl.cg == 1) {
+    if (flavour == 3) {
+      TD_CHECK_CUDA(cudaFuncSetAttribute(ts::lagged_gram_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts::SMEM_BYTES));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(workers * 2);
+      cfg.blockDim = dim3(ts::NUM_THREADS);
+      cfg.dynamicSmemBytes = ts::SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ts::lagged_gram_ts_kernel, tmaps[0], tmaps[1], P));
+    } else if (pl.cg == 1) {
       TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
       lagged_gram_umma_kernel<1><<<workers, NUM_THREADS, SMEM_BYTES, st>>>(tmaps[0], tmaps[1], P);
     } else {
@@ -805,9 +851,31 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       TD_CHECK_CUDA(cudaEventRecord(g_ev_stop, st));
       g_ev_valid = true;
     }
+#ifdef TD_TS_PROFILE
+    {
+      std::vector<long long> h((size_t)sms * 24);
+      TD_CHECK_CUDA(cudaStreamSynchronize(st));
+      TD_CHECK_CUDA(cudaMemcpy(h.data(), prof_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(prof_dev);
+      const char* names[24] = {"prod wait empty", "mma1 wait ready", "mma0 wait ready", "mma0 wait tempty", "mma1 wait tempty",
+                               "mma1 other", "mma0 other", "mma1 issue+commit", "conv wait full", "conv lds+cvt+sts", "conv wait aempty",
+                               "conv loop top", "conv st+arrive", "mma1 total", "mma0 total", "prod total", "mma0 issue+commit",
+                               "conv total", "epi wait tfull", "epi drain", "epi store+other", "epi total", "", ""};
+      for (int r = 0; r < 2; ++r) {
+        fprintf(stderr, "[tdgram prof] rank %d (avg Mclk over CTAs):", r);
+        for (int i = 0; i < 24; ++i) {
+          if (!names[i][0]) continue;
+          double sum = 0; int n = 0;
+          for (int b = r; b < workers * 2; b += 2) { sum += (double)h[(size_t)b * 24 + i]; ++n; }
+          fprintf(stderr, "  %s=%.2f", names[i], sum / n / 1e6);
+        }
+        fprintf(stderr, "\n");
+      }
+    }
+#endif
     if (debug_enabled())
-      fprintf(stderr, "[tdgram] gram launch: cg=%d workers=%d CB=%d Dz=%lld Dpad=%lld ntri=%d NK=%lld KS=%d chunk_kt=%d total=%lld Tp=%lld\n",
-              pl.cg, workers, pl.CB, (long long)pl.Dz, (long long)pl.Dpad, pl.ntri, (long long)pl.NK, P.KS, P.chunk_kt,
+      fprintf(stderr, "[tdgram] gram launch: flavour=%d cg=%d workers=%d CB=%d Dz=%lld Dpad=%lld ntri=%d NK=%lld KS=%d chunk_kt=%d total=%lld Tp=%lld\n",
+              flavour, pl.cg, workers, pl.CB, (long long)pl.Dz, (long long)pl.Dpad, pl.ntri, (long long)pl.NK, P.KS, P.chunk_kt,
               (long long)P.total_steps, (long long)pl.Tp);
     if ((rc = debug_sync(st, "gram kernel"))) return rc;
   }

@@ -26,7 +26,9 @@ def _dataset(n, c, pre, post, batch, seed, c2=1, pre2=0, post2=0, offset=0, chun
   return ds, batches
 
 
-@pytest.mark.parametrize('cta_group', [1, 2])
+# (cta_group, method): 128x128 tiles; CTA pairs with the A operand in tensor memory (the default
+# for pairs); CTA pairs with both operands in shared memory.
+@pytest.mark.parametrize('cta_group,method', [(1, 0), (2, 0), (2, 2)])
 @pytest.mark.parametrize('n,c,pre,post,batch', [
     (1000, 2, 1, 1, 100),       # C=2, L=3 (SURVEY build-plan shape)
     (1000, 3, 1, 2, 100),       # golden ridge_small shape
@@ -35,11 +37,11 @@ def _dataset(n, c, pre, post, batch, seed, c2=1, pre2=0, post2=0, offset=0, chun
     (2501, 8, 0, 7, 300),       # rows lost to drop_remainder (tail mask)
     (4100, 148, 3, 3, 1000),    # MEG fixture width, channel padding 148 -> 160
 ])
-def test_gram_matches_oracle(n, c, pre, post, batch, cta_group):
+def test_gram_matches_oracle(n, c, pre, post, batch, cta_group, method):
   ds, batches = _dataset(n, c, pre, post, batch, seed=n + c)
   (w, keep), = ds.passes()
   g = ops.lagged_gram([ds.stream('x')], keep,
-                      options=ops.gram_options(cta_group=cta_group)).cpu().numpy()
+                      options=ops.gram_options(method=method, cta_group=cta_group)).cpu().numpy()
   x64 = gpu_util.design64(batches)
   want = x64.T @ x64
   assert gpu_util.rel_fro(g, want) < GRAM_TOL
