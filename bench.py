@@ -158,9 +158,11 @@ class ClockSampler(object):
     for line in self.proc.stdout:
       parts = [p.strip() for p in line.split(',')]
       if len(parts) >= 7:
-        self.samples.append(parts)
+        self.samples.append((time.time(), parts))
 
-  def stop(self):
+  def stop(self, windows=None):
+    """Median SM clock and throttle reasons of the samples taken inside `windows` (list of
+    (t0, t1) wall-clock intervals = the timed regions); all samples if none fell inside."""
     if self.proc is None:
       return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
     self.proc.terminate()
@@ -169,7 +171,10 @@ class ClockSampler(object):
     except subprocess.TimeoutExpired:
       self.proc.kill()
     sm, mx, reasons = [], [], set()
-    for p in self.samples:
+    inside = [p for t, p in self.samples
+              if windows and any(a <= t <= b + 0.03 for a, b in windows)]
+    in_window = bool(inside)
+    for p in (inside or [p for _, p in self.samples]):
       try:
         sm.append(float(p[0])); mx.append(float(p[1]))
       except ValueError:
@@ -180,7 +185,7 @@ class ClockSampler(object):
           reasons.add(name)
     return dict(sm_mhz=float(np.median(sm)) if sm else None,
                 sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
-                samples=len(sm))
+                samples=len(sm), sampled='inside the timed regions' if in_window else 'whole run')
 
 
 # ----------------------------------------------------------------------------------------------
@@ -188,9 +193,9 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one Gram launch on the bench workload (ncu --set
-# full capture, profiles/r01_ncu_gram_kernel_summary.txt): 533.2 MB + 35.3 MB.  The staged planes are
-# 4 x 118 MB and are read once (L2 hit rate 86 %), the Gram is written once.
-GRAM_DRAM_TRAFFIC_BYTES = 568439552
+# full capture, profiles/r01_ncu_gram_kernel_summary.txt): 554.0 MB + 42.1 MB.  The staged planes are
+# 4 x 118 MB and are read once (L2 hit rate 97 %), the Gram is written once.
+GRAM_DRAM_TRAFFIC_BYTES = 596103936
 
 
 def main():
@@ -268,17 +273,18 @@ def main():
       dist.barrier()
     torch.cuda.synchronize()
 
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()                                # nvidia-smi needs ~0.2 s to deliver its first sample
   for _ in range(warmup):
     fit(ds_res)
   barrier()
-  sampler = ClockSampler(local_rank)
-  if rank == 0:
-    sampler.start()
   ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         for _ in range(args.steps)]
   gram_ms = []
   barrier()
   wall0 = time.perf_counter()
+  win0 = time.time()
   for i in range(args.steps):
     flush.zero_()                                  # evict L2 between timed iterations
     if world > 1:
@@ -289,7 +295,7 @@ def main():
     gram_ms.append(ops.last_gram_kernel_ms())
   barrier()
   wall = time.perf_counter() - wall0
-  clocks = sampler.stop() if rank == 0 else None
+  windows = [(win0, time.time())]
   step_ms = [a.elapsed_time(b) for a, b in ev]
   t_res = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
   if world > 1:
@@ -307,6 +313,7 @@ def main():
     e2e_step()
   barrier()
   e2e_ev = []
+  win0 = time.time()
   for i in range(args.steps):
     flush.zero_()
     if world > 1:
@@ -317,6 +324,8 @@ def main():
     b.record()
     e2e_ev.append((a, b))
   barrier()
+  windows.append((win0, time.time()))
+  clocks = sampler.stop(windows) if rank == 0 else None
   t_e2e = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_ev)], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -416,7 +425,7 @@ def main():
       roofline=dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s',
                     frac=achieved / peak, traffic=GRAM_DRAM_TRAFFIC_BYTES if world == 1 else None,
                     traffic_source='profiles/r01_ncu_gram_kernel_summary.txt (ncu --set full, same workload)',
-                    kernel='lagged_gram_umma_kernel',
+                    kernel='ts::lagged_gram_ts_kernel',
                     flops_per_launch=f_alg, peak_source=peak_note, tf32_dense_live_tflops=tf32_live,
                     frac_of_live_tf32_over_3=achieved / (tf32_live / 3.0)),
       e2e=dict(value=world * frames / (e2e_ms * 1e-3), unit='frames/s',
