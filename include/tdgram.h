@@ -205,6 +205,26 @@ int td_wta_decide_u8(const double* r1_dev, const double* r2_dev, int64_t n, uint
 /* Utility: out[j, i] = out[i, j] for j > i (mirror the computed triangle). */
 int td_symmetrize_f32(float* G_dev, int64_t n, int64_t ldg, int from_upper, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------
+ * TFRecord / tf.train.Example reader (HOST code, no GPU needed).  Replaces
+ * tf.data.TFRecordDataset + tf.io.parse_example as the reference uses them to read one frame per
+ * record (brain_data.py:733-745, :758-812), discover_feature_shapes (:853-892) and count_tfrecords
+ * (:895-920); wire format written by ingest.py:1118-1172.  `file_bytes` is the whole file in host
+ * memory.  verify_crc: 0 none, 1 the length checksums, 2 length and data checksums (masked CRC32C).
+ *   td_tfrecord_count     number of well-framed records (on an error: those before the damage).
+ *   td_tfrecord_features  names ('\0'-separated into `names`), value counts and kinds (1 bytes,
+ *                         2 float, 3 int64) of the features of the FIRST record.
+ *   td_tfrecord_read_f32  out[r, :] = the requested features of record r side by side (widths[i]
+ *                         values each, int64 converted), row stride ld_out floats; a record that
+ *                         lacks a feature or holds another number of values is an error.
+ * ------------------------------------------------------------------------------------- */
+int td_tfrecord_count(const void* file_bytes, size_t n_bytes, int verify_crc, int64_t* n_records);
+int td_tfrecord_features(const void* file_bytes, size_t n_bytes, char* names, size_t names_cap,
+                         int32_t* widths, int32_t* kinds, int32_t max_features, int32_t* n_features);
+int td_tfrecord_read_f32(const void* file_bytes, size_t n_bytes, const char* const* names,
+                         const int32_t* widths, int32_t n_names, float* out_host, int64_t ld_out,
+                         int64_t max_records, int verify_crc, int64_t* n_records);
+
 #ifdef __cplusplus
 }
 #endif

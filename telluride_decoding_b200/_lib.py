@@ -41,7 +41,8 @@ EXPORTS = (
     'td_last_error', 'td_version', 'td_device_info', 'td_lagged_gram_workspace_bytes',
     'td_lagged_gram_f32', 'td_last_gram_kernel_ms', 'td_lagged_gram_range_f32', 'td_lagged_thin_f64', 'td_lagged_predict_f32', 'td_lagged_rows_f32',
     'td_ridge_solve', 'td_cca_solve', 'td_column_moments_f64', 'td_windowed_corr_f32',
-    'td_window_count', 'td_wta_decide_u8', 'td_symmetrize_f32')
+    'td_window_count', 'td_wta_decide_u8', 'td_symmetrize_f32', 'td_tfrecord_count',
+    'td_tfrecord_features', 'td_tfrecord_read_f32')
 
 _lib = None
 

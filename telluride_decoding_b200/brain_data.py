@@ -20,6 +20,7 @@ un-shuffled tail.  The reference's regression presets run with shuffle_buffer_si
 (regression.py:459, :479).
 """
 
+import os
 import random
 import re
 
@@ -555,6 +556,122 @@ class TrialBrainData(BrainData):
     return self._make_dataset(mode, files, temporal_context, mixup_batch, offset_counts=False)
 
 
+def discover_feature_shapes(tfrecord_file_name):
+  """{feature name: FixedLenFeature([width], dtype)} of the first record (brain_data.py:853-892)."""
+  if not isinstance(tfrecord_file_name, str):
+    raise TypeError('discover_feature_shapes: input must be a string filename.')
+  from telluride_decoding_b200 import tfrecord
+  return {name: FixedLenFeature([width,], tfrecord.KIND_NAMES.get(kind, 'float32'))
+          for name, width, kind in tfrecord.feature_table(tfrecord_file_name)}
+
+
+def count_tfrecords(tfrecord_file_name):
+  """(valid records, whether an error was found) of a TFRecord file (brain_data.py:895-920)."""
+  if not isinstance(tfrecord_file_name, str):
+    raise TypeError('tfrecord_file_name must be a string.')
+  from telluride_decoding_b200 import tfrecord
+  return tfrecord.count_tfrecords(tfrecord_file_name)
+
+
+class TFExampleData(TrialBrainData):
+  """Dataset of tf.train.Examples in several .tfrecords files, one trial per file, one frame per
+  record (brain_data.py:645-839).
+
+  File discovery, the feature table, field selection (`in1_fields` side by side, the `ones`
+  output of :778-780, the input-2 and attention placeholders of :795-810) and the per-file
+  context / interleave / batch semantics follow the reference; the records themselves are parsed
+  by the native reader (csrc/tfrecord.cu) into pinned memory and copied to the GPU once per file,
+  on first use."""
+
+  def __init__(self, *args, **kwargs):
+    self._file_data = {}
+    super(TFExampleData, self).__init__(*args, **kwargs)
+
+  def _get_data_file_names(self):
+    if not self.data_dir:
+      raise ValueError('Missing data_dir in TFExampleData initialization. '
+                       'Must specify the source of the data (FLAGS.tfrecords).')
+    if not isinstance(self.data_dir, str):
+      raise TypeError('data_dir must be a string, not a %s (**%s**)' %
+                      (type(self.data_dir), self.data_dir))
+    self._cached_file_names = []
+    for path, _, files in os.walk(self.data_dir):
+      self._cached_file_names += [os.path.join(path, f) for f in sorted(files)
+                                  if (f.endswith('.tfrecords') and '-bad-' not in f and
+                                      self.data_pattern in f)]
+    if not self._cached_file_names:
+      raise ValueError('Should not have an empty list of data files from %s.' % self.data_dir)
+    self.features = discover_feature_shapes(self._cached_file_names[0])
+
+  def _load_file(self, filename):
+    """(x, x2, y, a) device tensors of one file, parsed once."""
+    if filename in self._file_data:
+      return self._file_data[filename]
+    from telluride_decoding_b200 import tfrecord
+    if set(self.in1_fields) - set(self.features.keys()):
+      raise ValueError('Could not find all desired features (%s) in data (%s)' %
+                       (self.in1_fields, self.features.keys()))
+    groups = [list(self.in1_fields)]
+    if self.out_field != 'ones':
+      if self.out_field not in self.features:
+        raise ValueError('Could not find %s in parsed_features[%s]' %
+                         (self.out_field, self.features.keys()))
+      groups.append([self.out_field])
+    else:
+      groups.append([])
+    if self.in2_fields:
+      for k in self.in2_fields:
+        if k not in self.features:
+          raise ValueError('Could not find %s in parsed_features[%s]' % (k, self.features.keys()))
+    groups.append(list(self.in2_fields or []))
+    if self.attended_field and self.attended_field not in self.features:
+      raise ValueError('Could not find %s in parsed_features[%s]' %
+                       (self.attended_field, self.features.keys()))
+    groups.append([self.attended_field] if self.attended_field else [])
+    names = [n for g in groups for n in g]
+    widths = [int(self.features[n].shape[0]) for n in names]
+    host = tfrecord.read_features(filename, names, widths)
+    dev = _lib.as_device_f32(host.cuda(non_blocking=True))
+    parts, col = [], 0
+    for g in groups:
+      w = sum(int(self.features[n].shape[0]) for n in g)
+      parts.append(dev[:, col:col + w].contiguous() if w else None)
+      col += w
+    x, y, x2, a = parts
+    n = int(x.shape[0])
+    if y is None:                                   # 'ones' (brain_data.py:778-780)
+      y = torch.ones((n, 1), dtype=torch.float32, device=x.device)
+    if x2 is None:                                  # placeholder: first input column (:795-800)
+      x2 = x[:, 0:1].contiguous()
+    if a is None:                                   # placeholder zeros (:806-810)
+      a = torch.zeros((n, 1), dtype=torch.float32, device=x.device)
+    self._file_data[filename] = (x, x2, y, a)
+    return self._file_data[filename]
+
+  def add_trial(self, *args, **kwargs):
+    raise TypeError('TFExampleData reads its trials from data_dir; use TrialBrainData.add_trial.')
+
+  def set_trials(self, *args, **kwargs):
+    raise TypeError('TFExampleData reads its trials from data_dir; use TrialBrainData.set_trials.')
+
+  def create_dataset(self, mode='train', temporal_context=True, mixup_batch=False,
+                     mismatch_batch=False):
+    if mismatch_batch:
+      raise NotImplementedError('mismatch_batch randomisation is outside the decoding hot path.')
+    filename_list = self.filter_file_names(mode)
+    if not filename_list:
+      raise ValueError('No files to process in mode %s from directory %s: %s' %
+                       (mode, self.data_dir, self.all_files()))
+    loaded = [self._load_file(f) for f in filename_list]
+    cat = lambda i: torch.cat([t[i] for t in loaded], dim=0)
+    self._x, self._x2, self._y, self._a = cat(0), cat(1), cat(2), cat(3)
+    files, cur = [], 0
+    for f, t in zip(filename_list, loaded):
+      files.append((f, cur, int(t[0].shape[0])))
+      cur += int(t[0].shape[0])
+    return self._make_dataset(mode, files, temporal_context, mixup_batch, offset_counts=False)
+
+
 def create_brain_dataset(data_type, in_fields, out_field, frame_rate, pre_context=0,
                          post_context=0, in2_fields=None, in2_pre_context=0, in2_post_context=0,
                          input_offset=0, attended_field=None, initial_batch_size=1000000,
@@ -563,8 +680,8 @@ def create_brain_dataset(data_type, in_fields, out_field, frame_rate, pre_contex
                          validate_file_pattern=None, test_file_pattern=None):
   """Creates any of the brain datasets that we know about (brain_data.py:959-1049).
 
-  'test' -> TestBrainData, 'trials' -> TrialBrainData (in-memory multi-file).  The 'tfrecord'
-  reader of the reference is outside this package's scope.
+  'test' -> TestBrainData, 'tfrecord' -> TFExampleData (files on disk, native parser),
+  'trials' -> TrialBrainData (the same semantics for trials already in memory).
   """
   if not isinstance(data_type, str):
     raise TypeError('create_brain_dataset type must be a string.')
@@ -584,6 +701,5 @@ def create_brain_dataset(data_type, in_fields, out_field, frame_rate, pre_contex
   if data_type in ('trials', 'memory'):
     return TrialBrainData(in_fields, out_field, frame_rate, **kwargs)
   if data_type in ('tfrecord', 'tfrecords', 'tfexample'):
-    raise TypeError('create_brain_dataset: the TFRecord reader is not part of the B200 hot path; '
-                    'load trials with TrialBrainData.add_trial.')
+    return TFExampleData(in_fields, out_field, frame_rate, **kwargs)
   raise TypeError('create_brain_dataset unknown data type %s' % data_type)

@@ -162,14 +162,42 @@ def solve_regression(stats, lambdas, use_offset=True, method=2):
   return out
 
 
+def _ledoit_wolf_shrinkage(dataset, use_offset, g_aug, mean_x, mu, n):
+  """Shrinkage of brain_model.py:457-465 (float64).  sum_x2tx2 follows :440-443: every batch is
+  centred by the mean of all rows seen up to and including it, squared elementwise, and its Gram
+  is accumulated -- an order-dependent statistic, so the batches are walked in the reference's order."""
+  sum_x = None
+  sum_x2tx2 = None
+  rows_seen = 0
+  for inputs, _ in dataset:
+    x = inputs['input_1'].to(torch.float64)
+    if use_offset:
+      x = torch.cat((x, torch.ones((x.shape[0], 1), dtype=x.dtype, device=x.device)), dim=1)
+    rows_seen += x.shape[0]
+    batch_sum = x.sum(dim=0, keepdim=True)
+    sum_x = batch_sum if sum_x is None else sum_x + batch_sum
+    centred_sq = (x - sum_x / rows_seen) ** 2
+    gram = centred_sq.t() @ centred_sq
+    sum_x2tx2 = gram if sum_x2tx2 is None else sum_x2tx2 + gram
+  d = g_aug.shape[0]
+  cov_x_zc = g_aug - torch.outer(mean_x, mean_x)
+  delta_ = cov_x_zc.clone()
+  delta_.diagonal().sub_(mu)
+  delta = float((delta_ ** 2).sum().item()) / d
+  beta_ = float((sum_x2tx2 / n - cov_x_zc ** 2).sum().item()) / (d * n)
+  return min(beta_, delta) / delta
+
+
 def calculate_linear_regressor_parameters_from_dataset(dataset, lamb=0.1, use_offset=True,
                                                        use_ridge=True, return_covariances=True):
   """Estimate the parameters for a linear regressor from a dataset (brain_model.py:384-481).
 
   Returns (W [D, Dy], b [1, Dy] (zeros((1,)) without offset), cov_x, cov_xy, shrinkage) as numpy
   float32 arrays like the reference.  `use_ridge=False` is the Blankertz shrinkage of :456-476
-  with a fixed lambda in [0, 1]; the Ledoit-Wolf estimate (lamb == -1) needs the Gram of the
-  squared centred design and is not on this path.
+  with a fixed lambda in [0, 1] or, for lamb == -1, the Ledoit-Wolf estimate of :440-443, :457-465.
+  Ledoit-Wolf needs the Gram of the squared design centred by the RUNNING mean of the batches seen
+  so far, which is not a lagged stream: that one statistic is accumulated from the materialised
+  minibatches (td_lagged_rows_f32 + a library GEMM), everything else comes from the lagged kernels.
   """
   if not is_dataset(dataset):
     raise TypeError('dataset input to '
@@ -184,15 +212,16 @@ def calculate_linear_regressor_parameters_from_dataset(dataset, lamb=0.1, use_of
     sol = ops.ridge_solve(g_aug, c_aug, n, [lamb])[0]
     reg_diag, scale = float(lamb), 1.0
   else:
-    if lamb == -1:
-      raise NotImplementedError('Ledoit-Wolf shrinkage (lamb == -1) is outside the B200 hot path.')
-    if lamb > 1 or lamb < 0:
-      raise ValueError('Regularization lambda must be between 0 and 1, not %g.' % lamb)
-    shrinkage = lamb
     # brain_model.py:450-452: the un-normalised sum minus ONE mean outer product (sic).
     mean_x = g_aug[:, -1] / n if use_offset else stats.xtv[:, -1] / n
     trace_zc = torch.trace(g_aug) - torch.sum(mean_x * mean_x)
     mu = float(trace_zc.item()) / n_col
+    if lamb == -1:
+      shrinkage = _ledoit_wolf_shrinkage(dataset, use_offset, g_aug, mean_x, mu, n)
+    elif lamb > 1 or lamb < 0:
+      raise ValueError('Regularization lambda must be between 0 and 1, not %g.' % lamb)
+    else:
+      shrinkage = lamb
     if shrinkage >= 1.0:
       sol = (c_aug / n / mu).to(torch.float32)
     else:   # ((1-s) A0 + s mu I) w = B0   <=>   (A0 + s mu/(1-s) I) w = B0 / (1-s)

@@ -29,7 +29,7 @@ def test_ridge_matches_reference_fixture(golden_dir, name):
   ds = bd.create_dataset('train')
   for tag, lamb, use_offset, use_ridge in (('ridge0', 0.0, True, True), ('ridge1em2', 1e-2, True, True),
                                            ('ridge10', 10.0, True, True), ('nooffset', 0.1, False, True),
-                                           ('shrink03', 0.3, True, False)):
+                                           ('shrink03', 0.3, True, False), ('lw', -1, True, False)):
     w, b, cov_x, cov_xy, shrink = brain_model.calculate_linear_regressor_parameters_from_dataset(
         ds, lamb=lamb, use_offset=use_offset, use_ridge=use_ridge)
     assert gpu_util.rel_fro(w, g[tag + '_w']) < W_TOL, tag
@@ -40,7 +40,10 @@ def test_ridge_matches_reference_fixture(golden_dir, name):
       assert b.shape == (1, g['y'].shape[1])
     else:
       assert b.shape == (1,) and b[0] == 0
-    assert float(shrink) == float(g[tag + '_shrinkage'])
+    if tag == 'lw':      # Ledoit-Wolf estimate (brain_model.py:457-465): a computed, not a passed, value
+      assert abs(float(shrink) - float(g[tag + '_shrinkage'])) <= 1e-4 * abs(float(g[tag + '_shrinkage']))
+    else:
+      assert float(shrink) == float(g[tag + '_shrinkage'])
     assert w.dtype == np.float32
   with pytest.raises(ValueError, match='Regularization lambda must be between 0 and 1'):
     brain_model.calculate_linear_regressor_parameters_from_dataset(ds, lamb=2, use_ridge=False)
