@@ -53,24 +53,32 @@ constexpr int A_SLOTS = 4;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int NACC = 128;                                // accumulator values per epilogue thread
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int NUM_BARRIERS = 2 * STAGES + 2 * A_SLOTS + 6;
+constexpr int NUM_BARRIERS = 2 * STAGES + 2 * A_SLOTS + 12;
 static_assert(8 * NUM_BARRIERS + 8 <= 256, "barrier block too small");
 
-// Region use bookkeeping shared by the MMA and epilogue roles: chunk number cm (mod 3) picks the two
-// regions; `umask` bit r is the parity of the next use of region r.
-struct RegionRing {
+// Region bookkeeping of one half (h = 0, 1) of the pair tile, kept identically by its MMA issuer and
+// its epilogue warps: chunk number cm (mod 3) picks the region, `own` bit r is the parity of this
+// half's next use of region r.  Every mbarrier of the accumulator hand-off belongs to ONE (half,
+// region) pair, so each has one waiting role that waits its phases strictly in order -- with one
+// barrier per region shared by both halves a half that runs two short chunks ahead would wait for a
+// phase whose predecessor has not completed yet, which the parity test reports as "done".
+struct HalfRing {
   int cm = 0;
-  uint32_t umask = 0;
-  int r[2];
-  uint32_t n[2];
-  __device__ __forceinline__ void next_chunk() {
-    r[0] = (2 * cm) % 3;
-    r[1] = (2 * cm + 1) % 3;
-    n[0] = (umask >> r[0]) & 1u;
-    umask ^= 1u << r[0];
-    n[1] = (umask >> r[1]) & 1u;
-    umask ^= 1u << r[1];
+  uint32_t own = 0;
+  int r;
+  uint32_t n;
+  __device__ __forceinline__ void next_chunk(int h) {
+    r = (2 * cm + h) % 3;
+    n = (own >> r) & 1u;
+    own ^= 1u << r;
     cm = (cm + 1 == 3) ? 0 : cm + 1;
+  }
+  // Parity to wait for on the OTHER half's "drained" barrier of region r before this use: region 1 is
+  // first used by half 1, regions 0 and 2 by half 0; the first user waits for the other half's previous
+  // drain (one phase back), the second user for the drain of the same ordinal.
+  __device__ __forceinline__ uint32_t drained_parity(int h) const {
+    const bool first_user = (r == 1) ? (h == 1) : (h == 0);
+    return first_user ? (n ^ 1u) : n;
   }
 };
 
@@ -80,6 +88,7 @@ __device__ __forceinline__ uint32_t lo_bits(uint32_t x) {
   return (__float_as_uint(d) + 0x1000u) & 0xFFFFE000u;
 }
 
+template <int ISSUERS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lagged_gram_ts_kernel(const __grid_constant__ CUtensorMap tmap0,
                       const __grid_constant__ CUtensorMap tmap1, const GramParams P) {
@@ -92,8 +101,8 @@ lagged_gram_ts_kernel(const __grid_constant__ CUtensorMap tmap0,
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };           // MMAs of the stage retired (both issuers)
   auto ready_bar = [&](int j) { return bar_base + 8u * (2 * STAGES + j); };       // leader: A slot + B lo of 16 frames built in both CTAs
   auto aempty_bar = [&](int j) { return bar_base + 8u * (2 * STAGES + A_SLOTS + j); };   // MMAs reading the slot retired
-  auto tfull_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * A_SLOTS + r); };
-  auto tempty_bar = [&](int r) { return bar_base + 8u * (2 * STAGES + 2 * A_SLOTS + 3 + r); };   // leader
+  auto tfull_bar = [&](int h, int r) { return bar_base + 8u * (2 * STAGES + 2 * A_SLOTS + 3 * h + r); };        // half h finished a chunk in region r
+  auto tempty_bar = [&](int h, int r) { return bar_base + 8u * (2 * STAGES + 2 * A_SLOTS + 6 + 3 * h + r); };   // leader: half h's chunk drained from region r
   const uint32_t tmem_slot = bar_base + 8u * NUM_BARRIERS;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
       smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
@@ -109,16 +118,17 @@ lagged_gram_ts_kernel(const __grid_constant__ CUtensorMap tmap0,
     ptx::prefetch_tmap(&tmap1);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 2);
+      ptx::mbar_init(empty_bar(s), ISSUERS);
     }
     for (int j = 0; j < A_SLOTS; ++j) {
       ptx::mbar_init(ready_bar(j), 2 * NUM_CONV);
-      ptx::mbar_init(aempty_bar(j), 2);
+      ptx::mbar_init(aempty_bar(j), ISSUERS);
     }
-    for (int r = 0; r < 3; ++r) {
-      ptx::mbar_init(tfull_bar(r), 1);
-      ptx::mbar_init(tempty_bar(r), 2 * (NUM_EPI / 2));
-    }
+    for (int h = 0; h < 2; ++h)
+      for (int r = 0; r < 3; ++r) {
+        ptx::mbar_init(tfull_bar(h, r), 1);
+        ptx::mbar_init(tempty_bar(h, r), 2 * (NUM_EPI / 2));
+      }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<2>(tmem_slot, TMEM_COLS);
@@ -169,84 +179,95 @@ lagged_gram_ts_kernel(const __grid_constant__ CUtensorMap tmap0,
         }
       }
       TS_PROF_FLUSH(15, 0)
-    } else if (warp <= 2 && rank == 0) {
-      // ===================== MMA issuers (pair leader): warp 1 -> half 0, warp 2 -> half 1 ========
-      const int h = warp - 1;
+    } else if (warp <= ISSUERS && rank == 0) {
+      // ===================== MMA issuers (pair leader) ==========================================
+      // ISSUERS == 2: warp 1 -> half 0, warp 2 -> half 1.  ISSUERS == 1: warp 1 issues both halves.
+      const int h_begin = (ISSUERS == 2) ? warp - 1 : 0;
+      const int h_end = (ISSUERS == 2) ? warp : 2;
       WorkIter wi(P, worker, n_workers);
       WorkItem it;
       int stage = 0;
       uint32_t kcount = 0;                       // k-tiles issued so far: A slots 2*kcount, 2*kcount + 1
-      RegionRing ring;
+      HalfRing ring_a, ring_b;                   // ISSUERS == 2: ring_a is this warp's half; 1: halves 0 and 1
       TS_PROF_DECL
       while (wi.next(P, it)) {
         int next_range = __ldg(&P.ktiles[it.kt_begin]).y;
         for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
           const long long c1 = min(it.kt_end, c0 + (long long)P.chunk_kt);
-          ring.next_chunk();
-          const int r = h ? ring.r[1] : ring.r[0];
-          const uint32_t d = tmem_base + (uint32_t)r * ACC_COLS;
-          TS_LAP(6)
-          ptx::mbar_wait(tempty_bar(r), (h ? ring.n[1] : ring.n[0]) ^ 1u);
-          TS_LAP(3)
+          ring_a.next_chunk(h_begin);
+          if (ISSUERS == 1) ring_b.next_chunk(1);
           for (long long kt = c0; kt < c1; ++kt, ++kcount) {
             const int range = next_range;
             if (kt + 1 < it.kt_end) next_range = __ldg(&P.ktiles[kt + 1]).y;
             const int ks0 = (range & 0xff) >> 3, ks1 = ((range >> 8) + 7) >> 3;
             const bool whole = (ks0 == 0) && (ks1 == BK / 8);
             const uint32_t sbase = smem_base + stage * STAGE_BYTES;
-            const uint64_t b_hi = ptx::umma_desc_k_sw128(sbase + OPERAND_BYTES + h * (OPERAND_BYTES / 2));
-            const uint64_t b_lo = ptx::umma_desc_k_sw128(sbase + 2 * OPERAND_BYTES + h * (OPERAND_BYTES / 2));
             const uint32_t first_acc = (kt > c0) ? 1u : 0u;
+            for (int h = h_begin; h < h_end; ++h) {
+              const HalfRing& hr = (ISSUERS == 2 || h == 0) ? ring_a : ring_b;
+              const int r = hr.r;
+              const uint32_t d = tmem_base + (uint32_t)r * ACC_COLS;
+              if (kt == c0) {
+                TS_LAP(6)
+                ptx::mbar_wait(tempty_bar(1 - h, r), hr.drained_parity(h));
+                TS_LAP(3)
+              }
+              const uint64_t b_hi = ptx::umma_desc_k_sw128(sbase + OPERAND_BYTES + h * (OPERAND_BYTES / 2));
+              const uint64_t b_lo = ptx::umma_desc_k_sw128(sbase + 2 * OPERAND_BYTES + h * (OPERAND_BYTES / 2));
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const uint32_t use = 2u * kcount + hh;
-              const uint32_t slot = use & (A_SLOTS - 1);
-              TS_LAP(6)
-              ptx::mbar_wait(ready_bar(slot), (use >> 2) & 1u);
-              TS_LAP(2)
-              ptx::tc_fence_after();
-              if (ptx::elect_one()) {
-                const uint32_t a_base = tmem_base + A_COL0 + slot * A_SLOT_COLS;
-                if (whole) {
+              for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t use = 2u * kcount + hh;
+                const uint32_t slot = use & (A_SLOTS - 1);
+                if (ISSUERS == 2 || h == 0) {
+                  TS_LAP(6)
+                  ptx::mbar_wait(ready_bar(slot), (use >> 2) & 1u);
+                  TS_LAP(2)
+                }
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                  const uint32_t a_base = tmem_base + A_COL0 + slot * A_SLOT_COLS;
+                  if (whole) {
 #pragma unroll
-                  for (int q = 0; q < 2; ++q) {
-                    const uint64_t adv = (uint64_t)((hh * 2 + q) * 2);     // 8 frames = 32 B = 2 x 16 B
-                    const uint32_t a_hi = a_base + q * 8, a_lo = a_base + 16 + q * 8;
-                    ptx::mma_tf32_ts_pair(d, a_hi, b_hi + adv, IDESC, (hh + q) ? 1u : first_acc);
-                    ptx::mma_tf32_ts_pair(d, a_hi, b_lo + adv, IDESC, 1u);
-                    ptx::mma_tf32_ts_pair(d, a_lo, b_hi + adv, IDESC, 1u);
-                  }
-                } else {
-#pragma unroll
-                  for (int q = 0; q < 2; ++q) {
-                    const int ks = hh * 2 + q;
-                    if (ks >= ks0 && ks < ks1) {
-                      const uint64_t adv = (uint64_t)(ks * 2);
+                    for (int q = 0; q < 2; ++q) {
+                      const uint64_t adv = (uint64_t)((hh * 2 + q) * 2);     // 8 frames = 32 B = 2 x 16 B
                       const uint32_t a_hi = a_base + q * 8, a_lo = a_base + 16 + q * 8;
-                      ptx::mma_tf32_ts_pair(d, a_hi, b_hi + adv, IDESC, (ks > ks0) ? 1u : first_acc);
+                      ptx::mma_tf32_ts_pair(d, a_hi, b_hi + adv, IDESC, (hh + q) ? 1u : first_acc);
                       ptx::mma_tf32_ts_pair(d, a_hi, b_lo + adv, IDESC, 1u);
                       ptx::mma_tf32_ts_pair(d, a_lo, b_hi + adv, IDESC, 1u);
                     }
+                  } else {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                      const int ks = hh * 2 + q;
+                      if (ks >= ks0 && ks < ks1) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        const uint32_t a_hi = a_base + q * 8, a_lo = a_base + 16 + q * 8;
+                        ptx::mma_tf32_ts_pair(d, a_hi, b_hi + adv, IDESC, (ks > ks0) ? 1u : first_acc);
+                        ptx::mma_tf32_ts_pair(d, a_hi, b_lo + adv, IDESC, 1u);
+                        ptx::mma_tf32_ts_pair(d, a_lo, b_hi + adv, IDESC, 1u);
+                      }
+                    }
+                  }
+                  if (ISSUERS == 2 || h == 1) ptx::mma_commit<2>(aempty_bar(slot));   // A slot reusable
+                  if (hh == 1) {
+                    if (ISSUERS == 2 || h == 1) ptx::mma_commit<2>(empty_bar(stage)); // stage reusable in both CTAs
+                    if (kt == c1 - 1) ptx::mma_commit<2>(tfull_bar(h, r));
                   }
                 }
-                ptx::mma_commit<2>(aempty_bar(slot));                   // A slot reusable (with the other issuer's commit)
-                if (hh == 1) {
-                  ptx::mma_commit<2>(empty_bar(stage));                 // stage reusable in both CTAs
-                  if (kt == c1 - 1) ptx::mma_commit<2>(tfull_bar(r));
-                }
+                __syncwarp();
+                TS_LAP(16)
               }
-              __syncwarp();
-              TS_LAP(16)
             }
             if (++stage == STAGES) stage = 0;
           }
         }
       }
-      if (h == 0) TS_PROF_FLUSH(14, 2, 3, 6, 16)
 #ifdef TD_TS_PROFILE
-      if (h == 1 && lane == 0 && P.prof) {
+      if (lane == 0 && P.prof) {
         long long* o = P.prof + blockIdx.x * 24;
-        o[1] = prof_acc[2]; o[4] = prof_acc[3]; o[5] = prof_acc[6]; o[7] = prof_acc[16]; o[13] = clock64() - prof_t0;
+        const long long total = clock64() - prof_t0;
+        if (warp == 1) { o[2] = prof_acc[2]; o[3] = prof_acc[3]; o[6] = prof_acc[6]; o[16] = prof_acc[16]; o[14] = total; }
+        else { o[1] = prof_acc[2]; o[4] = prof_acc[3]; o[5] = prof_acc[6]; o[7] = prof_acc[16]; o[13] = total; }
       }
 #endif
     }
@@ -329,20 +350,20 @@ lagged_gram_ts_kernel(const __grid_constant__ CUtensorMap tmap0,
     ptx::setmaxnreg_inc<168>();
     const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32)
     const int half = (warp - EPI_WARP0) >> 2;  // which 128-column half of the pair tile
-    const uint32_t tempty_leader0 = ptx::mapa(tempty_bar(0), 0);
+    const uint32_t tempty_leader0 = ptx::mapa(tempty_bar(half, 0), 0);
     WorkIter wi(P, worker, n_workers);
     WorkItem it;
-    RegionRing ring;
+    HalfRing ring;
     float acc[NACC];
     TS_PROF_DECL
     while (wi.next(P, it)) {
 #pragma unroll
       for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
       for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
-        ring.next_chunk();
-        const int r = half ? ring.r[1] : ring.r[0];
+        ring.next_chunk(half);
+        const int r = ring.r;
         TS_LAP(20)
-        ptx::mbar_wait(tfull_bar(r), half ? ring.n[1] : ring.n[0]);
+        ptx::mbar_wait(tfull_bar(half, r), ring.n);
         TS_LAP(18)
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)r * ACC_COLS;

@@ -813,7 +813,11 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
     if (flavour == 3) {
-      TD_CHECK_CUDA(cudaFuncSetAttribute(ts::lagged_gram_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts::SMEM_BYTES));
+      // One or two MMA issuing warps (development switch TD_TS_ISSUERS, default 2).
+      static int issuers = 0;
+      if (!issuers) { const char* e = getenv("TD_TS_ISSUERS"); issuers = (e && atoi(e) == 1) ? 1 : 2; }
+      auto kernel = (issuers == 1) ? ts::lagged_gram_ts_kernel<1> : ts::lagged_gram_ts_kernel<2>;
+      TD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts::SMEM_BYTES));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(workers * 2);
       cfg.blockDim = dim3(ts::NUM_THREADS);
@@ -826,7 +830,7 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ts::lagged_gram_ts_kernel, tmaps[0], tmaps[1], P));
+      TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmaps[0], tmaps[1], P));
     } else if (pl.cg == 1) {
       TD_CHECK_CUDA(cudaFuncSetAttribute(lagged_gram_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
       lagged_gram_umma_kernel<1><<<workers, NUM_THREADS, SMEM_BYTES, st>>>(tmaps[0], tmaps[1], P);

@@ -54,6 +54,28 @@ def test_gram_matches_oracle(n, c, pre, post, batch, cta_group, method):
   assert gpu_util.rel_fro(g, ref32) < GRAM_TOL
 
 
+@pytest.mark.parametrize('method', [0, 2])
+@pytest.mark.parametrize('chunk_rows,superchunk_rows', [(32, 4096), (64, 1024), (96, 2048), (128, 512)])
+def test_pair_kernels_with_short_chunks_and_many_work_items(method, chunk_rows, superchunk_rows):
+  """Schedule stress for the CTA-pair kernels: one-k-tile flush periods and tiny superchunks make
+  every accumulator hand-off and work-item boundary as frequent as possible (with 32-frame chunks
+  one half of the tile can run two chunks ahead of the other; a hand-off barrier shared by both
+  halves deadlocked there)."""
+  rng = np.random.RandomState(17)
+  n_trials, frames, c, lags = 5, 3111, 40, 32           # D = 1280: 5 x 5 pair tiles, ragged trial ends
+  x = (rng.randn(n_trials * frames, c) + 0.1).astype(np.float32)
+  xd = torch.as_tensor(x, device='cuda')
+  starts = [i * frames for i in range(n_trials)]
+  lens = [frames] * n_trials
+  keep = [frames - 7 * i for i in range(n_trials)]
+  stream = ops.Stream(xd, 0, lags - 1, starts, lens)
+  want = ops.lagged_gram([stream], keep, options=ops.gram_options(method=1))
+  for _ in range(3):
+    got = ops.lagged_gram([stream], keep, options=ops.gram_options(
+        method=method, cta_group=2, chunk_rows=chunk_rows, superchunk_rows=superchunk_rows))
+    assert gpu_util.rel_fro(got.cpu().numpy(), want.cpu().numpy()) < GRAM_TOL
+
+
 def test_simt_cross_check_agrees():
   ds, batches = _dataset(2000, 20, 2, 2, 200, seed=5)
   keep = ds.seg_rows
