@@ -223,78 +223,146 @@ __global__ void chol_build(const double* __restrict__ A0, const double* __restri
 // Factor the jb x jb diagonal block at (j0, j0) of every matrix in place (lower) and write the
 // inverse of the factor, Linv [batch][64][64] column-major (zero padded), for the panel solve.
 // info[l] = first non-positive pivot (1-based, global column) or unchanged.
+//
+// This kernel sits on the serial chain of the blocked factorisation (once per 64 columns, one CTA per
+// matrix), so it is built for latency, not throughput: the block is processed in four 16-column
+// steps; the 16 x 16 diagonal piece is factored AND inverted by one warp entirely in registers
+// (row per lane, columns and pivots exchanged by shuffles, no block-wide barrier inside), the panel
+// below it and the trailing update are short dot products from shared memory by all 256 threads
+// (three barriers per step).  The off-diagonal blocks of the inverse follow by block distance.
+constexpr int CH_SB = 16;                        // sub-block of chol_potf2
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+  return __shfl_sync(0xffffffffu, v, src);
+}
+
 __global__ void __launch_bounds__(256) chol_potf2(double* M, long long Nt, int j0, int jb, int* info,
                                                   double* __restrict__ Linv, long long linv_stride) {
   extern __shared__ double chol_sm[];
-  double (*T)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chol_sm);
-  double (*X)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chol_sm + CH_NB * (CH_NB + 1));
+  double (*T)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chol_sm);                          // the block: lower triangle, identity padding
+  double (*X)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chol_sm + CH_NB * (CH_NB + 1));    // its inverse
+  double (*P)[CH_SB + 1] = reinterpret_cast<double (*)[CH_SB + 1]>(chol_sm + 2 * CH_NB * (CH_NB + 1)); // panel of the current step
   double* Ml = M + (size_t)blockIdx.x * Nt * Nt + (size_t)j0 * Nt + j0;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  for (int e = threadIdx.x; e < CH_NB * CH_NB; e += blockDim.x) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < CH_NB * CH_NB; e += 256) {
     const int c = e >> 6, r = e & 63;
-    T[r][c] = (r >= c && r < jb) ? Ml[(size_t)c * Nt + r] : ((r == c) ? 1.0 : 0.0);   // identity padding
+    T[r][c] = (r >= c && r < jb) ? Ml[(size_t)c * Nt + r] : ((r == c) ? 1.0 : 0.0);
     X[r][c] = 0.0;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = 0; k < jb; ++k) {
-    const double d = T[k][k];
-    if (!(d > 0.0) && threadIdx.x == 0 && info[blockIdx.x] == 0) info[blockIdx.x] = j0 + k + 1;
-    // 1/sqrt(d): float seed + two Newton steps in double (relative error ~1e-16)
-    const double dd = d > 0.0 ? d : 1.0;
-    double rp = (double)rsqrtf((float)dd);
-    rp = rp * (1.5 - 0.5 * dd * rp * rp);
-    rp = rp * (1.5 - 0.5 * dd * rp * rp);
+  for (int o = 0; o < CH_NB; o += CH_SB) {
+    if (warp == 0) {
+      // ---- 16 x 16 diagonal piece: lane i (< 16) owns row i; lanes >= 16 mirror lane i - 16 ----
+      const int i = lane & 15;
+      double a[CH_SB];
+#pragma unroll
+      for (int c = 0; c < CH_SB; ++c) a[c] = (c <= i) ? T[o + i][o + c] : 0.0;
+      int bad = 0;
+#pragma unroll
+      for (int k = 0; k < CH_SB; ++k) {
+        const double d = shfl_f64(a[k], k);
+        if (!(d > 0.0) && bad == 0) bad = o + k + 1;
+        // 1/sqrt(d): float seed + two Newton steps in double (relative error ~1e-16)
+        const double dd = d > 0.0 ? d : 1.0;
+        double rp = (double)rsqrtf((float)dd);
+        rp = rp * (1.5 - 0.5 * dd * rp * rp);
+        rp = rp * (1.5 - 0.5 * dd * rp * rp);
+        const double lik = (i >= k) ? a[k] * rp : 0.0;       // L[i][k]; sqrt(d) on the diagonal
+        a[k] = lik;
+#pragma unroll
+        for (int c = k + 1; c < CH_SB; ++c) {
+          const double lck = shfl_f64(lik, c);
+          if (c <= i) a[c] -= lik * lck;
+        }
+      }
+      if (lane == 0 && bad && bad <= jb && info[blockIdx.x] == 0) info[blockIdx.x] = j0 + bad;
+      // inverse of the piece: lane j builds column j of Xd = Ld^-1 by forward substitution;
+      // L[r][k] is register a[k] of lane r, broadcast by shuffle (uniform r, k).
+      double x[CH_SB];
+      const double inv_diag = 1.0 / a[i];                    // 1 / L[i][i]
+#pragma unroll
+      for (int r = 0; r < CH_SB; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < r; ++k) acc += shfl_f64(a[k], r) * x[k];
+        const double dr = shfl_f64(inv_diag, r);
+        x[r] = (r < i) ? 0.0 : ((r == i) ? dr : -acc * dr);
+      }
+      if (lane < CH_SB) {
+#pragma unroll
+        for (int c = 0; c < CH_SB; ++c) {
+          if (c <= i) T[o + i][o + c] = a[c];
+          X[o + c][o + i] = x[c];                            // X[row c][col i] (zero above the diagonal)
+        }
+      }
+    }
     __syncthreads();
-    if (threadIdx.x >= k && threadIdx.x < CH_NB) T[threadIdx.x][k] *= rp;     // T[k][k] = sqrt(d)
+    const int below = CH_NB - o - CH_SB;                     // rows under the piece
+    // ---- panel: P[r][c] = sum_k T[o+16+r][o+k] * Xd[c][k]   (= A21 * Ld^-T) ----
+    for (int e = tid; e < below * CH_SB; e += 256) {
+      const int r = e >> 4, c = e & 15;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < CH_SB; ++k) acc += T[o + CH_SB + r][o + k] * X[o + c][o + k];
+      P[r][c] = acc;
+    }
     __syncthreads();
-    // rank-1 update of the remaining lower triangle: warp -> rows, lanes -> columns
-    for (int r = k + 1 + warp; r < CH_NB; r += 8) {
-      const double lr = T[r][k];
-      for (int c = k + 1 + lane; c <= r; c += 32) T[r][c] -= lr * T[c][k];
+    for (int e = tid; e < below * CH_SB; e += 256) {
+      const int r = e >> 4, c = e & 15;
+      T[o + CH_SB + r][o + c] = P[r][c];
+    }
+    // ---- trailing update of the lower triangle: T[r][c] -= sum_k P[r][k] * P[c][k] ----
+    for (int e = tid; e < below * below; e += 256) {
+      const int r = e / below, c = e - r * below;
+      if (c <= r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < CH_SB; ++k) acc += P[r][k] * P[c][k];
+        T[o + CH_SB + r][o + CH_SB + c] -= acc;
+      }
     }
     __syncthreads();
   }
-  // Linv by 32 x 32 blocks: inv([[A,0],[B,C]]) = [[inv A, 0], [-inv C * B * inv A, inv C]].
-  // The two diagonal inverses: one thread per column, forward substitution.
-  if (threadIdx.x < CH_NB) {
-    const int blk = threadIdx.x >> 5, j = (threadIdx.x & 31) + 32 * blk, lim = 32 * (blk + 1);
-    X[j][j] = 1.0 / T[j][j];
-    for (int i = j + 1; i < lim; ++i) {
-      double sacc = 0.0;
-      for (int kk = j; kk < i; ++kk) sacc += T[i][kk] * X[kk][j];
-      X[i][j] = -sacc / T[i][i];
+  // ---- off-diagonal blocks of X = L^-1, by block distance s:
+  //      X[i][j] = -Xd_i * sum_{k=j}^{i-1} L[i][k] X[k][j],  i = j + s  (16 x 16 blocks) ----
+  constexpr int NBK = CH_NB / CH_SB;
+  for (int s = 1; s < NBK; ++s) {
+    double keep[NBK - 1];
+#pragma unroll
+    for (int q = 0; q < NBK - 1; ++q) {                      // block column j = q (if j + s < 4)
+      keep[q] = 0.0;
+      if (q + s < NBK) {
+        const int r = tid >> 4, c = tid & 15, bi = q + s;
+        double acc = 0.0;
+        for (int k = q * CH_SB; k < bi * CH_SB; ++k) acc += T[bi * CH_SB + r][k] * X[k][q * CH_SB + c];
+        keep[q] = acc;
+      }
     }
-  }
-  __syncthreads();
-  // W = B * inv A  (into the upper-right corner of X as scratch), then X21 = -inv C * W.
-  for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
-    const int i = e >> 5, j = e & 31;
-    double sacc = 0.0;
-    for (int kk = j; kk < 32; ++kk) sacc += T[32 + i][kk] * X[kk][j];
-    X[i][32 + j] = sacc;                       // scratch (upper-right block is otherwise zero)
-  }
-  __syncthreads();
-  double keep[4];
+    __syncthreads();
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int e = threadIdx.x + q * 256;
-    const int i = e >> 5, j = e & 31;
-    double sacc = 0.0;
-    for (int kk = 0; kk <= i; ++kk) sacc += X[32 + i][32 + kk] * X[kk][32 + j];
-    keep[q] = -sacc;
-  }
-  __syncthreads();
+    for (int q = 0; q < NBK - 1; ++q)
+      if (q + s < NBK) X[(q + s) * CH_SB + (tid >> 4)][q * CH_SB + (tid & 15)] = keep[q];
+    __syncthreads();
+    // left-multiply by -Xd_i (in place needs a copy of the S block: read all, barrier, write)
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int e = threadIdx.x + q * 256;
-    const int i = e >> 5, j = e & 31;
-    X[32 + i][j] = keep[q];
-    X[i][32 + j] = 0.0;
+    for (int q = 0; q < NBK - 1; ++q) {
+      keep[q] = 0.0;
+      if (q + s < NBK) {
+        const int r = tid >> 4, c = tid & 15, bi = q + s;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < CH_SB; ++k) acc += X[bi * CH_SB + r][bi * CH_SB + k] * X[bi * CH_SB + k][q * CH_SB + c];
+        keep[q] = -acc;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NBK - 1; ++q)
+      if (q + s < NBK) X[(q + s) * CH_SB + (tid >> 4)][q * CH_SB + (tid & 15)] = keep[q];
+    __syncthreads();
   }
-  __syncthreads();
   double* Li = Linv + (size_t)blockIdx.x * linv_stride + (size_t)(j0 / CH_NB) * CH_NB * CH_NB;
-  for (int e = threadIdx.x; e < CH_NB * CH_NB; e += blockDim.x) {
+  for (int e = tid; e < CH_NB * CH_NB; e += 256) {
     const int c = e >> 6, r = e & 63;
     Li[e] = X[r][c];
     if (r >= c && r < jb && c < jb) Ml[(size_t)c * Nt + r] = T[r][c];
@@ -379,7 +447,7 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
   TD_CHECK_CUDA(cudaMemcpyAsync(lam_dev, lambdas, n_lambda * sizeof(double), cudaMemcpyHostToDevice, st));
   TD_CHECK_CUDA(cudaMemsetAsync(info, 0, n_lambda * sizeof(int), st));
   const double minus_one = -1.0, one = 1.0, zero = 0.0;
-  const int potf2_smem = 2 * CH_NB * (CH_NB + 1) * (int)sizeof(double);
+  const int potf2_smem = (2 * CH_NB * (CH_NB + 1) + CH_NB * (CH_SB + 1)) * (int)sizeof(double);
   TD_CHECK_CUDA(cudaFuncSetAttribute(chol_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem));
   const char* dbg_env = getenv("TD_DEBUG");
   const bool dbg = dbg_env && dbg_env[0] == '2';

@@ -10,7 +10,8 @@ torch.manual_seed(0)
 g = torch.randn(4 * n, n, device='cuda', dtype=torch.float64)
 G = g.t() @ g
 C = torch.randn(n, 1, device='cuda', dtype=torch.float64)
-lam = np.logspace(-6, 3, 20)
+n_lam = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+lam = np.logspace(-6, 3, 20)[:n_lam]
 for _ in range(3):
   w = ops.ridge_solve(G, C, 4.0 * n, lam, method=method)
 torch.cuda.synchronize()
