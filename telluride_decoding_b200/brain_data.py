@@ -106,6 +106,10 @@ class LaggedDataset(object):
     # x, x2, y, a: concatenated [frames, channels] CUDA tensors; files: [(name, start, length)].
     self.x, self.x2, self.y, self.a = x, x2, y, a
     self.files = list(files)
+    # [(row_end, cuda event)] when the tensors are still being filled by asynchronous host-to-device
+    # copies (TrialBrainData.set_trials with pinned host arrays): rows < row_end are valid once the
+    # event has completed.  None = everything is resident.
+    self.ready = None
     self.mode = mode
     self.final_batch_size = int(final_batch_size)
     self.repeat_count = int(repeat_count) if mode == 'train' else 1
@@ -174,8 +178,36 @@ class LaggedDataset(object):
       out.append((1.0, self.seg_keep_for_prefix(self.partial_rows)))
     return out
 
-  def stream(self, which):
-    """ops.Stream of 'x' (input_1), 'x2' (input_2), 'y' (output) or 'a' (attention)."""
+  def wait_ready(self):
+    """Makes the current stream wait for every pending host-to-device copy of the trials."""
+    if self.ready:
+      torch.cuda.current_stream().wait_event(self.ready[-1][1])
+      self.ready = None
+
+  def segment_groups(self):
+    """[(cuda event or None, [segment indices])]: segments grouped by the copy chunk that completes
+    them, in copy order, so that a sum over segments can start before the last trial has landed."""
+    if not self.ready:
+      return [(None, list(range(len(self.seg_rows))))]
+    ends = [e for e, _ in self.ready]
+    groups = [[] for _ in ends]
+    for i, (sx, lx, s2, l2) in enumerate(zip(self._sx, self._lx, self._s2, self._l2)):
+      last = max(sx + lx, s2 + l2)
+      g = 0
+      while g + 1 < len(ends) and last > ends[g]:
+        g += 1
+      groups[g].append(i)
+    return [(ev, seg) for (_, ev), seg in zip(self.ready, groups) if seg]
+
+  def stream(self, which, segments=None, wait=True):
+    """ops.Stream of 'x' (input_1), 'x2' (input_2), 'y' (output) or 'a' (attention); optionally of
+    a subset of the segments (wait=False: the caller orders itself after the copy events)."""
+    if wait:
+      self.wait_ready()
+    if segments is not None:
+      full = self.stream(which, wait=False)
+      return ops.Stream(full.data, full.pre, full.post, [full.seg_start[i] for i in segments],
+                        [full.seg_len[i] for i in segments])
     if which == 'x':
       return ops.Stream(self.x, self.pre, self.post, self._sx, self._lx)
     data = {'x2': self.x2, 'y': self.y, 'a': self.a}[which]
@@ -383,6 +415,11 @@ class BrainData(object):
 
   # Shared by the in-memory classes below.
   def _make_dataset(self, mode, files, temporal_context, mixup_batch, offset_counts):
+    ds = self._new_dataset(mode, files, temporal_context, mixup_batch, offset_counts)
+    ds.ready = getattr(self, '_ready', None)
+    return ds
+
+  def _new_dataset(self, mode, files, temporal_context, mixup_batch, offset_counts):
     return LaggedDataset(
         self._x, self._x2, self._y, self._a, files, self.in1_pre_context,
         self.in1_post_context, self.in2_pre_context, self.in2_post_context, self.input_offset,
@@ -494,9 +531,24 @@ class TrialBrainData(BrainData):
   def set_trials(self, names, lengths, input_data, output_data, input2_data=None,
                  attention_data=None):
     """All trials at once from arrays that already hold them back to back (no per-trial copies):
-    trial i is rows [sum(lengths[:i]), sum(lengths[:i+1])) of every array."""
-    x = _check_2d('input_data', _lib.as_device_f32(input_data))
-    y = _check_2d('output_data', _lib.as_device_f32(output_data))
+    trial i is rows [sum(lengths[:i]), sum(lengths[:i+1])) of every array.
+
+    Pinned host tensors are copied to the GPU asynchronously in a few chunks cut at trial
+    boundaries, on a side stream; the datasets made from this object know which rows each copy
+    completes, so the Gram of the first trials runs while the later ones are still on the PCIe bus."""
+    self._ready = None
+    pinned = (isinstance(input_data, torch.Tensor) and isinstance(output_data, torch.Tensor) and
+              input_data.device.type == 'cpu' and output_data.device.type == 'cpu' and
+              input_data.is_pinned() and output_data.is_pinned() and
+              input_data.dtype == torch.float32 and output_data.dtype == torch.float32 and
+              input_data.dim() == 2 and output_data.dim() == 2 and
+              input_data.is_contiguous() and output_data.is_contiguous() and
+              input_data.shape[0] == output_data.shape[0] and len(lengths) > 1)
+    if pinned:
+      x, y = self._async_upload(input_data, output_data, lengths)
+    else:
+      x = _check_2d('input_data', _lib.as_device_f32(input_data))
+      y = _check_2d('output_data', _lib.as_device_f32(output_data))
     n = int(x.shape[0])
     if sum(int(l) for l in lengths) != n or len(names) != len(lengths):
       raise ValueError('lengths must sum to the %d frames of input_data, one per name' % n)
@@ -527,6 +579,46 @@ class TrialBrainData(BrainData):
       self.features[self.in2_fields[0]] = FixedLenFeature([int(x2.shape[1]),])
     if self.attended_field:
       self.features[self.attended_field] = FixedLenFeature([int(a.shape[1]),])
+
+  _copy_streams = {}
+  # Cumulative fractions of the frames at which an upload chunk ends: a small first chunk so that
+  # the GPU starts early, then chunks that grow with the time the previous one takes to process
+  # (the Gram needs ~3x longer per frame than the PCIe copy).
+  UPLOAD_CUTS = (0.1, 0.4, 1.0)
+
+  def _async_upload(self, x_host, y_host, lengths):
+    """Device copies of two pinned [frames, channels] arrays, issued chunk by chunk on a side stream;
+    sets self._ready = [(row_end, event)]."""
+    _lib.require_cuda()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    x = torch.empty(x_host.shape, dtype=torch.float32, device=dev)
+    y = torch.empty(y_host.shape, dtype=torch.float32, device=dev)
+    side = TrialBrainData._copy_streams.get(dev.index)
+    if side is None:
+      side = TrialBrainData._copy_streams[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())        # the buffers may be recycled memory
+    n = int(x_host.shape[0])
+    cuts, cur = [], 0
+    for i, length in enumerate(lengths):                 # chunk ends at trial boundaries
+      cur += int(length)
+      if len(cuts) < len(self.UPLOAD_CUTS) and (cur >= self.UPLOAD_CUTS[len(cuts)] * n or
+                                                i == len(lengths) - 1):
+        cuts.append(cur)
+    if cuts[-1] != n:
+      cuts.append(n)
+    ready, r0 = [], 0
+    with torch.cuda.stream(side):
+      for r1 in cuts:
+        x[r0:r1].copy_(x_host[r0:r1], non_blocking=True)
+        y[r0:r1].copy_(y_host[r0:r1], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        ready.append((r1, ev))
+        r0 = r1
+    x.record_stream(side)
+    y.record_stream(side)
+    self._ready = ready
+    return x, y
 
   def _pack(self):
     if not self._dirty:

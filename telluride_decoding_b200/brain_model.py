@@ -96,32 +96,57 @@ class RegressionStats(object):
 
   @classmethod
   def from_dataset(cls, dataset, gram_options=None, workspace=None):
+    passes = dataset.passes()
+    groups = dataset.segment_groups() if len(passes) == 1 else None
+    if groups is not None and len(groups) > 1:
+      # The trials are still arriving from the host (TrialBrainData.set_trials with pinned arrays):
+      # the statistics are sums over segments, so every group of segments is processed as soon as
+      # the copy that completes it has finished.
+      weight, keep = passes[0]
+      total = None
+      for event, segs in groups:
+        torch.cuda.current_stream().wait_event(event)
+        part = cls._one_pass(dataset.stream('x', segs, wait=False), dataset.stream('y', segs, wait=False),
+                             [keep[i] for i in segs], gram_options, None)
+        if total is None:
+          total = part
+        else:
+          total.gram += part.gram
+          total.xtv += part.xtv
+          total.vtv += part.vtv
+      dataset.ready = None
+      if weight != 1.0:
+        total = cls(total.gram * weight, total.xtv * weight, total.vtv * weight)
+      return total
     x = dataset.stream('x')
     y = dataset.stream('y')
-    gram = xtv = vtv = None
-    for weight, keep in dataset.passes():
-      if y.channels + 1 <= 16:
-        g = ops.lagged_gram([x], keep, options=gram_options, workspace=workspace)
-        t, v = ops.lagged_thin(x, y, keep)
-      else:
-        # Wide target: x'y comes out of the two-stream Gram, the ones column from thin passes.
-        gz = ops.lagged_gram([x, y], keep, options=gram_options, workspace=workspace)
-        d = x.width
-        g = gz[:d, :d]
-        tx, n1 = ops.lagged_thin(x, None, keep)
-        ty, _ = ops.lagged_thin(y, None, keep)
-        t = torch.cat([gz[:d, d:].to(torch.float64), tx], dim=1)
-        v = torch.cat([torch.cat([gz[d:, d:].to(torch.float64), ty], dim=1),
-                       torch.cat([ty.t(), n1], dim=1)], dim=0)
-      if gram is None:
-        gram = g if weight == 1.0 else g * weight
-        xtv, vtv = t * weight, v * weight
-      else:
-        gram = gram + g * weight
-        xtv, vtv = xtv + t * weight, vtv + v * weight
-    if gram is None:
+    total = None
+    for weight, keep in passes:
+      part = cls._one_pass(x, y, keep, gram_options, workspace)
+      if weight != 1.0:
+        part = cls(part.gram * weight, part.xtv * weight, part.vtv * weight)
+      total = part if total is None else cls(total.gram + part.gram, total.xtv + part.xtv,
+                                             total.vtv + part.vtv)
+    if total is None:
       raise ValueError('Dataset has no complete minibatch: %r' % dataset)
-    return cls(gram, xtv, vtv)
+    return total
+
+  @classmethod
+  def _one_pass(cls, x, y, keep, gram_options, workspace):
+    if y.channels + 1 <= 16:
+      g = ops.lagged_gram([x], keep, options=gram_options, workspace=workspace)
+      t, v = ops.lagged_thin(x, y, keep)
+    else:
+      # Wide target: x'y comes out of the two-stream Gram, the ones column from thin passes.
+      gz = ops.lagged_gram([x, y], keep, options=gram_options, workspace=workspace)
+      d = x.width
+      g = gz[:d, :d]
+      tx, n1 = ops.lagged_thin(x, None, keep)
+      ty, _ = ops.lagged_thin(y, None, keep)
+      t = torch.cat([gz[:d, d:].to(torch.float64), tx], dim=1)
+      v = torch.cat([torch.cat([gz[d:, d:].to(torch.float64), ty], dim=1),
+                     torch.cat([ty.t(), n1], dim=1)], dim=0)
+    return cls(g, t, v)
 
   def __sub__(self, other):
     return RegressionStats(self.gram.to(torch.float64) - other.gram.to(torch.float64),

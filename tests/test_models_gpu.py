@@ -274,3 +274,47 @@ def test_pearson_known_answer():
   y = np.random.random((6, 2))
   npcor = np.diag(np.corrcoef(x, y, rowvar=False)[:2, 2:])
   np.testing.assert_allclose(brain_model.pearson_correlation(x, y).numpy(), npcor, atol=2e-7)
+
+
+def test_pinned_host_trials_are_uploaded_in_chunks_and_give_the_same_fit():
+  """TrialBrainData.set_trials with pinned host arrays: asynchronous chunked upload, statistics per
+  arrived group of trials -- same numbers as with resident tensors, and every other consumer of the
+  dataset (iteration, evaluate) waits for the copies."""
+  import torch
+  from telluride_decoding_b200 import brain_data
+  rng = np.random.default_rng(21)
+  lengths = [700, 650, 900, 512, 801, 640, 777]
+  n = sum(lengths)
+  x = rng.standard_normal((n, 12)).astype(np.float32)
+  y = (x[:, :1] * 0.7 + 0.2 * rng.standard_normal((n, 1))).astype(np.float32)
+  names = ['trial_%d' % i for i in range(len(lengths))]
+
+  def make(xa, ya):
+    bd = brain_data.TrialBrainData('eeg', 'envelope', 64.0, pre_context=1, post_context=6,
+                                   final_batch_size=100, shuffle_buffer_size=0)
+    bd.set_trials(names, lengths, xa, ya)
+    return bd
+
+  random_state = __import__('random').getstate()
+  resident = make(torch.as_tensor(x, device='cuda'), torch.as_tensor(y, device='cuda'))
+  __import__('random').setstate(random_state)           # same shuffled file order
+  hosted = make(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory())
+  assert hosted._ready is not None and len(hosted._ready) > 1
+  ds_r, ds_h = resident.create_dataset('train'), hosted.create_dataset('train')
+  assert len(ds_h.segment_groups()) > 1
+  s_r = brain_model.RegressionStats.from_dataset(ds_r)
+  s_h = brain_model.RegressionStats.from_dataset(ds_h)
+  assert gpu_util.rel_fro(s_h.gram.cpu().numpy(), s_r.gram.cpu().numpy()) < 1e-6
+  np.testing.assert_allclose(s_h.xtv.cpu().numpy(), s_r.xtv.cpu().numpy(), rtol=1e-9, atol=1e-9)
+  assert s_h.n == s_r.n
+  # a fresh hosted object consumed by iteration first
+  __import__('random').setstate(random_state)
+  hosted2 = make(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory())
+  for (da, ya), (db, yb) in zip(hosted2.create_dataset('train'), ds_r):
+    np.testing.assert_array_equal(da['input_1'].cpu().numpy(), db['input_1'].cpu().numpy())
+    np.testing.assert_array_equal(ya.cpu().numpy(), yb.cpu().numpy())
+  model = brain_model.BrainModelLinearRegression(ds_h, regularization_lambda=0.1)
+  model.fit(hosted2.create_dataset('train'))
+  ref = brain_model.BrainModelLinearRegression(ds_r, regularization_lambda=0.1)
+  ref.fit(ds_r)
+  assert gpu_util.rel_fro(model.weight_matrices[0], ref.weight_matrices[0]) < 1e-5
