@@ -458,18 +458,16 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
     if (dbg) cudaEventRecord(ev[0], st);
     chol_build<<<dim3(blocks_for(Nt * Da), nbat), 256, 0, st>>>(A0, B0, Da, Dy, lam_dev, l0, M);
     if (dbg) cudaEventRecord(ev[1], st);
-    // Look-ahead: the serial chain potf2 -> panel solve -> update of the NEXT panel's columns runs
-    // on the caller's stream; the wide trailing update of panel j runs on a side stream and overlaps
-    // the chain of panel j + 1.
+    // Two 64-column panels form a 128-column block.  The serial chain -- potf2, panel solve, the
+    // rank-64 update of the block's second panel, potf2, panel solve, then the rank-128 update of
+    // the NEXT block's columns -- runs on the caller's stream; the wide rank-128 trailing update of
+    // block b (everything right of the next block) runs on a side stream and overlaps the chain of
+    // block b + 1 (look-ahead).  Rank-128 updates halve the passes over the trailing matrix.
     cudaStream_t side = h->lane_stream[0];
-    int panel = 0;
-    for (int j0 = 0; j0 < Da; j0 += CH_NB, ++panel) {
-      const int jb = std::min(CH_NB, Da - j0);
-      // panel j's columns got their last update from narrow(j-1) (this stream); the wide updates that
-      // touched them finished with wide(j-2), which narrow(j-1) already waited for.
+    auto panel_factor = [&](int j0, int jb) -> int {
       chol_potf2<<<nbat, 256, potf2_smem, st>>>(M, Nt, j0, jb, info + l0, Linv, linv_stride);
       const long long below = Nt - j0 - jb;
-      if (below <= 0) continue;
+      if (below <= 0) return TD_OK;
       // panel solve P <- P L_jj^-T as a GEMM with the explicit 64 x 64 inverse
       chol_copy_panel<<<dim3(blocks_for(below * jb), nbat), 256, 0, st>>>(M, Nt, j0, jb, tmp);
       TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)below, jb, jb, &one,
@@ -477,32 +475,45 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
                                                 Linv + (size_t)(j0 / CH_NB) * CH_NB * CH_NB, CH_NB,
                                                 linv_stride, &zero, M + (size_t)j0 * Nt + j0 + jb,
                                                 (int)Nt, Nt * Nt, nbat));
-      TD_CHECK_CUDA(cudaEventRecord(h->ev_panel[panel & 7], st));
-      const long long t0 = (long long)j0 + jb;
-      if (t0 >= Da) continue;
-      // narrow update: the next panel's columns [t0, t0 + 64), after the previous wide update
-      // (which also wrote them) has finished
-      if (panel > 0) TD_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_wide[(panel - 1) & 7], 0));
-      const long long nnar = std::min<long long>(CH_NB, Da - t0);
-      {
-        const double* Prow = M + (size_t)j0 * Nt + t0;
-        double* C = M + (size_t)t0 * Nt + t0;
-        TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)(Nt - t0), (int)nnar, jb,
-                                                  &minus_one, Prow, (int)Nt, Nt * Nt, Prow, (int)Nt, Nt * Nt, &one,
-                                                  C, (int)Nt, Nt * Nt, nbat));
+      return TD_OK;
+    };
+    // C[c0:, c0:c0+nc] -= P[c0:, :] P[c0:c0+nc, :]'  with P = M[:, p0:p0+k]
+    auto update = [&](cublasHandle_t blas, long long p0, int k, long long c0, long long nc) -> int {
+      const double* Prow = M + (size_t)p0 * Nt + c0;
+      double* C = M + (size_t)c0 * Nt + c0;
+      TD_CHECK_SOLVER(cublasDgemmStridedBatched(blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)(Nt - c0), (int)nc, k,
+                                                &minus_one, Prow, (int)Nt, Nt * Nt, Prow, (int)Nt, Nt * Nt, &one,
+                                                C, (int)Nt, Nt * Nt, nbat));
+      return TD_OK;
+    };
+    constexpr int CH_BLK = 2 * CH_NB;
+    int blk = 0;
+    for (int b0 = 0; b0 < Da; b0 += CH_BLK, ++blk) {
+      const int kb = std::min(CH_BLK, Da - b0);              // columns of this block
+      const int jb1 = std::min(CH_NB, kb);
+      // The block's columns got their last updates from the previous block's narrow update (this
+      // stream) and from wide updates that the narrow update had already waited for.
+      if ((rc = panel_factor(b0, jb1))) return rc;
+      if (kb > jb1) {
+        const int t1 = b0 + jb1, jb2 = kb - jb1;
+        if ((rc = update(h->blas, b0, jb1, t1, jb2))) return rc;      // second panel, rank 64
+        if ((rc = panel_factor(t1, jb2))) return rc;
       }
-      // wide update on the side stream: columns [t0 + 64, Da), lower block-triangle, 512-column blocks
-      TD_CHECK_CUDA(cudaStreamWaitEvent(side, h->ev_panel[panel & 7], 0));
-      for (long long cb = t0 + nnar; cb < Da; cb += 512) {
-        const long long ncb = std::min<long long>(512, Da - cb);
-        const double* Prow = M + (size_t)j0 * Nt + cb;      // P[cb:, :]   [Nt - cb, jb], ld Nt
-        double* C = M + (size_t)cb * Nt + cb;               // C[cb:, cb:cb+ncb]
-        TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas_side, CUBLAS_OP_N, CUBLAS_OP_T, (int)(Nt - cb), (int)ncb, jb,
-                                                  &minus_one, Prow, (int)Nt, Nt * Nt, Prow, (int)Nt, Nt * Nt, &one,
-                                                  C, (int)Nt, Nt * Nt, nbat));
-      }
-      TD_CHECK_CUDA(cudaEventRecord(h->ev_wide[panel & 7], side));
+      TD_CHECK_CUDA(cudaEventRecord(h->ev_panel[blk & 7], st));
+      const long long t2 = (long long)b0 + kb;
+      if (t2 >= Da) continue;
+      // narrow update: the next block's columns, after the previous wide update (which also wrote
+      // them) has finished
+      if (blk > 0) TD_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_wide[(blk - 1) & 7], 0));
+      const long long nnar = std::min<long long>(CH_BLK, Da - t2);
+      if ((rc = update(h->blas, b0, kb, t2, nnar))) return rc;
+      // wide update on the side stream: columns [t2 + 128, Da), lower block-triangle, 512-column blocks
+      TD_CHECK_CUDA(cudaStreamWaitEvent(side, h->ev_panel[blk & 7], 0));
+      for (long long cb = t2 + nnar; cb < Da; cb += 512)
+        if ((rc = update(h->blas_side, b0, kb, cb, std::min<long long>(512, Da - cb)))) return rc;
+      TD_CHECK_CUDA(cudaEventRecord(h->ev_wide[blk & 7], side));
     }
+    const int panel = blk;
     // everything the side stream did must be visible before the back substitution
     if (panel > 0) TD_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_wide[(panel - 1) & 7], 0));
     TD_CHECK_CUDA(cudaEventRecord(h->ev_ready, side));
