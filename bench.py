@@ -193,9 +193,9 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one Gram launch on the bench workload (ncu --set
-# full capture, profiles/r01_ncu_gram_kernel_summary.txt): 554.0 MB + 42.1 MB.  The staged planes are
+# full capture, profiles/r01_ncu_gram_kernel_summary.txt): 556.7 MB + 41.2 MB.  The staged planes are
 # 4 x 118 MB and are read once (L2 hit rate 97 %), the Gram is written once.
-GRAM_DRAM_TRAFFIC_BYTES = 596103936
+GRAM_DRAM_TRAFFIC_BYTES = 597866752
 
 
 def main():
