@@ -170,6 +170,57 @@ def test_segment_additivity_and_toeplitz_structure_at_scale():
   assert gpu_util.rel_fro(diag, want_d) < GRAM_TOL
 
 
+def _lag_blocks_match(G, xd, n_trials, n, c, lags, pairs, tol):
+  """Lag block (k1, k2) of the Gram of a pre=0 design = sum over trials of x[k1:k1+h]' x[k2:k2+h],
+  h = n - max(k1, k2) (float64 on the device as the independent check)."""
+  x3 = xd.view(n_trials, n, c)
+  for k1, k2 in pairs:
+    h = n - max(k1, k2)
+    want = torch.zeros((c, c), dtype=torch.float64, device=xd.device)
+    for i in range(n_trials):
+      want += x3[i, k1:k1 + h].to(torch.float64).t() @ x3[i, k2:k2 + h].to(torch.float64)
+    got = G[k1 * c:(k1 + 1) * c, k2 * c:(k2 + 1) * c].to(torch.float64)
+    err = float(torch.linalg.norm(got - want) / torch.linalg.norm(want))
+    assert err < tol, (k1, k2, err)
+
+
+def test_full_size_config2_recording():
+  """BASELINE.json configs[1] at full size (60 x 7680 frames, 64 channels, 32 lags, D = 2048):
+  exact symmetry, additivity over a split of the trials, and lag blocks against float64."""
+  gen = torch.Generator(device='cuda')
+  gen.manual_seed(2)
+  n_trials, n, c, lags = 60, 7680, 64, 32
+  xd = torch.randn((n_trials * n, c), generator=gen, device='cuda')
+  starts = [i * n for i in range(n_trials)]
+  lens = [n] * n_trials
+  G = ops.lagged_gram([ops.Stream(xd, 0, lags - 1, starts, lens)], lens)
+  assert torch.equal(G, G.t())
+  _lag_blocks_match(G, xd, n_trials, n, c, lags, [(0, 0), (3, 20), (31, 31), (0, 31), (17, 18)], 2e-5)
+  keep_a = [n if i < 23 else 0 for i in range(n_trials)]
+  keep_b = [0 if i < 23 else n for i in range(n_trials)]
+  Ga = ops.lagged_gram([ops.Stream(xd, 0, lags - 1, starts, lens)], keep_a).to(torch.float64)
+  Gb = ops.lagged_gram([ops.Stream(xd, 0, lags - 1, starts, lens)], keep_b).to(torch.float64)
+  assert gpu_util.rel_fro((Ga + Gb).cpu().numpy(), G.to(torch.float64).cpu().numpy()) < 5e-6
+
+
+def test_config4_width_one_trial():
+  """BASELINE.json configs[3] width (306 channels x 100 lags, D = 30 600, 7875 pair tiles) on one
+  100 000-frame trial: thousands of work items per CTA pair, a boundary every 156 k-tiles -- the
+  shape on which a shared accumulator hand-off barrier used to deadlock."""
+  free, _ = torch.cuda.mem_get_info()
+  if free < 12 * (1 << 30):
+    pytest.skip('needs 12 GB of device memory')
+  gen = torch.Generator(device='cuda')
+  gen.manual_seed(4)
+  n, c, lags = 100000, 306, 100
+  xd = torch.randn((n, c), generator=gen, device='cuda')
+  G = ops.lagged_gram([ops.Stream(xd, 0, lags - 1, [0], [n])], [n])
+  _lag_blocks_match(G, xd, 1, n, c, lags, [(0, 0), (3, 50), (99, 99), (17, 18), (0, 99)], 2e-5)
+  assert torch.equal(G[:4096, :4096], G[:4096, :4096].t())
+  del G
+  torch.cuda.empty_cache()
+
+
 def test_argument_errors_surface_as_exceptions():
   x = torch.zeros((100, 4), device='cuda')
   from telluride_decoding_b200 import _lib
