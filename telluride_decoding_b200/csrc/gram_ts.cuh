@@ -37,9 +37,6 @@ namespace ts {
 #define TS_PROF_DECL
 #define TS_PROF_FLUSH(total_idx, ...) {}
 #endif
-#ifndef TD_TS_EXP
-#define TD_TS_EXP 0
-#endif
 
 constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = 3 * OPERAND_BYTES;           // A_raw, B_raw (hi), B_lo
