@@ -206,6 +206,19 @@ def window_count(n_frames, width, step):
   return int(_lib.load().td_window_count(int(n_frames), int(width), int(step)))
 
 
+def total_windows(seg_len, widths, steps):
+  """Number of windows over all segments and shapes: sum of (n - W)//S + 1 where n >= W
+  (result_store.py:262-271); vectorised, this sits on the host path of every decoder call."""
+  import numpy as np
+  lens = np.asarray(seg_len, dtype=np.int64)
+  total = 0
+  for w, s in zip(widths, steps):
+    if w > 0 and s > 0:
+      fits = lens[lens >= w]
+      total += int(((fits - w) // s + 1).sum())
+  return total
+
+
 def windowed_corr(a, b, seg_start, seg_len, widths, steps, mode, reduction='first', mu_a=None,
                   mu_b=None, power=None, lda_params=None):
   """Sliding-window values for every (width, step) shape in one pass over the data.
@@ -217,8 +230,7 @@ def windowed_corr(a, b, seg_start, seg_len, widths, steps, mode, reduction='firs
   lib = _lib.load()
   mode_id = {'plain': 0, 'global': 1, 'local': 2, 'global_all': 3}[mode]
   dims = int(a.shape[1]) if mode_id else 1
-  total = sum(((n - w) // s + 1) for w, s in zip(widths, steps) for n in seg_len
-              if w > 0 and s > 0 and n >= w)
+  total = total_windows(seg_len, widths, steps)
   cols = dims if mode_id >= 2 else 1
   out = torch.empty((max(total, 1), cols), dtype=torch.float64, device=a.device)
   offsets = (ctypes.c_int64 * (len(widths) + 1))()

@@ -230,3 +230,14 @@ def test_scaled_lda_matches_reference(golden_dir):
   other.model_params = dec.model_params
   np.testing.assert_allclose(other.reduce_with_lda(d['s1_corr'])[:, 0], g['transform_s1'][:, 0],
                              rtol=1e-9, atol=1e-12)
+
+
+def test_total_windows_matches_the_store_rule():
+  """(n - W)//S + 1 windows per segment with n >= W (test/result_store_test.py:217-218)."""
+  from telluride_decoding_b200 import ops
+  lens = [1000, 7680, 99, 128, 0, 3841]
+  widths, steps = [128, 256, 640, 3840, 201], [64, 128, 320, 1920, 100]
+  want = sum((n - w) // s + 1 for w, s in zip(widths, steps) for n in lens if n >= w)
+  assert ops.total_windows(lens, widths, steps) == want
+  assert ops.total_windows([1000], [201], [100]) == 8
+  assert ops.total_windows([], [10], [5]) == 0
