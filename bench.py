@@ -374,9 +374,9 @@ def main():
                single_pass_frames_per_s=frames / (r['gram_pass_s'] + r['solve_s']))
 
   # stage, gram, symmetrize, thin, thin-reduce + solve: scale, colmajor, build, take_y, store and per
-  # 64-column panel potf2 + copy (factor) and one back-substitution kernel
+  # 64-column panel potf2 (factor) and one back-substitution kernel (cuBLAS GEMMs are not counted)
   n_panels = (CFG['channels'] * (CFG['pre'] + 1 + CFG['post']) + 1 + 63) // 64
-  n_launch = 5 + 5 + 3 * n_panels
+  n_launch = 5 + 5 + 2 * n_panels
 
   # ---- AAD leg (BASELINE.json configs[4]): sliding-window correlation + winner-take-all ----------
   aad = None

@@ -220,8 +220,8 @@ __global__ void chol_build(const double* __restrict__ A0, const double* __restri
   Ml[c * Nt + r] = v;
 }
 
-// Factor the jb x jb diagonal block at (j0, j0) of every matrix in place (lower) and write the
-// inverse of the factor, Linv [batch][64][64] column-major (zero padded), for the panel solve.
+// Factor the jb x jb diagonal block at (j0, j0) of every working matrix M, store the factor (lower)
+// at the same place of L and write the inverse of the factor, Linv [batch][64][64] column-major (zero padded), for the panel solve.
 // info[l] = first non-positive pivot (1-based, global column) or unchanged.
 //
 // This kernel sits on the serial chain of the blocked factorisation (once per 64 columns, one CTA per
@@ -236,13 +236,15 @@ __device__ __forceinline__ double shfl_f64(double v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
 }
 
-__global__ void __launch_bounds__(256) chol_potf2(double* M, long long Nt, int j0, int jb, int* info,
-                                                  double* __restrict__ Linv, long long linv_stride) {
+__global__ void __launch_bounds__(256) chol_potf2(const double* __restrict__ M, double* __restrict__ L, long long Nt,
+                                                  int j0, int jb, int* info, double* __restrict__ Linv,
+                                                  long long linv_stride) {
   extern __shared__ double chol_sm[];
   double (*T)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chol_sm);                          // the block: lower triangle, identity padding
   double (*X)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(chol_sm + CH_NB * (CH_NB + 1));    // its inverse
   double (*P)[CH_SB + 1] = reinterpret_cast<double (*)[CH_SB + 1]>(chol_sm + 2 * CH_NB * (CH_NB + 1)); // panel of the current step
-  double* Ml = M + (size_t)blockIdx.x * Nt * Nt + (size_t)j0 * Nt + j0;
+  const double* Ml = M + (size_t)blockIdx.x * Nt * Nt + (size_t)j0 * Nt + j0;
+  double* Ll = L + (size_t)blockIdx.x * Nt * Nt + (size_t)j0 * Nt + j0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int e = tid; e < CH_NB * CH_NB; e += 256) {
     const int c = e >> 6, r = e & 63;
@@ -365,20 +367,8 @@ __global__ void __launch_bounds__(256) chol_potf2(double* M, long long Nt, int j
   for (int e = tid; e < CH_NB * CH_NB; e += 256) {
     const int c = e >> 6, r = e & 63;
     Li[e] = X[r][c];
-    if (r >= c && r < jb && c < jb) Ml[(size_t)c * Nt + r] = T[r][c];
+    if (r >= c && r < jb && c < jb) Ll[(size_t)c * Nt + r] = T[r][c];
   }
-}
-
-// tmp[batch][64][Nt] <- the panel rows below the diagonal block (source of the panel GEMM).
-__global__ void chol_copy_panel(const double* __restrict__ M, long long Nt, int j0, int jb,
-                                double* __restrict__ tmp) {
-  const long long below0 = (long long)j0 + jb;
-  const long long rows = Nt - below0;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * jb) return;
-  const long long c = i / rows, r = below0 + (i - c * rows);
-  tmp[(size_t)blockIdx.y * CH_NB * Nt + (size_t)c * Nt + r] =
-      M[(size_t)blockIdx.y * Nt * Nt + (size_t)(j0 + c) * Nt + r];
 }
 
 // Back substitution step for block j: x_j = L_jj^-T y_j (a 64 x 64 product with the stored inverse,
@@ -435,14 +425,14 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
   int rc;
   const long long Nt = (long long)Da + Dy;
   const size_t per = (size_t)Nt * Nt * sizeof(double);
-  const int batch_max = (int)std::max<size_t>(1, std::min<size_t>(n_lambda, ((size_t)6 << 30) / per));
+  const int batch_max = (int)std::max<size_t>(1, std::min<size_t>(n_lambda, ((size_t)6 << 30) / (2 * per)));
   const long long n_panels = (Da + CH_NB - 1) / CH_NB;
   const long long linv_stride = n_panels * CH_NB * CH_NB;
-  double *M, *Y, *Xs, *lam_dev, *Linv, *tmp;
+  double *M, *L, *Y, *Xs, *lam_dev, *Linv;     // M: working matrices (updated in place), L: the factors
   int* info;
   if ((rc = sc.get((size_t)Nt * Nt * batch_max, &M)) || (rc = sc.get((size_t)Da * Dy * batch_max, &Y)) || (rc = sc.get((size_t)Da * Dy * batch_max, &Xs)) ||
       (rc = sc.get(n_lambda, &lam_dev)) || (rc = sc.get(n_lambda, &info)) ||
-      (rc = sc.get((size_t)linv_stride * batch_max, &Linv)) || (rc = sc.get((size_t)CH_NB * Nt * batch_max, &tmp)))
+      (rc = sc.get((size_t)linv_stride * batch_max, &Linv)) || (rc = sc.get((size_t)Nt * Nt * batch_max, &L)))
     return rc;
   TD_CHECK_CUDA(cudaMemcpyAsync(lam_dev, lambdas, n_lambda * sizeof(double), cudaMemcpyHostToDevice, st));
   TD_CHECK_CUDA(cudaMemsetAsync(info, 0, n_lambda * sizeof(int), st));
@@ -465,21 +455,21 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
     // block b + 1 (look-ahead).  Rank-128 updates halve the passes over the trailing matrix.
     cudaStream_t side = h->lane_stream[0];
     auto panel_factor = [&](int j0, int jb) -> int {
-      chol_potf2<<<nbat, 256, potf2_smem, st>>>(M, Nt, j0, jb, info + l0, Linv, linv_stride);
+      chol_potf2<<<nbat, 256, potf2_smem, st>>>(M, L, Nt, j0, jb, info + l0, Linv, linv_stride);
       const long long below = Nt - j0 - jb;
       if (below <= 0) return TD_OK;
-      // panel solve P <- P L_jj^-T as a GEMM with the explicit 64 x 64 inverse
-      chol_copy_panel<<<dim3(blocks_for(below * jb), nbat), 256, 0, st>>>(M, Nt, j0, jb, tmp);
+      // panel solve L21 = A21 L_jj^-T as a GEMM with the explicit 64 x 64 inverse, out of place
+      // (working matrix -> factor matrix), so no copy of the panel is needed
       TD_CHECK_SOLVER(cublasDgemmStridedBatched(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)below, jb, jb, &one,
-                                                tmp + j0 + jb, (int)Nt, (long long)CH_NB * Nt,
+                                                M + (size_t)j0 * Nt + j0 + jb, (int)Nt, Nt * Nt,
                                                 Linv + (size_t)(j0 / CH_NB) * CH_NB * CH_NB, CH_NB,
-                                                linv_stride, &zero, M + (size_t)j0 * Nt + j0 + jb,
+                                                linv_stride, &zero, L + (size_t)j0 * Nt + j0 + jb,
                                                 (int)Nt, Nt * Nt, nbat));
       return TD_OK;
     };
-    // C[c0:, c0:c0+nc] -= P[c0:, :] P[c0:c0+nc, :]'  with P = M[:, p0:p0+k]
+    // C[c0:, c0:c0+nc] -= P[c0:, :] P[c0:c0+nc, :]'  with P = L[:, p0:p0+k], C in the working matrix
     auto update = [&](cublasHandle_t blas, long long p0, int k, long long c0, long long nc) -> int {
-      const double* Prow = M + (size_t)p0 * Nt + c0;
+      const double* Prow = L + (size_t)p0 * Nt + c0;
       double* C = M + (size_t)c0 * Nt + c0;
       TD_CHECK_SOLVER(cublasDgemmStridedBatched(blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)(Nt - c0), (int)nc, k,
                                                 &minus_one, Prow, (int)Nt, Nt * Nt, Prow, (int)Nt, Nt * Nt, &one,
@@ -519,10 +509,10 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
     TD_CHECK_CUDA(cudaEventRecord(h->ev_ready, side));
     TD_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_ready, 0));
     if (dbg) cudaEventRecord(ev[2], st);
-    chol_take_y<<<dim3(blocks_for((long long)Da * Dy), nbat), 256, 0, st>>>(M, Nt, Da, Dy, Y);
+    chol_take_y<<<dim3(blocks_for((long long)Da * Dy), nbat), 256, 0, st>>>(L, Nt, Da, Dy, Y);
     for (int j0 = ((Da - 1) / CH_NB) * CH_NB; j0 >= 0; j0 -= CH_NB) {
       const int jb = std::min(CH_NB, Da - j0);
-      chol_back<<<dim3(blocks_for(std::max(j0, 1)), nbat, Dy), 256, 0, st>>>(M, Nt, Da, j0, jb, Linv, linv_stride, Y, Xs);
+      chol_back<<<dim3(blocks_for(std::max(j0, 1)), nbat, Dy), 256, 0, st>>>(L, Nt, Da, j0, jb, Linv, linv_stride, Y, Xs);
     }
     chol_store<<<dim3(blocks_for((long long)Da * Dy), nbat), 256, 0, st>>>(Xs, Da, Dy, W_out + (size_t)l0 * Da * Dy);
     TD_CHECK_CUDA(cudaGetLastError());
