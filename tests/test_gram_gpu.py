@@ -76,6 +76,27 @@ def test_pair_kernels_with_short_chunks_and_many_work_items(method, chunk_rows, 
     assert gpu_util.rel_fro(got.cpu().numpy(), want.cpu().numpy()) < GRAM_TOL
 
 
+@pytest.mark.parametrize('method', [0, 2])
+def test_two_stream_gram_on_the_pair_kernels(method):
+  """Z = [X | X2] wide enough for CTA pairs (two tensor maps, channel padding 40 -> 64 and 6 -> 8
+  boxes, different contexts per stream, ragged kept rows) against the fp32 cross-check kernel."""
+  rng = np.random.RandomState(23)
+  n_trials, frames = 4, 2500
+  x = (rng.randn(n_trials * frames, 40) + 0.2).astype(np.float32)
+  x2 = rng.randn(n_trials * frames, 6).astype(np.float32)
+  xd, x2d = torch.as_tensor(x, device='cuda'), torch.as_tensor(x2, device='cuda')
+  starts = [i * frames for i in range(n_trials)]
+  lens = [frames] * n_trials
+  keep = [frames, frames - 100, frames, frames - 1]
+  sx = ops.Stream(xd, 3, 22, starts, lens)            # 26 lags x 40 = 1040 columns
+  s2 = ops.Stream(x2d, 0, 5, starts, lens)            # 6 lags x 6 = 36 columns
+  want = ops.lagged_gram([sx, s2], keep, options=ops.gram_options(method=1)).cpu().numpy()
+  got = ops.lagged_gram([sx, s2], keep, options=ops.gram_options(method=method, cta_group=2)).cpu().numpy()
+  assert got.shape == (1076, 1076)
+  assert gpu_util.rel_fro(got, want) < GRAM_TOL
+  np.testing.assert_array_equal(got, got.T)
+
+
 def test_simt_cross_check_agrees():
   ds, batches = _dataset(2000, 20, 2, 2, 200, seed=5)
   keep = ds.seg_rows
