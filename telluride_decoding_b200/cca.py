@@ -6,7 +6,6 @@ x'x, y'y and x'y over the two lagged inputs come from ONE pass of the two-stream
 Gram over Z = [X | Y]; the whitening / SVD runs in cuSOLVER (float64).
 """
 
-import numpy as np
 import torch
 
 from telluride_decoding_b200 import brain_model

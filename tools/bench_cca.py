@@ -4,7 +4,6 @@
 Prints one JSON line with the device times of the statistics and of the solve."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 from telluride_decoding_b200 import brain_data, cca
 

@@ -1,6 +1,6 @@
 """Development aid: run only td_ridge_solve on a random SPD system (for ncu / TD_DEBUG=2) and check
 the batched sweep against a float64 torch solve."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from telluride_decoding_b200 import ops
