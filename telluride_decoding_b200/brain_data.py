@@ -586,6 +586,20 @@ class TrialBrainData(BrainData):
   # (the Gram needs ~3x longer per frame than the PCIe copy).
   UPLOAD_CUTS = (0.1, 0.4, 1.0)
 
+  @classmethod
+  def upload_cuts(cls, lengths):
+    """Row ends of the upload chunks: the first trial boundary at or after each UPLOAD_CUTS fraction."""
+    n = sum(int(l) for l in lengths)
+    cuts, cur = [], 0
+    for i, length in enumerate(lengths):                 # chunk ends at trial boundaries
+      cur += int(length)
+      if len(cuts) < len(cls.UPLOAD_CUTS) and (cur >= cls.UPLOAD_CUTS[len(cuts)] * n or
+                                               i == len(lengths) - 1):
+        cuts.append(cur)
+    if cuts[-1] != n:
+      cuts.append(n)
+    return cuts
+
   def _async_upload(self, x_host, y_host, lengths):
     """Device copies of two pinned [frames, channels] arrays, issued chunk by chunk on a side stream;
     sets self._ready = [(row_end, event)]."""
@@ -597,15 +611,7 @@ class TrialBrainData(BrainData):
     if side is None:
       side = TrialBrainData._copy_streams[dev.index] = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream())        # the buffers may be recycled memory
-    n = int(x_host.shape[0])
-    cuts, cur = [], 0
-    for i, length in enumerate(lengths):                 # chunk ends at trial boundaries
-      cur += int(length)
-      if len(cuts) < len(self.UPLOAD_CUTS) and (cur >= self.UPLOAD_CUTS[len(cuts)] * n or
-                                                i == len(lengths) - 1):
-        cuts.append(cur)
-    if cuts[-1] != n:
-      cuts.append(n)
+    cuts = self.upload_cuts(lengths)
     ready, r0 = [], 0
     with torch.cuda.stream(side):
       for r1 in cuts:

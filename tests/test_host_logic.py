@@ -241,3 +241,30 @@ def test_total_windows_matches_the_store_rule():
   assert ops.total_windows(lens, widths, steps) == want
   assert ops.total_windows([1000], [201], [100]) == 8
   assert ops.total_windows([], [10], [5]) == 0
+
+
+def test_upload_chunks_and_segment_groups():
+  """Trial-aligned upload chunks (10 / 40 / 100 % of the frames) and the grouping of dataset
+  segments by the chunk that completes them (events replaced by tags: no GPU needed)."""
+  import torch
+  from telluride_decoding_b200 import brain_data
+  assert brain_data.TrialBrainData.upload_cuts([7680] * 60) == [46080, 184320, 460800]
+  assert brain_data.TrialBrainData.upload_cuts([700, 650, 900, 512, 801, 640, 777]) == [700, 2250, 4980]
+  assert brain_data.TrialBrainData.upload_cuts([5, 5]) == [5, 10]
+  assert brain_data.TrialBrainData.upload_cuts([10, 1, 1]) == [10, 11, 12]
+  lengths = [700, 650, 900, 512, 801, 640, 777]
+  n = sum(lengths)
+  x = torch.zeros((n, 3)); y = torch.zeros((n, 1)); z = torch.zeros((n, 1))
+  files, cur = [], 0
+  order = [3, 0, 6, 1, 5, 2, 4]                      # dataset file order differs from the row order
+  starts = np.concatenate(([0], np.cumsum(lengths)[:-1]))
+  for i in order:
+    files.append(('t%d' % i, int(starts[i]), lengths[i]))
+  ds = brain_data.LaggedDataset(x, z, y, z, files, 1, 2, 0, 0, 0, 1000000, 100, 1, 0, 'train')
+  assert ds.segment_groups() == [(None, list(range(7)))]
+  ds.ready = [(700, 'ev0'), (2250, 'ev1'), (4980, 'ev2')]
+  groups = ds.segment_groups()
+  assert [ev for ev, _ in groups] == ['ev0', 'ev1', 'ev2']
+  by_event = {ev: sorted(order[s] for s in segs) for ev, segs in groups}
+  assert by_event == {'ev0': [0], 'ev1': [1, 2], 'ev2': [3, 4, 5, 6]}
+  assert sorted(s for _, segs in groups for s in segs) == list(range(7))
