@@ -99,10 +99,59 @@ __global__ void __launch_bounds__(256) gram_simt_kernel(MultiView mv, const int6
 constexpr int THIN_TB = 256;      // frames per block
 constexpr int THIN_CB = 64;       // channels per block
 constexpr int THIN_QMAX = 16;
-constexpr int THIN_KT = 4;        // lags per thread (register window)
+constexpr int THIN_KT = 8;        // lags per thread (register window)
 constexpr int THIN_QFAST = 4;     // target columns handled by the register-tiled path
 constexpr int THIN_SLICES = 64;   // partial-sum copies: blocks add into slice (block % 64) to keep
                                   // same-address float64 atomics from serialising, then one reduce
+
+// Register-tiled core of thin_kernel for QT target columns: THIN_KT consecutive lags of one channel.
+// The frames x[r+k0 .. r+k0+KT) slide through registers, so one shared-memory load of x and QT of the
+// targets feed KT*QT FMAs; fp32 partial sums are carried into float64 every 32 frames.
+template <int QT>
+__device__ __forceinline__ void thin_fast(const float* __restrict__ xs, const float* __restrict__ vs, int rows,
+                                          int halo_rows, int cl, int k0, int L, int channels, int c,
+                                          double* __restrict__ xtv) {
+  double accd[THIN_KT][QT];
+#pragma unroll
+  for (int i = 0; i < THIN_KT; ++i)
+#pragma unroll
+    for (int q = 0; q < QT; ++q) accd[i][q] = 0.0;
+  for (int r0 = 0; r0 < rows; r0 += 32) {
+    float accf[THIN_KT][QT];
+#pragma unroll
+    for (int i = 0; i < THIN_KT; ++i)
+#pragma unroll
+      for (int q = 0; q < QT; ++q) accf[i][q] = 0.0f;
+    const int r1 = min(rows, r0 + 32);
+    float win[THIN_KT];
+#pragma unroll
+    for (int i = 0; i < THIN_KT - 1; ++i)
+      win[i + 1] = (r0 + k0 + i < halo_rows) ? xs[(r0 + k0 + i) * THIN_CB + cl] : 0.0f;
+    for (int r = r0; r < r1; ++r) {
+#pragma unroll
+      for (int i = 0; i < THIN_KT - 1; ++i) win[i] = win[i + 1];
+      // (loaded by frame, not by lag validity: the value slides down to the lower lags)
+      win[THIN_KT - 1] = (r + k0 + THIN_KT - 1 < halo_rows) ? xs[(r + k0 + THIN_KT - 1) * THIN_CB + cl] : 0.0f;
+#pragma unroll
+      for (int q = 0; q < QT; ++q) {
+        const float vv = vs[r * QT + q];
+#pragma unroll
+        for (int i = 0; i < THIN_KT; ++i) accf[i][q] = fmaf(win[i], vv, accf[i][q]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < THIN_KT; ++i)
+#pragma unroll
+      for (int q = 0; q < QT; ++q) accd[i][q] += (double)accf[i][q];
+  }
+#pragma unroll
+  for (int i = 0; i < THIN_KT; ++i) {
+    if (k0 + i >= L) continue;
+    const int64_t j = (int64_t)(k0 + i) * channels + c;
+#pragma unroll
+    for (int q = 0; q < QT; ++q) atomicAdd(xtv + j * QT + q, accd[i][q]);
+  }
+}
 
 // Block = (256-frame piece of a segment, 64-channel block).  The raw frames it needs (piece + lag
 // halo) and the targets are staged in shared memory once; thread j = (lag k, channel c) then walks
@@ -150,46 +199,11 @@ __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, i
     if (c >= x.channels) continue;
     const int k0 = kg * THIN_KT;
     if (Q <= THIN_QFAST) {
-      double accd[THIN_KT][THIN_QFAST];
-#pragma unroll
-      for (int i = 0; i < THIN_KT; ++i)
-#pragma unroll
-        for (int q = 0; q < THIN_QFAST; ++q) accd[i][q] = 0.0;
-      for (int r0 = 0; r0 < rows; r0 += 32) {
-        float accf[THIN_KT][THIN_QFAST];
-#pragma unroll
-        for (int i = 0; i < THIN_KT; ++i)
-#pragma unroll
-          for (int q = 0; q < THIN_QFAST; ++q) accf[i][q] = 0.0f;
-        const int r1 = min(rows, r0 + 32);
-        float win[THIN_KT];
-#pragma unroll
-        for (int i = 0; i < THIN_KT - 1; ++i)
-          win[i + 1] = (r0 + k0 + i < halo_rows) ? xs[(r0 + k0 + i) * THIN_CB + cl] : 0.0f;
-        for (int r = r0; r < r1; ++r) {
-#pragma unroll
-          for (int i = 0; i < THIN_KT - 1; ++i) win[i] = win[i + 1];
-          // (loaded by frame, not by lag validity: the value slides down to the lower lags)
-          win[THIN_KT - 1] = (r + k0 + THIN_KT - 1 < halo_rows) ? xs[(r + k0 + THIN_KT - 1) * THIN_CB + cl] : 0.0f;
-#pragma unroll
-          for (int q = 0; q < THIN_QFAST; ++q) {
-            const float vv = (q < Q) ? vs[r * Q + q] : 0.0f;
-#pragma unroll
-            for (int i = 0; i < THIN_KT; ++i) accf[i][q] = fmaf(win[i], vv, accf[i][q]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < THIN_KT; ++i)
-#pragma unroll
-          for (int q = 0; q < THIN_QFAST; ++q) accd[i][q] += (double)accf[i][q];
-      }
-#pragma unroll
-      for (int i = 0; i < THIN_KT; ++i) {
-        if (k0 + i >= L) continue;
-        const int64_t j = (int64_t)(k0 + i) * x.channels + c;
-#pragma unroll
-        for (int q = 0; q < THIN_QFAST; ++q)
-          if (q < Q) atomicAdd(xtv + j * Q + q, accd[i][q]);
+      switch (Q) {
+        case 1: thin_fast<1>(xs, vs, rows, halo_rows, cl, k0, L, x.channels, c, xtv); break;
+        case 2: thin_fast<2>(xs, vs, rows, halo_rows, cl, k0, L, x.channels, c, xtv); break;
+        case 3: thin_fast<3>(xs, vs, rows, halo_rows, cl, k0, L, x.channels, c, xtv); break;
+        default: thin_fast<4>(xs, vs, rows, halo_rows, cl, k0, L, x.channels, c, xtv); break;
       }
     } else {
       for (int i = 0; i < THIN_KT && k0 + i < L; ++i) {
