@@ -25,6 +25,7 @@ from telluride_decoding import attention_decoder              # noqa: E402
 from telluride_decoding import brain_model                    # noqa: E402
 from telluride_decoding import cca                            # noqa: E402
 from telluride_decoding import infer_decoder                  # noqa: E402
+from telluride_decoding import preprocess                     # noqa: E402
 from telluride_decoding import result_store                   # noqa: E402
 from telluride_decoding import scaled_lda                     # noqa: E402
 
@@ -205,6 +206,23 @@ def lda_case():
   print('wrote lda: dprime', dprime, 'slope', params.slope)
 
 
+def streaming_context_case():
+  """Reference Preprocessor.add_context (preprocess.py:487-522) fed batch by batch."""
+  rng = np.random.RandomState(31)
+  x = rng.randn(57, 5).astype(np.float32)
+  out = {'x': x}
+  cases = {'p2q3': (2, 3, [0, 10, 20, 35, 57]), 'p0q4': (0, 4, [0, 6, 30, 57]),
+           'p3q0': (3, 0, [0, 20, 57])}
+  for tag, (pre, post, cuts) in cases.items():
+    p = preprocess.Preprocessor('test', 100, 100, pre_context=pre, post_context=post)
+    for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+      out['%s_%d' % (tag, i)] = p.add_context(x[a:b].astype(np.float64))
+    out[tag + '_cuts'] = np.array(cuts)
+    out[tag + '_ctx'] = np.array([pre, post])
+  np.savez_compressed(os.path.join(OUT, 'streaming_context.npz'), **out)
+  print('wrote streaming_context', {k: v.shape for k, v in out.items() if k.startswith('p2q3_')})
+
+
 def main():
   os.makedirs(OUT, exist_ok=True)
   ridge_case('ridge_small', seed=11, n_frames=1000, channels=3, pre=1, post=2, dy=2,
@@ -216,6 +234,7 @@ def main():
   cca_test42()
   decoder_case()
   lda_case()
+  streaming_context_case()
 
 
 if __name__ == '__main__':

@@ -435,3 +435,37 @@ def aad_accuracy(attention, labels):
   lab = np.reshape(np.asarray(labels), (-1, 1))
   correct = np.logical_xor(att >= 0.5, lab)
   return np.sum(correct) / float(len(correct))
+
+
+# ----------------------------------------------------------------------------
+# Streaming context                        preprocess.py:487-527
+# ----------------------------------------------------------------------------
+
+class StreamingContext(object):
+  """Online lag builder: Preprocessor.add_context (preprocess.py:487-522).  The state is the last
+  pre+post frames (zeros of length pre before the first batch, :500-501); each call returns the
+  rows of the running stream that are complete, i.e. delayed by post_context frames."""
+
+  def __init__(self, pre_context, post_context):
+    self.pre, self.post = int(pre_context), int(post_context)
+    self.state = None
+
+  def reset(self):
+    self.state = None
+
+  def add_context(self, data):
+    data = np.asarray(data)
+    if self.pre == 0 and self.post == 0:
+      return data
+    if self.state is None:
+      self.state = np.zeros((self.pre, data.shape[1]), dtype=data.dtype)
+    joined = np.concatenate((self.state, data))
+    self.state = joined[-(self.pre + self.post):, :]
+    rows = joined.shape[0] - self.pre - self.post
+    if rows < 0:
+      raise ValueError('negative dimensions are not allowed')
+    lags = self.pre + self.post + 1
+    out = np.empty((rows, data.shape[1] * lags), dtype=data.dtype)
+    for k in range(lags):                                     # block k = joined[t + k]
+      out[:, k * data.shape[1]:(k + 1) * data.shape[1]] = joined[k:k + rows]
+    return out

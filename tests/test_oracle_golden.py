@@ -184,3 +184,22 @@ def test_wta_and_step_goldens_from_reference_tests():
   np.testing.assert_array_equal(ora.step_attention(cor1, cor2), [1] * 3 + [0] * 10)
   assert ora.wta_attention(0.6, 0.4) and not ora.wta_attention(0.4, 0.6)
   assert ora.aad_accuracy([True, False, True], [0, 1, 0]) == 1.0
+
+
+def test_streaming_context_matches_reference_preprocessor(golden_dir):
+  """Preprocessor.add_context fed batch by batch (preprocess.py:487-522; the reference's own check
+  is test/preprocess_test.py:235-251)."""
+  g = np.load(os.path.join(golden_dir, 'streaming_context.npz'))
+  x = g['x']
+  for tag in ('p2q3', 'p0q4', 'p3q0'):
+    pre, post = [int(v) for v in g[tag + '_ctx']]
+    cuts = [int(v) for v in g[tag + '_cuts']]
+    ctx = ora.StreamingContext(pre, post)
+    outs = []
+    for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+      got = ctx.add_context(x[a:b])
+      np.testing.assert_array_equal(got, g['%s_%d' % (tag, i)].astype(np.float32))
+      outs.append(got)
+    # the stream of rows equals the offline lag builder, delayed by post_context frames
+    full = ora.add_context(x, pre, post)
+    np.testing.assert_array_equal(np.concatenate(outs), full[:x.shape[0] - post])
