@@ -535,7 +535,9 @@ class TrialBrainData(BrainData):
 
     Pinned host tensors are copied to the GPU asynchronously in a few chunks cut at trial
     boundaries, on a side stream; the datasets made from this object know which rows each copy
-    completes, so the Gram of the first trials runs while the later ones are still on the PCIe bus."""
+    completes, so the Gram of the first trials runs while the later ones are still on the PCIe bus.
+    The host arrays must not be modified until the copies have completed (first use of a dataset
+    made from this object); this object keeps them alive."""
     self._ready = None
     pinned = (isinstance(input_data, torch.Tensor) and isinstance(output_data, torch.Tensor) and
               input_data.device.type == 'cpu' and output_data.device.type == 'cpu' and
@@ -624,6 +626,7 @@ class TrialBrainData(BrainData):
     x.record_stream(side)
     y.record_stream(side)
     self._ready = ready
+    self._host_arrays = (x_host, y_host)            # keep the pinned sources alive while in flight
     return x, y
 
   def _pack(self):

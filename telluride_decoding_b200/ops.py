@@ -48,7 +48,17 @@ class GramWorkspace(object):
     return self.buffer
 
 
-_default_workspace = GramWorkspace()
+_default_workspaces = {}
+
+
+def _default_workspace_for(device):
+  """One cached workspace per (device, stream): calls on the same stream are ordered, calls on
+  different streams must not share staging memory."""
+  key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+  ws = _default_workspaces.get(key)
+  if ws is None:
+    ws = _default_workspaces[key] = GramWorkspace()
+  return ws
 
 
 def lagged_gram(streams, seg_keep, out=None, options=None, workspace=None, seg_first=None):
@@ -69,7 +79,7 @@ def lagged_gram(streams, seg_keep, out=None, options=None, workspace=None, seg_f
   nbytes = ctypes.c_size_t(0)
   _lib.check(lib.td_lagged_gram_workspace_bytes(carr, len(streams), first, keep, len(seg_keep),
                                                 ctypes.byref(options), ctypes.byref(nbytes)))
-  ws = (workspace or _default_workspace).get(nbytes.value, device)
+  ws = (workspace or _default_workspace_for(device)).get(nbytes.value, device)
   with torch.cuda.device(device):
     _lib.check(lib.td_lagged_gram_f32(carr, len(streams), first, keep, len(seg_keep), _lib.ptr(out),
                                       ctypes.c_int64(out.stride(0)), ctypes.byref(options),
