@@ -223,6 +223,27 @@ def streaming_context_case():
   print('wrote streaming_context', {k: v.shape for k, v in out.items() if k.startswith('p2q3_')})
 
 
+def ssd_case():
+  """Reference StateSpaceAttentionDecoder (attention_decoder.py:176-451) on a stream of correlation
+  pairs with an attention switch every 25 pairs: with and without the offset, with a forward lag."""
+  rng = np.random.RandomState(3)
+  n = 90
+  att = (np.arange(n) // 25) % 2 == 0
+  r1 = np.where(att, 0.25, 0.08) + 0.05 * rng.randn(n)
+  r2 = np.where(att, 0.08, 0.25) + 0.05 * rng.randn(n)
+  out = dict(r1=r1, r2=r2)
+  settings = {'default': dict(), 'offset1': dict(offset=1.0),
+              'lag3': dict(forward_lag=3, backward_lag=6)}
+  for tag, kw in settings.items():
+    dec = attention_decoder.StateSpaceAttentionDecoder(20, 1, 10, 1.0, **kw)
+    dec.tune(np.abs(r1[:20]), np.abs(r2[:20]))
+    out[tag + '_tuned'] = np.array(dec.mu_d + dec.rho_d)
+    out[tag + '_out'] = np.array([dec.attention(a, b) for a, b in zip(r1, r2)], dtype=np.float64)
+    out[tag + '_final'] = np.array(dec.mu_d + dec.rho_d)
+  np.savez_compressed(os.path.join(OUT, 'ssd.npz'), **out)
+  print('wrote ssd', out['default_out'][-1])
+
+
 def main():
   os.makedirs(OUT, exist_ok=True)
   ridge_case('ridge_small', seed=11, n_frames=1000, channels=3, pre=1, post=2, dy=2,
@@ -235,6 +256,7 @@ def main():
   decoder_case()
   lda_case()
   streaming_context_case()
+  ssd_case()
 
 
 if __name__ == '__main__':

@@ -268,3 +268,53 @@ def test_upload_chunks_and_segment_groups():
   by_event = {ev: sorted(order[s] for s in segs) for ev, segs in groups}
   assert by_event == {'ev0': [0], 'ev1': [1, 2], 'ev2': [3, 4, 5, 6]}
   assert sorted(s for _, segs in groups for s in segs) == list(range(7))
+
+
+def test_state_space_decoder_matches_reference(golden_dir):
+  """StateSpaceAttentionDecoder against the unmodified reference class (tests/golden/ssd.npz from
+  oracle/gen_golden.py): every output triple of a 90-pair stream, three settings."""
+  from telluride_decoding_b200 import attention_decoder
+  g = np.load(os.path.join(golden_dir, 'ssd.npz'))
+  r1, r2 = g['r1'], g['r2']
+  settings = {'default': dict(), 'offset1': dict(offset=1.0),
+              'lag3': dict(forward_lag=3, backward_lag=6)}
+  for tag, kw in settings.items():
+    dec = attention_decoder.StateSpaceAttentionDecoder(20, 1, 10, 1.0, **kw)
+    dec.tune(np.abs(r1[:20]), np.abs(r2[:20]))
+    np.testing.assert_allclose(np.array(dec.mu_d + dec.rho_d), g[tag + '_tuned'], rtol=1e-13)
+    got = np.array([dec.attention(a, b) for a, b in zip(r1, r2)], dtype=np.float64)
+    np.testing.assert_allclose(got, g[tag + '_out'], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(np.array(dec.mu_d + dec.rho_d), g[tag + '_final'], rtol=1e-11)
+    assert (got[:dec.k_w - 1] == 0.5).all()            # undecided until the window is full
+
+
+def test_state_space_decoder_like_the_reference_tests():
+  """test/attention_decoder_test.py:184-236 (decodes synthetic switches, error < 15 %), :238-284
+  (log-normal initialisation) and :291-300 (factory)."""
+  from telluride_decoding_b200 import attention_decoder
+  rng = np.random.RandomState(0)
+  n, switch, init = 1000, 300, 100
+  true_state = ((np.arange(n) // switch) % 2) + 1
+  att, unatt = 0.2 + 0.1 * rng.randn(n), 0.05 + 0.1 * rng.randn(n)
+  corr = np.where((true_state == 1)[:, None], np.stack([att, unatt], 1), np.stack([unatt, att], 1))
+  corr = np.minimum(1, np.maximum(-1, corr))
+  ad = attention_decoder.StateSpaceAttentionDecoder(20, 1, 10, 1)
+  ad.tune_log_normal_priors(corr[:init, 0], corr[:init, 1])
+  results = np.zeros((n - ad.k_w - init, 3))
+  for i in range(n - init):
+    results[i - ad.k_w] = ad.attention(corr[i + init, 0], corr[i + init, 1])
+  s1 = results[:, 0] > 0.5
+  assert np.mean(s1 != (true_state[init + ad.k_w:] < 2)) < 0.15
+  data_a = np.exp(rng.randn(200000) * 0.1 + 0.2)
+  data_b = np.exp(rng.randn(200000) * 0.1)
+  ad = attention_decoder.StateSpaceAttentionDecoder(20, 1, 10, 1, 1)
+  ad.tune(data_a, data_b)
+  assert abs(ad.mu_d[0] - np.mean(np.log(data_a))) < 1e-3
+  assert abs(ad.rho_d[0] - 1.0 / np.var(np.log(data_a))) < 5
+  ad2 = attention_decoder.StateSpaceAttentionDecoder(20, 1, 10, 1, 1, offset=1.0)
+  ad2.tune(data_a, data_b)
+  assert ad2.mu_d[0] > np.mean(np.log(data_a)) + 0.01
+  assert isinstance(attention_decoder.create_attention_decoder('ssd'),
+                    attention_decoder.StateSpaceAttentionDecoder)
+  with pytest.raises(ValueError, match='Unknown type'):
+    attention_decoder.create_attention_decoder('bad type name')
