@@ -9,20 +9,21 @@
 //      separated by >= (pre+post) zero frames.  Row (stream q, lag k, channel c) of Z' is then the
 //      staged row c read at a time shift of (k - pre): a plain TMA box at a shifted coordinate.
 //      Zero padding at segment edges comes from the zero gaps / TMA out-of-bounds fill.
-//   2. gram:   persistent warp-specialised kernel.  K dimension = time, cut into 32-frame
-//      k-tiles; M/N = rows of Z' in 128-row operand tiles made of CB-channel TMA boxes.
-//        warp 0      TMA producer: lands the RAW fp32 tiles (K-major, 128B swizzle), 3-stage ring
-//        warps 10-11 converters: build the 3xTF32 split in shared memory once per staged tile --
-//                    hi is the raw tile itself (kind::tf32 ignores the 13 low mantissa bits, i.e.
-//                    truncates; verified on B200), lo = tf32_rna(x - trunc(x)) goes to a second
-//                    tile; they also zero the frames of a k-tile that are not design rows of this
-//                    call.  Only half of the operand bytes cross L2 -> SM this way; with both
-//                    planes staged in HBM the kernel was bound by that ingest (measured: dropping
-//                    two of three MMAs did not change its duration, halving the TMA bytes did).
-//        warp 1      issues hi*hi + hi*lo + lo*hi tcgen05.mma (kind::tf32) into a TMEM accumulator
-//        warps 2-9   epilogue: every `chunk` k-tiles the accumulator is drained into fp32 registers
-//                    (round-to-nearest adds; bounds the tensor-core accumulation length), while the
-//                    MMA warp continues in the second TMEM buffer.
+//   2. gram:   persistent warp-specialised kernels.  K dimension = time, cut into 32-frame k-tiles;
+//      M/N = rows of Z' in 128-row operand tiles made of CB-channel TMA boxes; raw fp32 tiles land
+//      by TMA (K-major, 128B swizzle); the 3xTF32 split is built on chip (hi = the raw tile, because
+//      kind::tf32 truncates the 13 low mantissa bits -- verified on B200; lo = tf32_rna(x - trunc(x)));
+//      hi*hi + hi*lo + lo*hi tcgen05.mma into TMEM; every `chunk` k-tiles the accumulator is drained
+//      into fp32 registers (bounds the tensor-core accumulation length).  Two flavours:
+//        * ts::lagged_gram_ts_kernel (gram_ts.cuh): CTA pairs, A operand written to TENSOR memory by
+//          the converter warps, two MMA issuing warps, three rotating accumulator regions.  Default
+//          for designs of >= 512 columns.
+//        * lagged_gram_umma_kernel<CG> (below): both operands from shared memory.
+//            warp 0      TMA producer, 3-stage ring
+//            warps 10-11 converters (lo tile + masking of frames that are not design rows)
+//            warp 1      MMA issue (elect.sync), double-buffered TMEM accumulator
+//            warps 2-9   epilogue
+//          CG = 1 (128x128 tiles) for narrow designs; CG = 2 kept as method 2.
 //      Work = (superchunk, lower-triangle tile, k-range) split evenly over CTAs (stream-K); partial
 //      tiles are combined with fp32 red.add into G.
 //   3. the computed triangle is mirrored by td_symmetrize_f32.
