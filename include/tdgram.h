@@ -157,7 +157,10 @@ int td_ridge_solve(const double* G_aug_dev, const double* C_aug_dev, int Da, int
  * Gxy [D1,D2], sum_x [D1], sum_y [D2]; n_frames = total rows, n_norm = n_batches*n_row - 1.
  * Outputs float32: rot_x [D1,dim], rot_y [D2,dim], mean_x [D1], mean_y [D2], e [dim].
  * Signs: each (rot_x[:,i], rot_y[:,i]) pair is normalised so that the entry of rot_x[:,i] with
- * the largest magnitude is positive.  Synchronises the stream. */
+ * the largest magnitude is positive.  With reg > 10*eps_eig the whitening is by Cholesky factors
+ * (same canonical pairs, ~10x faster); otherwise, or if a factorisation fails or the dim-th
+ * canonical correlation is below 1e-4 of the first, by the reference's eigendecompositions with the
+ * eps_eig threshold and an SVD.  Synchronises the stream. */
 int td_cca_solve(const double* Gxx_dev, const double* Gyy_dev, const double* Gxy_dev,
                  const double* sum_x_dev, const double* sum_y_dev, int D1, int D2,
                  double n_frames, double n_norm, double reg, double eps_eig, int dim,

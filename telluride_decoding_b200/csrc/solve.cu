@@ -154,6 +154,21 @@ __global__ void copy_f32(const double* in, float* out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)in[i];
 }
+// out[:, i] = Q[:, n-1-i] for i < dim (eigenvectors of the `dim` largest eigenvalues, largest first),
+// sigma[i] = sqrt(max(w[n-1-i], 0)); Q column-major [n, n], out column-major [n, dim].
+__global__ void take_top_eigvecs(const double* Q, const double* w, long long n, int dim, double* out, double* sigma) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dim) sigma[i] = sqrt(fmax(w[n - 1 - i], 0.0));
+  if (i >= n * dim) return;
+  const long long c = i / n, r = i - c * n;
+  out[i] = Q[(n - 1 - c) * n + r];
+}
+// V[:, j] /= sigma[j], column-major [rows, cols]
+__global__ void scale_cols_recip(double* V, const double* sigma, long long rows, long long cols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  V[i] /= sigma[i / rows];
+}
 // One block per column i of the column-major pair (rx [D1, dim], ry [D2, dim]): make the largest
 // |entry| of rx[:, i] positive, flipping both columns together.
 __global__ void normalise_signs(double* rx, long long D1, double* ry, long long D2) {
@@ -696,16 +711,87 @@ extern "C" int td_cca_solve(const double* Gxx, const double* Gyy, const double* 
   mean_f32<<<blocks_for(D1), 256, 0, st>>>(sum_x, n_frames, mean_x, D1);
   mean_f32<<<blocks_for(D2), 256, 0, st>>>(sum_y, n_frames, mean_y, D2);
   TD_CHECK_CUDA(cudaGetLastError());
+  const double one = 1.0, zero = 0.0;
+  int hinfo[2] = {0, 0};
+  // ---- fast path: Cholesky whitening -------------------------------------------------------------
+  // With reg > eps_eig both covariances are positive definite and the reference's pseudo-inverse
+  // square root keeps every eigenvalue (cca.py:349-360), so the canonical pairs are those of the
+  // generalised problem and any whitening gives them (up to the joint sign of a pair):
+  //   Sxx = L1 L1', Syy = L2 L2', T = L1^-1 Sxy L2^-T = U E V', rot_x = L1^-T U, rot_y = L2^-T V.
+  // The SVD comes from the eigenvectors of the smaller Gram of T; it needs sigma_dim well above the
+  // rounding floor of sigma_1^2, otherwise (or if a factorisation fails) the eigendecomposition
+  // path below runs.
+  if (reg > 10.0 * eps_eig) {
+    int lw1 = 0, lw2 = 0;
+    TD_CHECK_SOLVER(cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, D1, Sxx, D1, &lw1));
+    TD_CHECK_SOLVER(cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, D2, Syy, D2, &lw2));
+    double* pwork;
+    if ((rc = sc.get((size_t)std::max(lw1, lw2), &pwork))) return rc;
+    TD_CHECK_SOLVER(cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, D1, Sxx, D1, pwork, lw1, info));
+    TD_CHECK_SOLVER(cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, D2, Syy, D2, pwork, lw2, info + 1));
+    // column-major Sxy buffer = Sxy' [D2, D1]:  T' = L2^-1 Sxy' L1^-T
+    TD_CHECK_SOLVER(cublasDtrsm(h->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT,
+                                D2, D1, &one, Syy, D2, Sxy, D2));
+    TD_CHECK_SOLVER(cublasDtrsm(h->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+                                D2, D1, &one, Sxx, D1, Sxy, D2));
+    const bool small_is_y = D2 <= D1;                  // Gram over the smaller side
+    const int ns = small_is_y ? D2 : D1, nl = small_is_y ? D1 : D2;
+    double *C, *ws, *top_s, *top_l, *sigma;
+    if ((rc = sc.get((long long)ns * ns, &C)) || (rc = sc.get(ns, &ws)) || (rc = sc.get((long long)ns * dim, &top_s)) ||
+        (rc = sc.get((long long)nl * dim, &top_l)) || (rc = sc.get(dim, &sigma)))
+      return rc;
+    if (small_is_y)   // C = T' T'^T  [D2, D2]
+      TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, D2, D2, D1, &one, Sxy, D2, Sxy, D2, &zero, C, D2));
+    else              // C = T'^T T'  [D1, D1]
+      TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, D1, D1, D2, &one, Sxy, D2, Sxy, D2, &zero, C, D1));
+    int* info3;
+    if ((rc = sc.get(1, &info3))) return rc;
+    if ((rc = eigh(h, sc, C, ns, ws, info3))) return rc;
+    take_top_eigvecs<<<blocks_for((long long)ns * dim), 256, 0, st>>>(C, ws, ns, dim, top_s, sigma);
+    if (small_is_y)   // top_s = V (y side, [D2, dim]); U = T V / sigma = T'^T V / sigma  [D1, dim]
+      TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_T, CUBLAS_OP_N, D1, dim, D2, &one, Sxy, D2, top_s, D2, &zero, top_l, D1));
+    else              // top_s = U (x side, [D1, dim]); V = T' U / sigma  [D2, dim]
+      TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_N, D2, dim, D1, &one, Sxy, D2, top_s, D1, &zero, top_l, D2));
+    scale_cols_recip<<<blocks_for((long long)nl * dim), 256, 0, st>>>(top_l, sigma, nl, dim);
+    TD_CHECK_CUDA(cudaGetLastError());
+    double* ux = small_is_y ? top_l : top_s;           // [D1, dim]
+    double* vy = small_is_y ? top_s : top_l;           // [D2, dim]
+    std::vector<double> hs(dim);
+    int hinfo3[3] = {0, 0, 0};
+    TD_CHECK_CUDA(cudaMemcpyAsync(hinfo3, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    TD_CHECK_CUDA(cudaMemcpyAsync(hinfo3 + 2, info3, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TD_CHECK_CUDA(cudaMemcpyAsync(hs.data(), sigma, dim * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TD_CHECK_CUDA(cudaStreamSynchronize(st));
+    const bool usable = hinfo3[0] == 0 && hinfo3[1] == 0 && hinfo3[2] == 0 && hs[0] > 0.0 &&
+                        hs[dim - 1] > 1e-4 * hs[0];
+    if (usable) {
+      // rot_x = L1^-T U, rot_y = L2^-T V
+      TD_CHECK_SOLVER(cublasDtrsm(h->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+                                  D1, dim, &one, Sxx, D1, ux, D1));
+      TD_CHECK_SOLVER(cublasDtrsm(h->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+                                  D2, dim, &one, Syy, D2, vy, D2));
+      normalise_signs<<<dim, 256, 0, st>>>(ux, D1, vy, D2);
+      to_rowmajor_f32<<<blocks_for((long long)D1 * dim), 256, 0, st>>>(ux, D1, rot_x, D1, dim);
+      to_rowmajor_f32<<<blocks_for((long long)D2 * dim), 256, 0, st>>>(vy, D2, rot_y, D2, dim);
+      copy_f32<<<blocks_for(dim), 256, 0, st>>>(sigma, e_out, dim);
+      TD_CHECK_CUDA(cudaGetLastError());
+      TD_CHECK_CUDA(cudaStreamSynchronize(st));
+      return TD_OK;
+    }
+    // fall back: rebuild the covariances the factorisations overwrote
+    make_cov<<<blocks_for(n11), 256, 0, st>>>(Gxx, sum_x, sum_x, n_frames, n_norm, reg, 1, Sxx, D1, D1);
+    make_cov<<<blocks_for(n22), 256, 0, st>>>(Gyy, sum_y, sum_y, n_frames, n_norm, reg, 1, Syy, D2, D2);
+    make_cov<<<blocks_for(n12), 256, 0, st>>>(Gxy, sum_x, sum_y, n_frames, n_norm, 0.0, 0, Sxy, D1, D2);
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
   if ((rc = eigh(h, sc, Sxx, D1, w1, info))) return rc;
   if ((rc = eigh(h, sc, Syy, D2, w2, info + 1))) return rc;
-  int hinfo[2] = {0, 0};
   TD_CHECK_CUDA(cudaMemcpyAsync(hinfo, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   TD_CHECK_CUDA(cudaStreamSynchronize(st));
   if (hinfo[0] || hinfo[1]) { set_error("td_cca_solve: syevd did not converge (info %d, %d)", hinfo[0], hinfo[1]); return TD_ERR_SOLVER; }
   // K = V diag(w^-1/2) V' over eigenvalues > eps   (cca.py:349-360)
   scale_cols_inv4<<<blocks_for(n11), 256, 0, st>>>(Sxx, w1, eps_eig, D1);
   scale_cols_inv4<<<blocks_for(n22), 256, 0, st>>>(Syy, w2, eps_eig, D2);
-  const double one = 1.0, zero = 0.0;
   TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, D1, D1, D1, &one, Sxx, D1, Sxx, D1, &zero, K11, D1));
   TD_CHECK_SOLVER(cublasDgemm(h->blas, CUBLAS_OP_N, CUBLAS_OP_T, D2, D2, D2, &one, Syy, D2, Syy, D2, &zero, K22, D2));
   // Row-major Sxy [D1, D2] is column-major Sxy' [D2, D1].  T' = K22 Sxy' K11   (cca.py:361)
