@@ -227,6 +227,23 @@ def test_cca_matches_reference_fixture(golden_dir):
     cca.calculate_cca_parameters_from_dataset([1], 3)
 
 
+def test_cca_cholesky_whitening_equals_the_eigendecomposition_route(golden_dir):
+  """td_cca_solve takes Cholesky whitening when reg > 10 * eps_eig and the reference's route
+  (syevd, eps threshold, gesvd) otherwise: at reg = 0.1 an eps_eig of 0.02 drops no eigenvalue
+  (all are >= reg) but selects the second route, so both must give the same canonical pairs."""
+  g = _golden(golden_dir, 'cca_small')
+  bd = gpu_util.make_test_data(g['x'], np.ones((g['x'].shape[0], 1), np.float32), g['x2'],
+                               post_context=int(g['post1']), in2_post_context=int(g['post2']),
+                               final_batch_size=int(g['batch']))
+  stats = cca.CcaStats.from_dataset(bd.create_dataset('train'))
+  dim = int(g['dim'])
+  fast = cca.solve_cca(stats, dim, 0.1, eps_eig=1e-12)
+  slow = cca.solve_cca(stats, dim, 0.1, eps_eig=0.02)
+  for a, b in zip(fast, slow):
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-5, atol=2e-6)
+  np.testing.assert_allclose(fast[4].cpu().numpy().reshape(-1), g['e'].reshape(-1)[:dim], rtol=1e-4)
+
+
 def test_cca_seed42_structure_like_reference_test(golden_dir):
   """test/cca_test.py:80-123 construction: eigenvalue pattern and the reference's own output."""
   g = _golden(golden_dir, 'cca_seed42')
