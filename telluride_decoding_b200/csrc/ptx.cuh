@@ -84,12 +84,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.  The bound is
+// generous (~20 s of SM clocks) so that a kernel that is merely preempted or run under a tool is not
+// mistaken for a deadlock.
+constexpr long long MBAR_TIMEOUT_CLOCKS = 40000000000LL;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) {   // ~1 s at 2 GHz
+    if (clock64() - t0 > MBAR_TIMEOUT_CLOCKS) {
       printf("tdgram: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
              blockIdx.x, threadIdx.x, bar, parity);
       __trap();
@@ -272,7 +275,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   if (mbar_try_wait_cluster(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) {
+    if (clock64() - t0 > MBAR_TIMEOUT_CLOCKS) {
       printf("tdgram: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
              blockIdx.x, threadIdx.x, bar, parity);
       __trap();
