@@ -56,30 +56,25 @@ def interleave_kept_prefix(lengths, kept_total):
   Stream order: round r emits row r of every file with more than r rows, in file order
   (tf.data interleave, cycle_length = n_files, block_length = 1; brain_data.py:725-728).
   """
-  lengths = [int(n) for n in lengths]
-  kept = [0] * len(lengths)
+  lengths = np.asarray([int(n) for n in lengths], dtype=np.int64)
   remaining = int(kept_total)
-  if remaining <= 0:
-    return kept
+  if remaining <= 0 or lengths.size == 0:
+    return [0] * int(lengths.size)
   # Largest round count R such that sum_f min(n_f, R) <= kept_total.
-  lo, hi = 0, max(lengths + [0])
+  lo, hi = 0, int(lengths.max())
   while lo < hi:
     mid = (lo + hi + 1) // 2
-    if sum(min(n, mid) for n in lengths) <= remaining:
+    if int(np.minimum(lengths, mid).sum()) <= remaining:
       lo = mid
     else:
       hi = mid - 1
   full_rounds = lo
-  for f, n in enumerate(lengths):
-    kept[f] = min(n, full_rounds)
-  remaining -= sum(kept)
-  for f, n in enumerate(lengths):
-    if remaining <= 0:
-      break
-    if n > full_rounds:
-      kept[f] += 1
-      remaining -= 1
-  return kept
+  kept = np.minimum(lengths, full_rounds)
+  remaining -= int(kept.sum())
+  if remaining > 0:                       # the cut falls inside round `full_rounds`: first files in order
+    longer = np.nonzero(lengths > full_rounds)[0][:remaining]
+    kept[longer] += 1
+  return [int(k) for k in kept]
 
 
 def interleave_order(lengths):
