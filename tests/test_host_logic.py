@@ -28,6 +28,18 @@ def test_kept_prefix_matches_oracle_interleave(lengths, batch):
   np.testing.assert_array_equal(r2, ora.interleave_order(lengths)[1])
 
 
+def test_kept_prefix_every_cut_of_random_file_sets():
+  """Every cut position of 200 random file sets against the oracle's explicit stream order."""
+  import random
+  rng = random.Random(0)
+  for _ in range(200):
+    lengths = [rng.randint(0, 12) for _ in range(rng.randint(1, 7))]
+    fi, _ = ora.interleave_order(lengths)
+    for cut in range(0, len(fi) + 2):
+      want = [int(np.sum(fi[:cut] == f)) for f in range(len(lengths))]
+      assert brain_data.interleave_kept_prefix(lengths, cut) == want, (lengths, cut)
+
+
 def _dataset(files_len, pre=0, post=0, pre2=0, post2=0, offset=0, chunk=1000000, batch=10,
              mode='test', repeat=1, offset_counts=True):
   n = sum(files_len)
