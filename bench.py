@@ -1,16 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the dense decoding hot path (BASELINE.json metric: lagged-Gram frames/s + TFLOP/s).
 
-Workload (BASELINE.json configs[1]): synthetic 64-channel EEG, 1 h at 128 Hz (60 trials x 7680
-frames), 32 lags (pre 0 / post 31, D = 2048 + bias), one envelope target, ridge with a 20-lambda
-regularisation sweep (logspace(-6, 3, 20)), minibatch 768 (no frame is dropped).
+Headline workload = BASELINE.json configs[3], the configuration the north-star target is quoted on:
+synthetic 306-channel MEG, 1 h at 1 kHz (36 trials x 100 000 frames), 100 lags (pre 0 / post 99,
+D = 30 600), one envelope target, minibatch 1000 (no frame is dropped).
 
-A step = one pass of the hot path: lagged Gram (tcgen05 3xTF32) + thin products X'[y|1] +
-(N > 1: NCCL allreduce of the partial statistics) + the 20-lambda solve.  With N GPUs every rank
-holds its own hour of recording (weak scaling: N hours fitted as one model; the lambda sweep is
-split over ranks and all-gathered).
+A step = one pass of the hot path over the WHOLE recording through the public API
+(`sharding.sharded_regression_stats`): the lagged Gram X'X on tcgen05 tensor cores in 3xTF32, the
+thin products X'[y|1] in float64 and -- with N > 1 GPUs -- ONE NCCL allreduce of the partial
+statistics.  Strong scaling: the SAME recording is cut into N contiguous frame ranges
+(`sharding.shard_rows`, cuts on 32-frame tiles in the middle of trials, lag halo read from the same
+trial), so `value` = frames of the one recording / step time.
 
-  python bench.py --gpus 1 --steps 5 --warmup 3            # this framework
+Secondary legs (N = 1 only, after the headline): cfg2 (64-ch EEG x 32 lags, ridge with a 20-lambda
+sweep, checked against the CPU oracle at every lambda), evaluate / predict throughput, cfg3 (CCA),
+cfg5 (two-speaker attention decoding) and the windowed-correlation kernel's HBM roofline.
+
+  python bench.py --gpus 1 --steps 3 --warmup 3            # this framework
   python bench.py --impl reference ...                     # the reference's CPU path (oracle port)
 """
 
@@ -22,76 +28,30 @@ import sys
 import threading
 import time
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+  # The CPU arm uses every host core it can; torchrun exports OMP_NUM_THREADS=1 to its workers, which
+  # would silently halve (or worse) the baseline, so the BLAS thread count is pinned before numpy loads.
+  try:
+    _cores = len(os.sched_getaffinity(0))
+  except AttributeError:
+    _cores = os.cpu_count() or 1
+  for _k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+    os.environ[_k] = str(_cores)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
-CFG = dict(workload='cfg2: 64-ch EEG, 1 h @128 Hz (60 trials x 7680), 32 lags, ridge, 20-lambda sweep',
-           channels=64, trials=60, frames_per_trial=7680, pre=0, post=31, batch=768, n_lambda=20)
-LAMBDAS = np.logspace(-6, 3, CFG['n_lambda'])
-METRIC = 'lagged_gram_ridge_fit_frames_per_s'
-
-
-def make_host_data(seed):
-  """Synthetic z-scored EEG and an envelope that a 25-tap FIR of the EEG predicts (+ noise)."""
-  rng = np.random.default_rng(seed)
-  t = CFG['trials'] * CFG['frames_per_trial']
-  x = rng.standard_normal((t, CFG['channels']), dtype=np.float32)
-  taps = (rng.standard_normal((25, CFG['channels'])) / 40).astype(np.float32)
-  y = np.zeros((t, 1), np.float32)
-  for k in range(25):
-    y[:t - k, 0] += x[k:] @ taps[k]
-  y += 0.5 * rng.standard_normal((t, 1), dtype=np.float32)
-  return x, y
-
-
-# ----------------------------------------------------------------------------------------------
-# Reference arm / CPU baseline: the reference's algorithm (oracle port) on the host cores
-# ----------------------------------------------------------------------------------------------
-
-def cpu_reference(x, y, n_batches):
-  """Times the reference's per-minibatch path (Hankel build + x'x + x'y, brain_data.py:446-455,
-  brain_model.py:429-444) on `n_batches` minibatches and the full 20-lambda np.linalg.solve
-  (brain_model.py:447-479); returns whole-workload frames/s with the Gram time scaled up."""
-  from oracle import ref_numpy as ora
-  b, pre, post = CFG['batch'], CFG['pre'], CFG['post']
-  fpt = CFG['frames_per_trial']
-  total_batches = CFG['trials'] * fpt // b
-  n_batches = min(n_batches, total_batches)
-  sum_xtx = sum_xty = 0.0
-  sum_x = 0.0
-  done = 0
-  t0 = time.perf_counter()
-  trial = 0
-  while done < n_batches:
-    xs, ys = x[trial * fpt:(trial + 1) * fpt], y[trial * fpt:(trial + 1) * fpt]
-    design = ora.add_context(xs, pre, post)              # the reference materialises this
-    for s in range(0, fpt - b + 1, b):
-      if done >= n_batches:
-        break
-      xb = np.hstack((design[s:s + b], np.ones((b, 1), np.float32)))
-      sum_xtx = sum_xtx + np.matmul(xb.T, xb)
-      sum_x = sum_x + np.sum(xb, axis=0, keepdims=True)
-      sum_xty = sum_xty + np.matmul(xb.T, ys[s:s + b])
-      done += 1
-    trial += 1
-  t_gram = time.perf_counter() - t0
-  n = done * b
-  t0 = time.perf_counter()
-  for lam in LAMBDAS:                                    # one solve per lambda, like the reference
-    cov = sum_xtx / n
-    cov += lam * np.identity(cov.shape[0])
-    np.linalg.solve(cov, sum_xty / n)
-  t_solve = time.perf_counter() - t0
-  frames = CFG['trials'] * fpt
-  # The reference re-accumulates the Gram for EVERY lambda (regression.py:381-409).
-  t_one_pass = t_gram * total_batches / done
-  t_step = CFG['n_lambda'] * t_one_pass + t_solve
-  return dict(frames_per_s=frames / t_step, gram_pass_s=t_one_pass, solve_s=t_solve,
-              batches_timed=done, total_batches=total_batches,
-              gram_gflops=2.0 * n * 2049 ** 2 / t_gram / 1e9)
+CFG4 = dict(workload='cfg4: 306-ch MEG, 1 h @1 kHz (36 trials x 100000 frames), 100 lags (D = 30600): '
+                     'lagged Gram + thin products X\'[y|1]; the whole recording every step',
+            channels=306, trials=36, frames_per_trial=100000, pre=0, post=99, batch=1000)
+CFG2 = dict(workload='cfg2: 64-ch EEG, 1 h @128 Hz (60 trials x 7680), 32 lags, ridge, 20-lambda sweep',
+            channels=64, trials=60, frames_per_trial=7680, pre=0, post=31, batch=768, n_lambda=20)
+LAMBDAS = np.logspace(-6, 3, CFG2['n_lambda'])
+METRIC = 'lagged_gram_frames_per_s'
+SEED = 1000
 
 
 def cpu_cores():
@@ -101,31 +61,170 @@ def cpu_cores():
     return os.cpu_count()
 
 
+def use_all_cores():
+  """numpy/BLAS on every host core for the CPU legs (no-op if threadpoolctl is missing)."""
+  try:
+    import threadpoolctl
+    threadpoolctl.threadpool_limits(limits=cpu_cores())
+  except Exception:   # pylint: disable=broad-except
+    pass
+
+
+# ----------------------------------------------------------------------------------------------
+# Synthetic recordings (seeded per trial, so that a rank can make just the trials it touches)
+# ----------------------------------------------------------------------------------------------
+
+def make_trial(cfg, i, n_taps=25, n_src=8):
+  """z-scored sensor noise and an envelope that a short FIR of the first sensors predicts (+ noise)."""
+  fpt, c = cfg['frames_per_trial'], cfg['channels']
+  rng = np.random.default_rng(SEED + i)
+  x = rng.standard_normal((fpt, c), dtype=np.float32)
+  taps = (np.random.default_rng(SEED - 1).standard_normal((n_taps, n_src)) / 10).astype(np.float32)
+  y = np.zeros((fpt, 1), np.float32)
+  for k in range(n_taps):
+    y[:fpt - k, 0] += x[k:, :n_src] @ taps[k]
+  y += 0.5 * rng.standard_normal((fpt, 1), dtype=np.float32)
+  return x, y
+
+
+def fill_trials(cfg, x_out, y_out, trial_ids):
+  fpt = cfg['frames_per_trial']
+  for i in trial_ids:
+    x, y = make_trial(cfg, i)
+    x_out[i * fpt:(i + 1) * fpt] = torch_or_numpy(x, x_out)
+    y_out[i * fpt:(i + 1) * fpt] = torch_or_numpy(y, y_out)
+
+
+def torch_or_numpy(a, like):
+  if isinstance(like, np.ndarray):
+    return a
+  import torch
+  return torch.from_numpy(a)
+
+
+def make_cfg2_host_data(seed=SEED):
+  """Synthetic z-scored EEG and an envelope that a 25-tap FIR of the EEG predicts (+ noise)."""
+  rng = np.random.default_rng(seed)
+  t = CFG2['trials'] * CFG2['frames_per_trial']
+  x = rng.standard_normal((t, CFG2['channels']), dtype=np.float32)
+  taps = (rng.standard_normal((25, CFG2['channels'])) / 40).astype(np.float32)
+  y = np.zeros((t, 1), np.float32)
+  for k in range(25):
+    y[:t - k, 0] += x[k:] @ taps[k]
+  y += 0.5 * rng.standard_normal((t, 1), dtype=np.float32)
+  return x, y
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs: the reference's algorithm (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------
+
+def cpu_cfg4_minibatches(n_batches, rows, keep_gram=False):
+  """The reference's per-minibatch accumulation (lag design brain_data.py:446-455, then
+  `sum_xtx += x.T @ x`, `sum_x`, `sum_xty`, brain_model.py:429-444, float32 numpy/BLAS) on the first
+  `n_batches` minibatches of `rows` frames of trial 0 of the cfg4 recording.  Returns
+  (seconds, frames, gram or None).  Nothing is extrapolated: frames / seconds is the rate."""
+  from oracle import ref_numpy as ora
+  pre, post = CFG4['pre'], CFG4['post']
+  x, y = make_trial(CFG4, 0)
+  need = n_batches * rows + post
+  x, y = x[:need], y[:need]
+  sum_xtx = sum_xty = sum_x = 0.0
+  t0 = time.perf_counter()
+  # One trial is one file: the context is added to the whole file and then batched; building it
+  # per minibatch with the halo gives the same rows without holding 100000 x 30600 floats.
+  for b in range(n_batches):
+    lo, hi = b * rows, (b + 1) * rows
+    src = x[max(lo - pre, 0):hi + post]
+    design = ora.add_context(src, pre, post)[lo - max(lo - pre, 0):][:rows]
+    xb = np.hstack((design, np.ones((rows, 1), np.float32)))
+    sum_xtx = sum_xtx + np.matmul(xb.T, xb)
+    sum_x = sum_x + np.sum(xb, axis=0, keepdims=True)
+    sum_xty = sum_xty + np.matmul(xb.T, y[lo:hi])
+  dt = time.perf_counter() - t0
+  return dt, n_batches * rows, (sum_xtx if keep_gram else None)
+
+
+def cpu_cfg2_full_pass(x, y, batch, max_batches=None):
+  """One FULL pass of the reference's accumulation over the cfg2 recording (600 minibatches of 768,
+  or 4608 of the regression preset's 100, regression.py:434) and the 20 solves
+  (brain_model.py:447-479, float32 np.linalg.solve).  Returns times, weights [n_lambda, D+1]."""
+  from oracle import ref_numpy as ora
+  pre, post, fpt = CFG2['pre'], CFG2['post'], CFG2['frames_per_trial']
+  sum_xtx = sum_xty = 0.0
+  done = 0
+  total = CFG2['trials'] * (fpt // batch)
+  t0 = time.perf_counter()
+  for trial in range(CFG2['trials']):
+    xs, ys = x[trial * fpt:(trial + 1) * fpt], y[trial * fpt:(trial + 1) * fpt]
+    design = ora.add_context(xs, pre, post)              # the reference materialises this
+    for s in range(0, fpt - batch + 1, batch):
+      if max_batches is not None and done >= max_batches:
+        break
+      xb = np.hstack((design[s:s + batch], np.ones((batch, 1), np.float32)))
+      sum_xtx = sum_xtx + np.matmul(xb.T, xb)
+      sum_xty = sum_xty + np.matmul(xb.T, ys[s:s + batch])
+      done += 1
+  t_gram = time.perf_counter() - t0
+  n = done * batch
+  weights = []
+  t0 = time.perf_counter()
+  for lam in LAMBDAS:                                    # one solve per lambda, like the reference
+    cov = sum_xtx / n
+    cov += (lam * np.identity(cov.shape[0])).astype(cov.dtype)
+    weights.append(np.linalg.solve(cov, sum_xty / n)[:, 0])
+  t_solve = time.perf_counter() - t0
+  return dict(gram_s=t_gram, solve_s=t_solve, batches=done, total_batches=total, frames=n,
+              weights=np.stack(weights), gram_gflops=2.0 * n * 2049 ** 2 / t_gram / 1e9)
+
+
 def run_reference_arm(args, rank):
+  """`--impl reference`: the reference's CPU implementation of the headline path on the host cores.
+  One step = `--ref-batches` minibatches of `--ref-rows` frames of the cfg4 recording (a bounded
+  sample: a whole pass is 3600 minibatches, hours of CPU); value = frames of the sample / its time."""
   if rank != 0:
     return
-  x, y = make_host_data(1000)
-  per_step = 12                                    # minibatches per step: a bounded sample
+  use_all_cores()
+  rows, nb = args.ref_rows, args.ref_batches
   for _ in range(args.warmup):
-    cpu_reference(x, y, 2)
-  t0 = time.perf_counter()
-  res = None
+    cpu_cfg4_minibatches(1, min(rows, 200))
+  t_sum = 0.0
   for _ in range(args.steps):
-    res = cpu_reference(x, y, per_step)
-  dt = (time.perf_counter() - t0) / max(args.steps, 1)
-  sample = ('%d of %d minibatches of %d frames per step (Hankel build + x.T@x + x.T@y, numpy/BLAS '
-            'float32) scaled to one pass, x %d passes (the reference recomputes the Gram per lambda, '
-            'regression.py:381-409) + 20 x np.linalg.solve(2049); no tf.data overhead' %
-            (res['batches_timed'], res['total_batches'], CFG['batch'], CFG['n_lambda']))
-  line = dict(metric=METRIC, value=res['frames_per_s'], unit='frames/s', n_gpus=args.gpus,
-              steps=args.steps, warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True,
-              scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-              config=dict(CFG, parallelism='cpu'),
-              cpu_baseline=dict(value=res['frames_per_s'], unit='frames/s', cores=cpu_cores(),
-                                kind='port', sample=sample, gram_pass_s=res['gram_pass_s'],
-                                solve_s=res['solve_s'], gram_gflops=res['gram_gflops']),
-              e2e=dict(value=res['frames_per_s'], unit='frames/s', h2d_bytes_per_step=0,
-                       d2h_bytes_per_step=0))
+    dt, frames, _ = cpu_cfg4_minibatches(nb, rows)
+    t_sum += dt
+  dt = t_sum / max(args.steps, 1)
+  value = nb * rows / dt
+  d1 = CFG4['channels'] * (CFG4['pre'] + 1 + CFG4['post']) + 1
+  sample = ('%d minibatch(es) of %d frames of trial 0 per step: lag design + x.T@x + sum(x) + x.T@y over '
+            'D+1 = %d columns, numpy/BLAS float32 on %d threads; rate of the sample, nothing '
+            'extrapolated; no tf.data overhead' % (nb, rows, d1, cpu_cores()))
+  legs = {}
+  if args.legs != 'none':
+    x2, y2 = make_cfg2_host_data()
+    r = cpu_cfg2_full_pass(x2, y2, CFG2['batch'])
+    frames2 = CFG2['trials'] * CFG2['frames_per_trial']
+    legs['cfg2'] = dict(
+        workload=CFG2['workload'], measured='one full pass (600 minibatches of 768) + 20 solves',
+        gram_pass_s=r['gram_s'], solve_s=r['solve_s'], gram_gflops=r['gram_gflops'],
+        single_pass_frames_per_s=frames2 / (r['gram_s'] + r['solve_s']),
+        x_n_lambda_frames_per_s=frames2 / (CFG2['n_lambda'] * r['gram_s'] + r['solve_s']),
+        x_n_lambda_note='the reference re-accumulates the Gram for every lambda (regression.py:381-409): '
+                        '20 x the measured pass + the 20 solves (derived, not re-run)')
+    r100 = cpu_cfg2_full_pass(x2, y2, 100, max_batches=460)
+    legs['cfg2_batch100'] = dict(
+        measured='460 of 4560 minibatches of the regression preset batch 100 (regression.py:434)',
+        extrapolated=True, gram_gflops=r100['gram_gflops'],
+        single_pass_frames_per_s=frames2 / (r100['gram_s'] * r100['total_batches'] / r100['batches'] +
+                                            r100['solve_s']))
+  line = dict(metric=METRIC, value=value, unit='frames/s', n_gpus=args.gpus, steps=args.steps,
+              warmup=args.warmup, ms_per_step=dt * 1e3, higher_is_better=True, scaling='strong',
+              vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+              config=dict(CFG4, parallelism='cpu'),
+              tflops_alg=value * (d1 - 1) * d1 / 1e12,
+              cpu_baseline=dict(value=value, unit='frames/s', cores=cpu_cores(), kind='port', sample=sample,
+                                gram_gflops=2.0 * value * d1 * d1 / 1e9),
+              e2e=dict(value=value, unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+              legs=legs)
   print(json.dumps(line))
 
 
@@ -138,16 +237,17 @@ class ClockSampler(object):
            'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
            'clocks_event_reasons.sw_power_cap')
 
-  def __init__(self, index):
+  def __init__(self, index, period_ms=50):
     self.samples = []
     self.proc = None
     self.index = index
+    self.period_ms = period_ms
 
   def start(self):
     try:
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-           '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
+           '--format=csv,noheader,nounits', '-lms', str(self.period_ms)], stdout=subprocess.PIPE,
           stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
@@ -170,13 +270,13 @@ class ClockSampler(object):
       self.proc.wait(timeout=5)
     except subprocess.TimeoutExpired:
       self.proc.kill()
-    sm, mx, reasons = [], [], set()
+    sm, mx, pw, reasons = [], [], [], set()
     inside = [p for t, p in self.samples
               if windows and any(a <= t <= b + 0.03 for a, b in windows)]
     in_window = bool(inside)
     for p in (inside or [p for _, p in self.samples]):
       try:
-        sm.append(float(p[0])); mx.append(float(p[1]))
+        sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
       except ValueError:
         continue
       for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
@@ -185,29 +285,250 @@ class ClockSampler(object):
           reasons.add(name)
     return dict(sm_mhz=float(np.median(sm)) if sm else None,
                 sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                power_w_median=float(np.median(pw)) if pw else None,
                 samples=len(sm), sampled='inside the timed regions' if in_window else 'whole run')
 
 
+def load_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return dict(bf16=p.get('bf16_tflops', 1590.0), bf16_sustained=p.get('bf16_tflops_sustained', 1590.0),
+                hbm=p.get('hbm_gbs', 6500.0), source='MEASURED_PEAKS.json')
+  return dict(bf16=1590.0, bf16_sustained=1590.0, hbm=6500.0,
+              source='fallback of /opt/skills/guides/B200_PROFILING.md (1.59 PF bf16, 6.5 TB/s)')
+
+
 # ----------------------------------------------------------------------------------------------
-# This framework
+# Secondary legs (N = 1)
 # ----------------------------------------------------------------------------------------------
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one Gram launch on the bench workload (ncu --set
-# full capture, profiles/r01_ncu_gram_kernel_summary.txt): 556.7 MB + 41.2 MB.  The staged planes are
-# 4 x 118 MB and are read once (L2 hit rate 97 %), the Gram is written once.
-GRAM_DRAM_TRAFFIC_BYTES = 597866752
+def timed_ms(fn, steps, flush=None):
+  import torch
+  ev = []
+  for _ in range(steps):
+    if flush is not None:
+      flush.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = fn()
+    b.record()
+    ev.append((a, b))
+  torch.cuda.synchronize()
+  return float(np.mean([a.elapsed_time(b) for a, b in ev])), out
 
+
+def leg_cfg2(dev, peaks, flush, with_cpu):
+  """BASELINE.json configs[1]: ridge fit with a 20-lambda sweep (Gram + thin sums + batched solve),
+  resident and end to end; weights checked against the CPU oracle's full pass at EVERY lambda."""
+  import torch
+  from telluride_decoding_b200 import brain_data, brain_model, ops
+  x_host, y_host = make_cfg2_host_data()
+  x_pin = torch.from_numpy(x_host).pin_memory()
+  y_pin = torch.from_numpy(y_host).pin_memory()
+  fpt, trials = CFG2['frames_per_trial'], CFG2['trials']
+  frames = fpt * trials
+
+  def build_data(xd, yd, **kw):
+    bd = brain_data.TrialBrainData('eeg', 'envelope', 128.0, pre_context=CFG2['pre'],
+                                   post_context=CFG2['post'], final_batch_size=CFG2['batch'],
+                                   shuffle_buffer_size=0, **kw)
+    bd.set_trials(['trial_%02d' % i for i in range(trials)], [fpt] * trials, xd, yd)
+    return bd
+
+  gopt = ops.gram_options(timed=True)
+  lambdas = [float(l) for l in LAMBDAS]
+
+  def fit(dataset):
+    stats = brain_model.RegressionStats.from_dataset(dataset, gram_options=gopt)
+    g_aug, c_aug = stats.augmented(True)
+    return ops.ridge_solve(g_aug, c_aug, stats.n, lambdas, method=2)[:, :, 0]
+
+  ds_res = build_data(x_pin.to(dev), y_pin.to(dev)).create_dataset('train')
+  for _ in range(3):
+    fit(ds_res)
+  gram_ms = []
+  def fit_res():
+    w = fit(ds_res)
+    gram_ms.append(ops.last_gram_kernel_ms())
+    return w
+  step_ms, w = timed_ms(fit_res, 10, flush)
+  def e2e_step():
+    return fit(build_data(x_pin, y_pin).create_dataset('train')).cpu()
+  for _ in range(2):
+    e2e_step()
+  e2e_ms, w_host = timed_ms(e2e_step, 10, flush)
+  d = CFG2['channels'] * (CFG2['pre'] + 1 + CFG2['post'])
+  f_alg = float(frames) * d * (d + 1)
+  kernel_ms = float(np.mean(gram_ms))
+  peak = peaks['bf16'] / 6.0
+  leg = dict(workload=CFG2['workload'], ms_per_step=step_ms, frames_per_s=frames / (step_ms * 1e-3),
+             e2e_ms_per_step=e2e_ms, e2e_frames_per_s=frames / (e2e_ms * 1e-3),
+             h2d_bytes_per_step=int(x_pin.numel() * 4 + y_pin.numel() * 4),
+             d2h_bytes_per_step=int(w_host.numel() * 4), gram_kernel_ms=kernel_ms,
+             roofline=dict(bound='tensor', achieved=f_alg / (kernel_ms * 1e-3) / 1e12, peak=peak,
+                           unit='TFLOP/s', frac=f_alg / (kernel_ms * 1e-3) / 1e12 / peak,
+                           peak_source=peaks['source'] + ' bf16_tflops (burst: a ms-long kernel) / 2 / 3'),
+             lambdas='logspace(-6,3,20)', l2='256 MB write between timed steps')
+
+  # evaluate / predict throughput: the only numbers the reference publishes
+  # (doc/DecodingCodelab.md:654 ~100 k frames/s; TF2 demo notebook cell 20 ~32 k frames/s).
+  bd_eval = build_data(x_pin.to(dev), y_pin.to(dev))
+  ds_eval = bd_eval.create_dataset('test')
+  model = brain_model.BrainModelLinearRegression(ds_eval, regularization_lambda=0.1)
+  model.fit(ds_eval)
+  for _ in range(2):
+    model.evaluate(ds_eval)
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  for _ in range(5):
+    res = model.evaluate(ds_eval)
+  torch.cuda.synchronize()
+  ev_s = (time.perf_counter() - t0) / 5
+  leg['evaluate'] = dict(frames_per_s=frames / ev_s, ms=ev_s * 1e3,
+                         pearson_correlation_first=res['pearson_correlation_first'],
+                         what='BrainModelLinearRegression.evaluate: lagged forward + per-minibatch Pearson r, '
+                              'wall clock incl. the host read of the metrics',
+                         reference_published='~100 k frames/s (doc/DecodingCodelab.md:654), ~32 k frames/s '
+                                             '(TF2 demo notebook), other hardware')
+  if with_cpu:
+    use_all_cores()
+    r = cpu_cfg2_full_pass(x_host, y_host, CFG2['batch'])
+    w_gpu = w.cpu().numpy().astype(np.float64)
+    w_cpu = r['weights'].astype(np.float64)
+    w_rel = [float(np.linalg.norm(w_gpu[i] - w_cpu[i]) / np.linalg.norm(w_cpu[i]))
+             for i in range(len(lambdas))]
+    leg['parity'] = dict(w_rel_max=max(w_rel), w_rel_per_lambda=w_rel, tolerance=1e-4,
+                         against='oracle port, full float32 pass + np.linalg.solve at every lambda')
+    leg['cpu_baseline'] = dict(
+        kind='port', cores=cpu_cores(), measured='one full pass (600 minibatches of 768) + 20 solves',
+        gram_pass_s=r['gram_s'], solve_s=r['solve_s'], gram_gflops=r['gram_gflops'],
+        single_pass_frames_per_s=frames / (r['gram_s'] + r['solve_s']),
+        x_n_lambda_frames_per_s=frames / (CFG2['n_lambda'] * r['gram_s'] + r['solve_s']),
+        x_n_lambda_note='derived: 20 x the measured pass (regression.py:381-409) + the solves')
+  return leg
+
+
+def leg_windowed_corr(dev, peaks):
+  """The sliding-window correlation kernel alone on a bandwidth-sized problem (1000 trials x 76 800
+  frames x 8 correlation columns, six window shapes, global statistics): HBM GB/s against the
+  measured copy bandwidth and against the 8 TB/s north_star quotes."""
+  import torch
+  from telluride_decoding_b200 import ops
+  trials, frames, dims = 1000, 76800, 8
+  n = trials * frames
+  gen = torch.Generator(device=dev); gen.manual_seed(6)
+  a = torch.randn((n, dims), generator=gen, device=dev)
+  b = torch.randn((n, dims), generator=gen, device=dev)
+  mu = torch.zeros(dims, device=dev); pw = torch.ones(dims, device=dev)
+  widths = [1280, 2560, 6400, 12800, 25600, 38400]
+  steps_w = [w // 2 for w in widths]
+  starts = [i * frames for i in range(trials)]
+  lens = [frames] * trials
+  def run():
+    return ops.windowed_corr(a, b, starts, lens, widths, steps_w, 'global', reduction='mean',
+                             mu_a=mu, mu_b=mu, power=pw)
+  for _ in range(3):
+    run()
+  ms, (vals, _) = timed_ms(run, 10)
+  bytes_alg = 2.0 * n * dims * 4 + vals.numel() * 8
+  gbs = bytes_alg / (ms * 1e-3) / 1e9
+  del a, b
+  return dict(workload='1000 trials x 76800 frames x 8 columns, 6 window shapes (10-300 s @128 Hz), '
+                       'reduction mean; inputs 4.9 GB >> L2',
+              ms=ms, bytes_per_launch=bytes_alg,
+              roofline=dict(bound='hbm', achieved=gbs, peak=peaks['hbm'], unit='GB/s',
+                            frac=gbs / peaks['hbm'], frac_of_8tbs=gbs / 8000.0,
+                            peak_source=peaks['source'] + ' hbm_gbs',
+                            timing='CUDA events around the public op (table upload + one kernel)'))
+
+
+def leg_cfg3(dev):
+  """BASELINE.json configs[2]: BrainModelCCA, 64-ch EEG x 32 lags vs 32-band spectrogram x 16 lags,
+  8 canonical components, 1 h at 128 Hz."""
+  import torch
+  from telluride_decoding_b200 import brain_data, cca
+  rng = np.random.default_rng(SEED + 3)
+  trials, fpt = 60, 7680
+  n = trials * fpt
+  x = rng.standard_normal((n, 64), dtype=np.float32)
+  mix = (rng.standard_normal((64, 32)) / 8).astype(np.float32)
+  x2 = (x @ mix + rng.standard_normal((n, 32), dtype=np.float32)).astype(np.float32)
+  y = np.zeros((n, 1), np.float32)
+  bd = brain_data.TrialBrainData('eeg', 'envelope', 128.0, pre_context=0, post_context=31,
+                                 in2_fields='spectrogram', in2_pre_context=0, in2_post_context=15,
+                                 final_batch_size=768, shuffle_buffer_size=0)
+  bd.set_trials(['t%02d' % i for i in range(trials)], [fpt] * trials, torch.from_numpy(x).to(dev),
+                torch.from_numpy(y).to(dev), input2_data=torch.from_numpy(x2).to(dev))
+  ds = bd.create_dataset('train')
+  model = cca.BrainModelCCA(ds, cca_dims=8, regularization_lambda=0.1)
+  for _ in range(2):
+    model.fit(ds)
+  ms, _ = timed_ms(lambda: model.fit(ds), 5)
+  def stats_only():
+    return cca.CcaStats.from_dataset(ds)
+  ms_stats, _ = timed_ms(stats_only, 5)
+  res = model.evaluate(ds)
+  return dict(workload='cfg3: CCA 64 ch x 32 lags (2048) vs 32 bands x 16 lags (512), dim 8, 460800 frames',
+              fit_ms=ms, stats_ms=ms_stats, solve_ms=ms - ms_stats, frames_per_s=n / (ms * 1e-3),
+              first_canonical_r=float(res['cca_pearson_correlation_first']))
+
+
+def leg_cfg5(dev):
+  """BASELINE.json configs[4] (the correlation / decision half): 1000 trials x 60 s @128 Hz, two
+  speakers, windows of 1-30 s, winner-take-all."""
+  import torch
+  from telluride_decoding_b200 import ops
+  trials_a, frames_a = 1000, 7680
+  na = trials_a * frames_a
+  gen = torch.Generator(device=dev); gen.manual_seed(5)
+  env = torch.randn((na, 1), generator=gen, device=dev)
+  p1 = (0.3 * env + torch.randn((na, 1), generator=gen, device=dev)).contiguous()   # attended
+  p2 = torch.randn((na, 1), generator=gen, device=dev)                             # unattended
+  mu = torch.zeros(1, device=dev); pw = torch.ones(1, device=dev)
+  widths = [128, 256, 640, 1280, 2560, 3840]          # 1, 2, 5, 10, 20, 30 s windows
+  steps_w = [w // 2 for w in widths]
+  starts = [i * frames_a for i in range(trials_a)]
+  lens = [frames_a] * trials_a
+  def aad_step():
+    r1, _ = ops.windowed_corr(env, p1, starts, lens, widths, steps_w, 'global', reduction='first',
+                              mu_a=mu, mu_b=mu, power=pw)
+    r2, _ = ops.windowed_corr(env, p2, starts, lens, widths, steps_w, 'global', reduction='first',
+                              mu_a=mu, mu_b=mu, power=pw)
+    return ops.wta_decide(r1, r2)
+  for _ in range(3):
+    dec = aad_step()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  for _ in range(5):
+    dec = aad_step()
+  torch.cuda.synchronize()
+  aad_ms = (time.perf_counter() - t0) / 5 * 1e3
+  return dict(workload='cfg5 (windows + decision): 1000 trials x 7680 frames, 2 speakers, windows '
+                       '1/2/5/10/20/30 s (step W/2), global-statistics correlation, winner-take-all',
+              windows_per_s=2 * int(dec.numel()) / (aad_ms * 1e-3), decisions=int(dec.numel()),
+              ms=aad_ms, accuracy=float(dec.float().mean().item()),
+              note='wall clock of the public ops incl. host-side table building')
+
+
+# ----------------------------------------------------------------------------------------------
+# This framework: headline
+# ----------------------------------------------------------------------------------------------
 
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=5)
+  ap.add_argument('--steps', type=int, default=3)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-  ap.add_argument('--solve-method', type=int, default=2,
-                  help='2 batched blocked Cholesky sweep, 0 cuSOLVER Cholesky per lambda, 1 one eigh')
+  ap.add_argument('--legs', default='all', help='all | none | comma list of cfg2,wcorr,cfg3,cfg5,fit')
+  ap.add_argument('--e2e-steps', type=int, default=3, help='timed end-to-end steps (each a full recording)')
+  ap.add_argument('--minutes', type=float, default=60.0, help='development: shorter recording')
+  ap.add_argument('--ref-rows', type=int, default=1000, help='reference arm: frames per minibatch')
+  ap.add_argument('--ref-batches', type=int, default=1, help='reference arm: minibatches per step')
   ap.add_argument('--cta-group', type=int, default=0)
   ap.add_argument('--chunk-rows', type=int, default=0)
+  ap.add_argument('--gram-method', type=int, default=0)
   ap.add_argument('--skip-cpu-baseline', action='store_true')
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))
@@ -228,210 +549,229 @@ def main():
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
   warmup = max(args.warmup, 3)
-
-  x_host, y_host = make_host_data(1000 + rank)
-  x_pin = torch.from_numpy(x_host).pin_memory()
-  y_pin = torch.from_numpy(y_host).pin_memory()
-  fpt, trials = CFG['frames_per_trial'], CFG['trials']
+  peaks = load_peaks()
+  cfg = dict(CFG4)
+  if args.minutes != 60.0:
+    cfg['trials'] = max(1, int(round(args.minutes * 60000 / cfg['frames_per_trial'])))
+    cfg['workload'] = 'DEVELOPMENT SLICE (%g min) of ' % args.minutes + cfg['workload']
+  fpt, trials, c = cfg['frames_per_trial'], cfg['trials'], cfg['channels']
+  pre, post = cfg['pre'], cfg['post']
   frames = fpt * trials
+  d = c * (pre + 1 + post)
+  names = ['trial_%02d' % i for i in range(trials)]
+  lens = [fpt] * trials
+  starts = [i * fpt for i in range(trials)]
 
-  def build_data(xd, yd):
-    bd = brain_data.TrialBrainData('eeg', 'envelope', 128.0, pre_context=CFG['pre'],
-                                   post_context=CFG['post'], final_batch_size=CFG['batch'],
-                                   shuffle_buffer_size=0)
-    bd.set_trials(['trial_%02d' % i for i in range(trials)], [fpt] * trials, xd, yd)
-    return bd
+  # ---- this rank's share of the recording ----------------------------------------------------------
+  my_first, my_keep = sharding.shard_rows(None, lens, rank, world)
+  my_rows = sum(k - f for f, k in zip(my_first, my_keep))
+  row_lo, row_hi = sharding.needed_row_range(starts, lens, lens, pre, post, rank, world)
+  need_trials = [i for i in range(trials) if my_keep[i] > my_first[i]]
+  x_pin = torch.empty((frames, c), dtype=torch.float32, pin_memory=True)
+  y_pin = torch.empty((frames, 1), dtype=torch.float32, pin_memory=True)
+  fill_trials(cfg, x_pin, y_pin, need_trials)       # rows outside are never read (upload_rows)
 
-  gopt = ops.gram_options(cta_group=args.cta_group, chunk_rows=args.chunk_rows, timed=True)
-  my_lambdas = [float(l) for i, l in enumerate(LAMBDAS) if i % world == rank]
-  n_pad = (len(LAMBDAS) + world - 1) // world
+  def new_brain_data():
+    return brain_data.TrialBrainData('meg', 'envelope', 1000.0, pre_context=pre, post_context=post,
+                                     final_batch_size=cfg['batch'], shuffle_buffer_size=0)
 
-  def fit(dataset):
-    """The hot path: statistics -> (allreduce) -> lambda sweep.  Returns [n_lambda, D+1] weights."""
-    stats = brain_model.RegressionStats.from_dataset(dataset, gram_options=gopt)
-    if world > 1:
-      sharding.allreduce_sum_([stats.gram, stats.xtv, stats.vtv])
-    g_aug, c_aug = stats.augmented(True)
-    sol = ops.ridge_solve(g_aug, c_aug, stats.n, my_lambdas or [1.0], method=args.solve_method)
-    sol = sol[:, :, 0]
-    if world > 1:
-      pad = torch.zeros((n_pad, sol.shape[1]), dtype=sol.dtype, device=sol.device)
-      pad[:len(my_lambdas)] = sol[:len(my_lambdas)]
-      gathered = [torch.empty_like(pad) for _ in range(world)]
-      dist.all_gather(gathered, pad)
-      sol = torch.stack(gathered, dim=1).reshape(-1, sol.shape[1])[:len(LAMBDAS)]
-    return sol
-
-  # ---- resident arm: inputs already in HBM ------------------------------------------------------
-  bd_res = build_data(x_pin.to(dev), y_pin.to(dev))
-  ds_res = bd_res.create_dataset('train')
-  assert ds_res.num_batches * CFG['batch'] == frames
-  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+  gopt = ops.gram_options(method=args.gram_method, cta_group=args.cta_group,
+                          chunk_rows=args.chunk_rows, timed=True)
 
   def barrier():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
+  # ---- resident arm: the rank's frames already in HBM ----------------------------------------------
+  bd_res = new_brain_data()
+  bd_res.set_trials(names, lens, x_pin, y_pin, upload_rows=(row_lo, row_hi))
+  ds_res = bd_res.create_dataset('train')
+  assert ds_res.num_batches * cfg['batch'] == frames
+  torch.cuda.synchronize()
+
   sampler = ClockSampler(local_rank)
   if rank == 0:
-    sampler.start()                                # nvidia-smi needs ~0.2 s to deliver its first sample
+    sampler.start()
+  stats = None
   for _ in range(warmup):
-    fit(ds_res)
+    stats = None                                      # release the previous Gram before the next one
+    stats = sharding.sharded_regression_stats(ds_res, gram_options=gopt)
   barrier()
-  ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        for _ in range(args.steps)]
-  gram_ms = []
-  barrier()
-  wall0 = time.perf_counter()
+  gram_ms, ar_ms, step_ms = [], [], []
   win0 = time.time()
+  wall0 = time.perf_counter()
   for i in range(args.steps):
-    flush.zero_()                                  # evict L2 between timed iterations
+    stats = None
     if world > 1:
       dist.barrier()
-    ev[i][0].record()
-    w = fit(ds_res)
-    ev[i][1].record()
+    tm = {}
+    stats = sharding.sharded_regression_stats(ds_res, gram_options=gopt, timings=tm)
+    tm['allreduce_done'].synchronize()
+    step_ms.append(tm['start'].elapsed_time(tm['allreduce_done']))
+    ar_ms.append(tm['stats_done'].elapsed_time(tm['allreduce_done']))
     gram_ms.append(ops.last_gram_kernel_ms())
   barrier()
   wall = time.perf_counter() - wall0
   windows = [(win0, time.time())]
-  step_ms = [a.elapsed_time(b) for a, b in ev]
-  t_res = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+  t_res = torch.tensor([sum(step_ms), float(np.mean(ar_ms)), float(np.mean(gram_ms))],
+                       dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
-  ms_per_step = float(t_res.item()) / args.steps
+  ms_per_step = float(t_res[0].item()) / args.steps
+  allreduce_ms = float(t_res[1].item())
+  gram_kernel_ms_max = float(t_res[2].item())
+  n_stat = stats.n
 
-  # ---- end-to-end arm: host buffers in, weights out, copies inside the timed region -------------
+  # ---- end-to-end arm: host buffers in, fitted weights out ------------------------------------------
+  # Every step: pinned host arrays -> (this rank's rows + halo) -> device, statistics, allreduce, ONE
+  # ridge solve of the (D+1) x (D+1) system in float64 (replicated on every rank), weights -> host.
+  solve_ms = []
   def e2e_step():
-    # Host buffers straight into the public API: set_trials uploads the pinned arrays chunk by chunk
-    # on a side stream and the statistics of the first trials start while the rest is in flight.
-    ds = build_data(x_pin, y_pin).create_dataset('train')
-    return fit(ds).cpu()
-
-  for _ in range(2):
-    e2e_step()
-  barrier()
-  e2e_ev = []
-  win0 = time.time()
-  for i in range(args.steps):
-    flush.zero_()
-    if world > 1:
-      dist.barrier()
+    bd = new_brain_data()
+    bd.set_trials(names, lens, x_pin, y_pin, upload_rows=(row_lo, row_hi))
+    st = sharding.sharded_regression_stats(bd.create_dataset('train'), gram_options=gopt)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    w_host = e2e_step()
+    g_aug, c_aug = st.augmented(True)
+    del st
+    w = ops.ridge_solve(g_aug, c_aug, n_stat, [0.1], method=0)[0, :, 0]
     b.record()
-    e2e_ev.append((a, b))
-  barrier()
-  windows.append((win0, time.time()))
+    w_host = w.cpu()
+    solve_ms.append(a.elapsed_time(b))
+    return w_host
+
+  e2e = None
+  try:
+    stats_gram_check = stats.gram                   # kept for the parity check below
+    del stats
+    e2e_step()                                       # warm-up (allocator, cuSOLVER handles)
+    solve_ms.clear()
+    barrier()
+    e2e_ev = []
+    win0 = time.time()
+    for i in range(args.e2e_steps):
+      if world > 1:
+        dist.barrier()
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      w_host = e2e_step()
+      b.record()
+      e2e_ev.append((a, b))
+    barrier()
+    windows.append((win0, time.time()))
+    t_e2e = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_e2e.item()) / args.e2e_steps
+    e2e = dict(value=frames / (e2e_ms * 1e-3), unit='frames/s',
+               h2d_bytes_per_step=int((row_hi - row_lo) * (c + 1) * 4),
+               d2h_bytes_per_step=int(w_host.numel() * 4), ms_per_step=e2e_ms, steps=args.e2e_steps,
+               solve_ms=float(np.mean(solve_ms)),
+               what='TrialBrainData.set_trials(pinned host arrays, this rank\'s rows + lag halo) -> '
+                    'sharded_regression_stats -> ridge_solve(lambda 0.1, float64 Cholesky of the '
+                    '%d x %d system, replicated per rank) -> weights on the host' % (d + 1, d + 1))
+  except Exception as exc:   # pylint: disable=broad-except
+    e2e = dict(value=None, unit='frames/s', error=repr(exc)[:300])
+    stats_gram_check = None
   clocks = sampler.stop(windows) if rank == 0 else None
-  t_e2e = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_ev)], dtype=torch.float64, device=dev)
-  if world > 1:
-    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-  e2e_ms = float(t_e2e.item()) / args.steps
 
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
     return
 
-  # ---- roofline of the dominant kernel (the tcgen05 Gram) ---------------------------------------
-  d = CFG['channels'] * (CFG['pre'] + 1 + CFG['post'])
-  f_alg = float(frames) * d * (d + 1)               # symmetric-minimal flops of one launch (SURVEY 8d)
-  gram_kernel_ms = float(np.mean(gram_ms))
-  achieved = f_alg / (gram_kernel_ms * 1e-3) / 1e12
-  peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-  if os.path.exists(peaks_path):
-    peaks = json.load(open(peaks_path))
-    bf16 = peaks.get('bf16_tflops', 1590.0)
-    peak_note = 'MEASURED_PEAKS.json bf16_tflops (burst) / 2 (tf32 rate) / 3 (3xTF32)'
-  else:
-    bf16 = 1590.0
-    peak_note = 'fallback 1.59 PF bf16 / 2 / 3'
-  peak = bf16 / 2.0 / 3.0
-  # live TF32 dense rate for context (cuBLAS; denominator cross-check only)
-  torch.backends.cuda.matmul.allow_tf32 = True
-  a = torch.randn(8192, 8192, device=dev)
-  b = torch.randn(8192, 8192, device=dev)
-  best = 1e9
-  for _ in range(6):
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record(); torch.matmul(a, b); e.record(); torch.cuda.synchronize()
-    best = min(best, s.elapsed_time(e))
-  tf32_live = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
-  torch.backends.cuda.matmul.allow_tf32 = False
+  # ---- roofline of the dominant kernel (the tcgen05 Gram, rank 0's launch) --------------------------
+  rows0 = my_rows
+  f_alg = float(rows0) * d * (d + 1)                 # symmetric-minimal flops of one launch
+  kernel_ms = float(np.mean(gram_ms))
+  achieved = f_alg / (kernel_ms * 1e-3) / 1e12
+  long_step = kernel_ms > 500.0
+  peak = (peaks['bf16_sustained'] if long_step else peaks['bf16']) / 6.0
+  roofline = dict(
+      bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
+      traffic=None, kernel='ts::lagged_gram_ts_kernel', flops_per_launch=f_alg,
+      frames_per_launch=rows0, kernel_ms=kernel_ms, kernel_ms_max_over_ranks=gram_kernel_ms_max,
+      peak_source='%s bf16_tflops%s / 2 (tf32 rate) / 3 (3xTF32): the %s figure, the kernel runs for '
+                  '%.2f s' % (peaks['source'], '_sustained' if long_step else '',
+                              'sustained' if long_step else 'burst', kernel_ms * 1e-3),
+      frac_of_burst_peak=achieved / (peaks['bf16'] / 6.0),
+      frac_of_sustained_peak=achieved / (peaks['bf16_sustained'] / 6.0),
+      share_of_step=kernel_ms / ms_per_step)
 
-  cpu = None
+  # ---- parity of the bench's own numbers against the CPU oracle (untimed) + cpu_baseline ------------
+  cpu = parity = None
   if world == 1 and not args.skip_cpu_baseline:
-    r = cpu_reference(x_host, y_host, 40)
-    cpu = dict(value=r['frames_per_s'], unit='frames/s', cores=cpu_cores(), kind='port',
-               sample=('%d of %d minibatches of %d frames (Hankel build + x.T@x + x.T@y) scaled to '
-                       'one pass x %d lambda passes (regression.py:381-409) + 20 x np.linalg.solve; '
-                       'numpy/BLAS float32, no tf.data overhead' %
-                       (r['batches_timed'], r['total_batches'], CFG['batch'], CFG['n_lambda'])),
-               gram_pass_s=r['gram_pass_s'], solve_s=r['solve_s'], gram_gflops=r['gram_gflops'],
-               single_pass_frames_per_s=frames / (r['gram_pass_s'] + r['solve_s']))
+    use_all_cores()
+    rows = args.ref_rows
+    nb = 3
+    dt, nfr, g_cpu = cpu_cfg4_minibatches(nb, rows, keep_gram=True)
+    cpu = dict(value=nfr / dt, unit='frames/s', cores=cpu_cores(), kind='port',
+               sample='%d minibatches of %d frames of trial 0 (lag design + x.T@x + sum(x) + x.T@y, '
+                      'numpy/BLAS float32); rate of the sample, nothing extrapolated' % (nb, rows),
+               gram_gflops=2.0 * nfr / dt * (d + 1) ** 2 / 1e9, seconds=dt)
+    # the same rows through the kernel: design rows [0, nb*rows) of trial 0
+    sx = ds_res.stream('x')
+    keep = [nb * rows] + [0] * (trials - 1)
+    g_gpu = ops.lagged_gram([sx], keep, options=ops.gram_options(method=args.gram_method))
+    g64 = g_gpu.cpu().numpy().astype(np.float64)
+    want = g_cpu[:d, :d].astype(np.float64)
+    parity = dict(gram_rel_fro=float(np.linalg.norm(g64 - want) / np.linalg.norm(want)),
+                  rows='design rows [0, %d) of trial 0, all %d x %d entries' % (nb * rows, d, d),
+                  against='oracle port (float32 numpy accumulation)', tolerance=1e-5)
+    del g_gpu, g64, want, g_cpu
+    # lag blocks of the full-recording Gram against float64 autocorrelations of the raw frames
+    if stats_gram_check is not None:
+      xd = ds_res.stream('x').data.view(trials, fpt, c)
+      errs = []
+      for (k1, k2) in ((0, 0), (3, 50), (99, 99), (17, 18), (0, 99)):
+        want = torch.zeros((c, c), dtype=torch.float64, device=dev)
+        hi = fpt - max(k1, k2)
+        for i in range(trials):
+          want += xd[i, k1:k1 + hi].to(torch.float64).t() @ xd[i, k2:k2 + hi].to(torch.float64)
+        got = stats_gram_check[k1 * c:(k1 + 1) * c, k2 * c:(k2 + 1) * c].to(torch.float64)
+        errs.append(float(torch.linalg.norm(got - want) / torch.linalg.norm(want)))
+      parity['full_recording_lag_blocks_rel_fro_max'] = max(errs)
+      parity['full_recording_note'] = ('five 306 x 306 lag blocks of the timed step\'s Gram vs float64 '
+                                       'torch products of the raw frames (not the oracle: 3.6 M rows)')
+  stats_gram_check = None
 
-  # stage, gram, symmetrize, thin, thin-reduce + solve: scale, colmajor, build, take_y, store and per
-  # 64-column panel potf2 (factor) and one back-substitution kernel (cuBLAS GEMMs are not counted)
-  n_panels = (CFG['channels'] * (CFG['pre'] + 1 + CFG['post']) + 1 + 63) // 64
-  n_launch = 5 + 5 + 2 * n_panels
+  # stage, gram, symmetrize, thin, thin-reduce (+ memsets / library allreduce, not counted)
+  n_launch = 5
+  legs = {}
+  want = ['cfg2', 'wcorr', 'cfg3', 'cfg5'] if args.legs == 'all' else \
+         ([] if args.legs == 'none' else args.legs.split(','))
+  if world == 1 and want:
+    torch.cuda.empty_cache()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    for name, fn in (('cfg2', lambda: leg_cfg2(dev, peaks, flush, not args.skip_cpu_baseline)),
+                     ('wcorr', lambda: leg_windowed_corr(dev, peaks)),
+                     ('cfg3', lambda: leg_cfg3(dev)),
+                     ('cfg5', lambda: leg_cfg5(dev))):
+      if name in want:
+        try:
+          legs[name] = fn()
+        except Exception as exc:   # pylint: disable=broad-except
+          legs[name] = dict(error=repr(exc)[:300])
+        torch.cuda.empty_cache()
 
-  # ---- AAD leg (BASELINE.json configs[4]): sliding-window correlation + winner-take-all ----------
-  aad = None
-  if world == 1:
-    trials_a, frames_a = 1000, 7680                     # 60 s @128 Hz per trial
-    na = trials_a * frames_a
-    gen = torch.Generator(device=dev); gen.manual_seed(5)
-    env = torch.randn((na, 1), generator=gen, device=dev)
-    p1 = (0.3 * env + torch.randn((na, 1), generator=gen, device=dev)).contiguous()   # attended
-    p2 = torch.randn((na, 1), generator=gen, device=dev)                             # unattended
-    mu = torch.zeros(1, device=dev); pw = torch.ones(1, device=dev)
-    widths = [128, 256, 640, 1280, 2560, 3840]          # 1, 2, 5, 10, 20, 30 s windows
-    steps_w = [w // 2 for w in widths]
-    starts = [i * frames_a for i in range(trials_a)]
-    lens = [frames_a] * trials_a
-    def aad_step():
-      r1, _ = ops.windowed_corr(env, p1, starts, lens, widths, steps_w, 'global', reduction='first',
-                                mu_a=mu, mu_b=mu, power=pw)
-      r2, _ = ops.windowed_corr(env, p2, starts, lens, widths, steps_w, 'global', reduction='first',
-                                mu_a=mu, mu_b=mu, power=pw)
-      return ops.wta_decide(r1, r2)
-    for _ in range(3):
-      dec = aad_step()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(5):
-      dec = aad_step()
-    torch.cuda.synchronize()
-    aad_ms = (time.perf_counter() - t0) / 5 * 1e3
-    aad = dict(workload='cfg5: 1000 trials x 7680 frames, 2 speakers, windows 1/2/5/10/20/30 s (step W/2), '
-                        'global-statistics correlation, reduction first, winner-take-all',
-               windows_per_s=2 * int(dec.numel()) / (aad_ms * 1e-3), decisions=int(dec.numel()),
-               ms=aad_ms, accuracy=float(dec.float().mean().item()),
-               note='wall clock of the public ops incl. host-side table building; kernel-only numbers in profiles/')
+  par = ('single GPU' if world == 1 else
+         'one recording time-sharded x%d (sharding.shard_rows: contiguous frame ranges, cuts on 32-frame '
+         'tiles inside trials, lag halo from the same trial), 1 NCCL allreduce of the fp32 Gram + 1 of the '
+         'packed f64 thin sums' % world)
   line = dict(
-      metric=METRIC, value=world * frames / (ms_per_step * 1e-3), unit='frames/s', n_gpus=world,
+      metric=METRIC, value=frames / (ms_per_step * 1e-3), unit='frames/s', n_gpus=world,
       steps=args.steps, warmup=warmup, ms_per_step=ms_per_step, higher_is_better=True,
-      scaling='weak', vs_baseline=None, dtype='tf32x3 (fp32-equivalent), f64 solve',
+      scaling='strong', vs_baseline=None, dtype='tf32x3 (fp32-equivalent) Gram, f64 thin sums',
       data='synthetic',
-      config=dict(CFG, parallelism='frames sharded x%d, 1 allreduce' % world if world > 1 else 'single GPU',
-                  l2='256 MB write between timed steps (outside the per-step CUDA events)',
-                  solve_method=args.solve_method, lambdas='logspace(-6,3,20)'),
+      config=dict(cfg, parallelism=par, D=d,
+                  l2='inputs (%.1f GB of raw frames per rank) are far larger than the 126 MB L2; '
+                     'no flush needed' % ((row_hi - row_lo) * c * 4 / 1e9)),
       gpu_launches=n_launch * args.steps,
-      tflops_alg=world * f_alg / (ms_per_step * 1e-3) / 1e12,
-      gram_kernel_ms=gram_kernel_ms, step_wall_ms=wall / args.steps * 1e3,
-      roofline=dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s',
-                    frac=achieved / peak, traffic=GRAM_DRAM_TRAFFIC_BYTES if world == 1 else None,
-                    traffic_source='profiles/r01_ncu_gram_kernel_summary.txt (ncu --set full, same workload)',
-                    kernel='ts::lagged_gram_ts_kernel',
-                    flops_per_launch=f_alg, peak_source=peak_note, tf32_dense_live_tflops=tf32_live,
-                    frac_of_live_tf32_over_3=achieved / (tf32_live / 3.0)),
-      e2e=dict(value=world * frames / (e2e_ms * 1e-3), unit='frames/s',
-               h2d_bytes_per_step=int(x_pin.numel() * 4 + y_pin.numel() * 4),
-               d2h_bytes_per_step=int(w_host.numel() * 4), ms_per_step=e2e_ms),
-      clocks=clocks, cpu_baseline=cpu, aad=aad)
+      tflops_alg=float(frames) * d * (d + 1) / (ms_per_step * 1e-3) / 1e12,
+      gram_kernel_ms=kernel_ms, allreduce_ms=allreduce_ms if world > 1 else 0.0,
+      step_wall_ms=wall / args.steps * 1e3, rows_checked=n_stat == frames,
+      roofline=roofline, e2e=e2e, clocks=clocks, cpu_baseline=cpu, parity=parity, legs=legs)
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()

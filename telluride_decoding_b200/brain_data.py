@@ -524,7 +524,7 @@ class TrialBrainData(BrainData):
       self.features[self.attended_field] = FixedLenFeature([int(a.shape[1]),])
 
   def set_trials(self, names, lengths, input_data, output_data, input2_data=None,
-                 attention_data=None):
+                 attention_data=None, upload_rows=None):
     """All trials at once from arrays that already hold them back to back (no per-trial copies):
     trial i is rows [sum(lengths[:i]), sum(lengths[:i+1])) of every array.
 
@@ -532,7 +532,11 @@ class TrialBrainData(BrainData):
     boundaries, on a side stream; the datasets made from this object know which rows each copy
     completes, so the Gram of the first trials runs while the later ones are still on the PCIe bus.
     The host arrays must not be modified until the copies have completed (first use of a dataset
-    made from this object); this object keeps them alive."""
+    made from this object); this object keeps them alive.
+
+    upload_rows = (row_begin, row_end): time-sharded fits (sharding.needed_row_range) -- only these
+    rows of the pinned host arrays are copied, the rest of the device arrays is zero; the host
+    rows outside the range are never read."""
     self._ready = None
     pinned = (isinstance(input_data, torch.Tensor) and isinstance(output_data, torch.Tensor) and
               input_data.device.type == 'cpu' and output_data.device.type == 'cpu' and
@@ -541,8 +545,10 @@ class TrialBrainData(BrainData):
               input_data.dim() == 2 and output_data.dim() == 2 and
               input_data.is_contiguous() and output_data.is_contiguous() and
               input_data.shape[0] == output_data.shape[0] and len(lengths) > 1)
+    if upload_rows is not None and not pinned:
+      raise ValueError('upload_rows needs pinned, contiguous float32 host tensors')
     if pinned:
-      x, y = self._async_upload(input_data, output_data, lengths)
+      x, y = self._async_upload(input_data, output_data, lengths, upload_rows)
     else:
       x = _check_2d('input_data', _lib.as_device_f32(input_data))
       y = _check_2d('output_data', _lib.as_device_f32(output_data))
@@ -597,27 +603,34 @@ class TrialBrainData(BrainData):
       cuts.append(n)
     return cuts
 
-  def _async_upload(self, x_host, y_host, lengths):
+  def _async_upload(self, x_host, y_host, lengths, upload_rows=None):
     """Device copies of two pinned [frames, channels] arrays, issued chunk by chunk on a side stream;
     sets self._ready = [(row_end, event)]."""
     _lib.require_cuda()
     dev = torch.device('cuda', torch.cuda.current_device())
-    x = torch.empty(x_host.shape, dtype=torch.float32, device=dev)
-    y = torch.empty(y_host.shape, dtype=torch.float32, device=dev)
+    alloc = torch.empty if upload_rows is None else torch.zeros
+    x = alloc(x_host.shape, dtype=torch.float32, device=dev)
+    y = alloc(y_host.shape, dtype=torch.float32, device=dev)
     side = TrialBrainData._copy_streams.get(dev.index)
     if side is None:
       side = TrialBrainData._copy_streams[dev.index] = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream())        # the buffers may be recycled memory
     cuts = self.upload_cuts(lengths)
-    ready, r0 = [], 0
+    n = int(x_host.shape[0])
+    lo, hi = (0, n) if upload_rows is None else (max(int(upload_rows[0]), 0), min(int(upload_rows[1]), n))
+    ready, r0 = [], lo
     with torch.cuda.stream(side):
-      for r1 in cuts:
-        x[r0:r1].copy_(x_host[r0:r1], non_blocking=True)
-        y[r0:r1].copy_(y_host[r0:r1], non_blocking=True)
+      for cut in cuts:
+        r1 = min(max(cut, lo), hi) if cut != cuts[-1] else hi
+        if r1 > r0:
+          x[r0:r1].copy_(x_host[r0:r1], non_blocking=True)
+          y[r0:r1].copy_(y_host[r0:r1], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(side)
-        ready.append((r1, ev))
-        r0 = r1
+        # Rows before `lo` and after `hi` are zeros that no design row of this rank reads: the last
+        # chunk's event covers everything up to the end of the arrays.
+        ready.append((cut if cut != cuts[-1] else n, ev))
+        r0 = max(r0, r1)
     x.record_stream(side)
     y.record_stream(side)
     self._ready = ready

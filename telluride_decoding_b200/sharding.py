@@ -78,16 +78,42 @@ def allreduce_sum_(tensors, group=None):
   return tensors
 
 
-def sharded_regression_stats(dataset, gram_options=None, workspace=None, group=None):
+def needed_row_range(seg_start, seg_len, seg_rows, pre, post, rank, world):
+  """(row_begin, row_end) of a raw [frames, channels] array that `rank` touches: its share of the
+  design rows (shard_rows over `seg_rows` kept rows per segment) plus the lag halo -- `pre` / `post`
+  frames of the SAME segment on either side (brain_data.py:448-455 pads with zeros only at trial /
+  chunk edges).  A rank whose share is empty gets (0, 0)."""
+  first, keep = shard_rows(None, seg_rows, rank, world)
+  lo, hi = None, 0
+  for st, ln, f, k in zip(seg_start, seg_len, first, keep):
+    if k <= f:
+      continue
+    a = int(st) + max(f - int(pre), 0)
+    b = int(st) + min(k + int(post), int(ln))
+    lo = a if lo is None else min(lo, a)
+    hi = max(hi, b)
+  return (0, 0) if lo is None else (lo, hi)
+
+
+def sharded_regression_stats(dataset, gram_options=None, workspace=None, group=None, timings=None):
   """RegressionStats of the whole dataset, each rank accumulating its share of the frames.
 
   All ranks hold the same dataset description (the raw frames only need to be valid for the
-  rank's own rows plus the lag halo)."""
+  rank's own rows plus the lag halo, see needed_row_range).  `timings`, if a dict, receives CUDA
+  events 'start', 'stats_done', 'allreduce_done' recorded on the current stream."""
   from telluride_decoding_b200 import brain_model
   from telluride_decoding_b200 import ops
   rank = dist.get_rank(group) if is_distributed() else 0
   world = dist.get_world_size(group) if is_distributed() else 1
+
+  def mark(name):
+    if timings is not None:
+      ev = torch.cuda.Event(enable_timing=True)
+      ev.record()
+      timings[name] = ev
+
   x, y = dataset.stream('x'), dataset.stream('y')
+  mark('start')
   gram = xtv = vtv = None
   for weight, keep in dataset.passes():
     first, mine = shard_rows(None, keep, rank, world)
@@ -99,5 +125,7 @@ def sharded_regression_stats(dataset, gram_options=None, workspace=None, group=N
     else:
       gram = gram + g * weight
       xtv, vtv = xtv + t * weight, vtv + v * weight
+  mark('stats_done')
   allreduce_sum_([gram, xtv, vtv], group=group)
+  mark('allreduce_done')
   return brain_model.RegressionStats(gram, xtv, vtv)

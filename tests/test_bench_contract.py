@@ -13,7 +13,7 @@ def _run(extra_env=None):
   env.update(extra_env or {})
   env.setdefault('OMP_NUM_THREADS', '4')
   out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
-                        '--warmup', '0', '--gpus', '1'], capture_output=True, text=True, env=env, timeout=600)
+                        '--warmup', '0', '--gpus', '1', '--ref-rows', '64', '--legs', 'none'], capture_output=True, text=True, env=env, timeout=600)
   assert out.returncode == 0, out.stderr[-2000:]
   return out.stdout.strip()
 

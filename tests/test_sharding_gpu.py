@@ -1,0 +1,123 @@
+"""GPU parity of the time-sharded path: every rank's tcgen05 Gram over its own row ranges
+(`seg_first`/`seg_keep` cut MID-TRIAL by sharding.shard_rows), summed over ranks, equals the oracle's
+X'X and the unsharded kernel.  Reference semantics: the zero padding of brain_data.py:448-455 exists
+only at file / chunk edges, never at a rank cut -- a rank reads the lag halo from the neighbouring
+frames of the same trial."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_numpy as ora
+from telluride_decoding_b200 import ops
+from telluride_decoding_b200 import sharding
+from tests import gpu_util
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _trials(seed, lens, c, c2=None):
+  rng = np.random.RandomState(seed)
+  x = (rng.randn(sum(lens), c) + 0.15).astype(np.float32)
+  x2 = rng.randn(sum(lens), c2).astype(np.float32) if c2 else None
+  y = rng.randn(sum(lens), 1).astype(np.float32)
+  starts = np.concatenate(([0], np.cumsum(lens)[:-1])).tolist()
+  return x, x2, y, starts
+
+
+def _oracle_design(x, starts, lens, keep, pre, post):
+  """float64 lagged rows [0, keep) of every trial, built by the oracle's add_context per trial."""
+  parts = [ora.add_context(x[s:s + n], pre, post)[:k].astype(np.float64)
+           for s, n, k in zip(starts, lens, keep)]
+  return np.concatenate(parts, axis=0)
+
+
+@pytest.mark.parametrize('world', [2, 3, 8])
+@pytest.mark.parametrize('cta_group', [1, 2])
+def test_sharded_gram_sums_to_the_oracle_gram(world, cta_group):
+  """pre > 0 and post > 0, ragged kept rows, cuts in the middle of trials."""
+  lens = [5000, 3333, 7001, 1200]
+  keep = [5000, 3300, 6900, 1200]
+  c, pre, post = 24, 5, 17                                   # D = 552
+  x, _, y, starts = _trials(31 + world, lens, c)
+  xd, yd = torch.as_tensor(x, device='cuda'), torch.as_tensor(y, device='cuda')
+  sx = ops.Stream(xd, pre, post, starts, lens)
+  sy = ops.Stream(yd, 0, 0, starts, lens)
+  opt = ops.gram_options(cta_group=cta_group)
+  whole = ops.lagged_gram([sx], keep, options=opt).double()
+  t_whole, v_whole = ops.lagged_thin(sx, sy, keep)
+  total = torch.zeros_like(whole)
+  t_sum, v_sum = torch.zeros_like(t_whole), torch.zeros_like(v_whole)
+  mid_trial_cuts = 0
+  for rank in range(world):
+    first, mine = sharding.shard_rows(None, keep, rank, world)
+    mid_trial_cuts += sum(1 for f, k in zip(first, keep) if 0 < f < k)
+    total += ops.lagged_gram([sx], mine, options=opt, seg_first=first).double()
+    t, v = ops.lagged_thin(sx, sy, mine, seg_first=first)
+    t_sum += t
+    v_sum += v
+  assert mid_trial_cuts >= world - 1 - (len(lens) - 1)       # the plan really cuts inside trials
+  design = _oracle_design(x, starts, lens, keep, pre, post)
+  want = design.T @ design
+  assert gpu_util.rel_fro(total.cpu().numpy(), want) < 1e-5
+  assert gpu_util.rel_fro(total.cpu().numpy(), whole.cpu().numpy()) < 5e-6
+  ycat = np.concatenate([y[s:s + k] for s, k in zip(starts, keep)]).astype(np.float64)
+  v = np.concatenate([ycat, np.ones_like(ycat)], axis=1)
+  np.testing.assert_allclose(t_sum.cpu().numpy(), design.T @ v, rtol=1e-5, atol=1e-4)
+  np.testing.assert_allclose(v_sum.cpu().numpy(), v.T @ v, rtol=1e-6)
+  np.testing.assert_allclose(t_sum.cpu().numpy(), t_whole.cpu().numpy(), rtol=1e-9, atol=1e-7)
+
+
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_sharded_two_stream_gram(world):
+  """Z = [X | X2] with different contexts per stream on the CTA-pair kernel, rows cut mid-trial."""
+  lens = [4100, 2900, 6000]
+  keep = [4100, 2800, 5990]
+  x, x2, _, starts = _trials(77, lens, 40, 6)
+  xd, x2d = torch.as_tensor(x, device='cuda'), torch.as_tensor(x2, device='cuda')
+  sx = ops.Stream(xd, 3, 22, starts, lens)                    # 26 lags x 40 = 1040 columns
+  s2 = ops.Stream(x2d, 2, 5, starts, lens)                    # 8 lags x 6 = 48 columns
+  whole = ops.lagged_gram([sx, s2], keep).double()
+  total = torch.zeros_like(whole)
+  for rank in range(world):
+    first, mine = sharding.shard_rows(None, keep, rank, world)
+    total += ops.lagged_gram([sx, s2], mine, seg_first=first).double()
+  z = np.concatenate([_oracle_design(x, starts, lens, keep, 3, 22),
+                      _oracle_design(x2, starts, lens, keep, 2, 5)], axis=1)
+  assert gpu_util.rel_fro(total.cpu().numpy(), z.T @ z) < 1e-5
+  assert gpu_util.rel_fro(total.cpu().numpy(), whole.cpu().numpy()) < 5e-6
+
+
+def test_shard_with_nonzero_first_rows_and_unaligned_cut():
+  """A shard of a shard: seg_first > 0 to begin with, cuts NOT on k-tile boundaries (align=1)."""
+  lens = [3000, 2000]
+  first0, keep = [37, 0], [2950, 1999]
+  x, _, _, starts = _trials(5, lens, 16)
+  sx = ops.Stream(torch.as_tensor(x, device='cuda'), 2, 9, starts, lens)
+  total = None
+  for rank in range(3):
+    first, mine = sharding.shard_rows(first0, keep, rank, 3, align=1)
+    g = ops.lagged_gram([sx], mine, seg_first=first, options=ops.gram_options(cta_group=2)).double()
+    total = g if total is None else total + g
+  parts = [ora.add_context(x[s:s + n], 2, 9)[f:k].astype(np.float64)
+           for s, n, f, k in zip(starts, lens, first0, keep)]
+  design = np.concatenate(parts, axis=0)
+  assert gpu_util.rel_fro(total.cpu().numpy(), design.T @ design) < 1e-5
+
+
+def test_two_process_nccl_sharded_statistics():
+  """Two ranks over NCCL (tools/dist_check.py under torchrun): sharded statistics + allreduce equal
+  the single-GPU statistics and weights.  Skips on a box with one GPU."""
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+         '--master-addr', '127.0.0.1', '--master-port', '29731',
+         os.path.join(ROOT, 'tools', 'dist_check.py')]
+  res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+  assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+  assert res.stdout.count('OK') == 2
