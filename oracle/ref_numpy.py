@@ -217,12 +217,17 @@ def sufficient_stats(batches, with_input2=False):
 # ----------------------------------------------------------------------------
 
 def cca_from_batches(batches, dim, regularization=0.1, mini_batch_count=1000,
-                     eps_eig=1e-12):
+                     eps_eig=1e-12, dtype=None):
   """cca.py:311-332 streams x'x, y'y, x'y and column sums over input_1 / input_2;
   :337-343 normalises by (n_batches * last_batch_rows - 1), subtracts the mean outer
   product WITHOUT rescaling it and adds reg*I to the two auto-covariances;
   :345-366 whitens through a general eig, SVDs the whitened cross-covariance and
   returns the first `dim` directions.
+
+  dtype=np.float64 is the FLOAT64 TWIN: the same steps on inputs promoted to
+  float64.  The reference runs them in the float32 of its inputs, and a float32 general `eig`
+  + SVD leaves ~1e-4 of rounding in the rotations; the twin says how far the reference's own
+  output is from the exact answer of its algorithm.
   """
   if regularization < 0.0:
     raise ValueError('regularization lambda must be >= 0')
@@ -232,8 +237,8 @@ def cca_from_batches(batches, dim, regularization=0.1, mini_batch_count=1000,
   frames = 0
   rows = 0
   for xd, _ in (batches if not mini_batch_count else batches[:mini_batch_count]):
-    x = np.asarray(xd['input_1'])
-    y = np.asarray(xd['input_2'])
+    x = np.asarray(xd['input_1'], dtype=dtype)
+    y = np.asarray(xd['input_2'], dtype=dtype)
     if x.shape[1] == 0:
       raise ValueError('First input to CCA estimator must have more than 0 columns.')
     if y.shape[1] == 0:

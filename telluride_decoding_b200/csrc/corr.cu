@@ -21,13 +21,34 @@ namespace {
 
 constexpr int MAX_SIZES = 16;
 constexpr int CORR_THREADS = 256;
-constexpr int MAX_PARTIALS = 24576;      // doubles of shared memory per block (192 KiB)
 
 struct WinSpec {
   int n_sizes;
   long long W[MAX_SIZES];
   long long S[MAX_SIZES];
   long long g;
+};
+
+// Stream-ordered device buffers freed on every exit path.
+struct DevBufs {
+  std::vector<void*> ptrs;
+  cudaStream_t st;
+  explicit DevBufs(cudaStream_t s) : st(s) {}
+  ~DevBufs() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+  template <typename T>
+  int put(const std::vector<T>& host, T** dev) {
+    int rc = upload(host, dev, st);
+    if (rc == TD_OK) ptrs.push_back(*dev);
+    return rc;
+  }
+  template <typename T>
+  int alloc(size_t n, T** dev) {
+    int rc = ensure_mempool_config();
+    if (rc) return rc;
+    TD_CHECK_CUDA(cudaMallocAsync((void**)dev, n * sizeof(T), st));
+    ptrs.push_back(*dev);
+    return TD_OK;
+  }
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -116,72 +137,130 @@ __device__ __forceinline__ double frame_signal_regs(const float (&a)[DIMS], cons
   return (double)(s / (float)DIMS);
 }
 
-// Phase-1 fast path: rows of DIMS floats (DIMS % 4 == 0) fetched with 16-byte loads.
+// ---------------------------------------------------------------------------------------------
+// Phase 1: per-chunk partial sums (g = gcd of all widths and steps frames per chunk), written to
+// global memory: part[(chunk_base[seg] + ch) * ncol + col], float64.
+//   ncol: mode 0/1: 1 (the reduced signal)   mode 3: dims   mode 2: 5*dims (a, b, aa, bb, ab)
+// A block handles CHUNKS_PER_BLOCK consecutive chunks of ONE segment (table blk_seg / blk_ch0):
+// with g >= 32 one warp per chunk (coalesced 16-byte loads, two frames in flight per lane, float32
+// per-frame arithmetic in the reference's order, float64 carry, shuffle reduction); with g < 32 one
+// thread per chunk.  Partials are tiny next to the signals (8 bytes per g frames and column).
+// ---------------------------------------------------------------------------------------------
+struct CorrArgs {
+  const float* a; long long lda_a;
+  const float* b; long long ldb;
+  int dims, mode, reduction, ncol;
+  const long long* seg_start;
+  const long long* seg_len;
+  const long long* chunk_base;
+  const int* blk_seg;
+  const long long* blk_ch0;
+  int chunks_per_block;
+  long long g;
+  const float* mu_a; const float* mu_b; const float* power; const double* lda;
+  double* part;
+};
+
+// Rows of DIMS floats (DIMS % 4 == 0), 16-byte loads, two frames per lane in flight.
 template <int DIMS>
-__device__ __forceinline__ void chunk_sums_vec(const float* A, long long lda_a, const float* B,
-                                               long long ldb, long long nchunk, long long g, int mode,
-                                               int reduction, const float* mu_a, const float* mu_b,
-                                               const float* power, const double* lda, double* part,
-                                               int warp, int lane, int nwarp) {
-  for (long long ch = warp; ch < nchunk; ch += nwarp) {
-    double s = 0.0;
-    double sd[DIMS];
+__device__ __forceinline__ void chunk_vec_rows(const CorrArgs& P, const float* A, const float* B,
+                                               long long ch, const float* mu_a, const float* mu_b,
+                                               const float* power, const double* lda, double* out,
+                                               int lane) {
+  const long long g = P.g;
+  double s = 0.0;
+  double sd[DIMS];
 #pragma unroll
-    for (int d = 0; d < DIMS; ++d) sd[d] = 0.0;
-    for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32) {
-      float av[DIMS], bv[DIMS];
-      const float4* pa = reinterpret_cast<const float4*>(A + t * lda_a);
-      const float4* pb = reinterpret_cast<const float4*>(B + t * ldb);
+  for (int d = 0; d < DIMS; ++d) sd[d] = 0.0;
+  const long long t_end = (ch + 1) * g;
+  for (long long t = ch * g + lane; t < t_end; t += 64) {
+    float av[2][DIMS], bv[2][DIMS];
+    const bool second = t + 32 < t_end;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long tt = (u == 0 || second) ? t + 32 * u : t;
+      const float4* pa = reinterpret_cast<const float4*>(A + tt * P.lda_a);
+      const float4* pb = reinterpret_cast<const float4*>(B + tt * P.ldb);
 #pragma unroll
       for (int v = 0; v < DIMS / 4; ++v) {
         const float4 x = __ldg(pa + v), y = __ldg(pb + v);
-        av[4 * v] = x.x; av[4 * v + 1] = x.y; av[4 * v + 2] = x.z; av[4 * v + 3] = x.w;
-        bv[4 * v] = y.x; bv[4 * v + 1] = y.y; bv[4 * v + 2] = y.z; bv[4 * v + 3] = y.w;
+        av[u][4 * v] = x.x; av[u][4 * v + 1] = x.y; av[u][4 * v + 2] = x.z; av[u][4 * v + 3] = x.w;
+        bv[u][4 * v] = y.x; bv[u][4 * v + 1] = y.y; bv[u][4 * v + 2] = y.z; bv[u][4 * v + 3] = y.w;
       }
-      if (mode == 1) {
-        s += frame_signal_regs<DIMS>(av, bv, reduction, mu_a, mu_b, power, lda);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !second) break;
+      if (P.mode == 1) {
+        s += frame_signal_regs<DIMS>(av[u], bv[u], P.reduction, mu_a, mu_b, power, lda);
       } else {
 #pragma unroll
         for (int d = 0; d < DIMS; ++d)
-          sd[d] += (double)(((av[d] - mu_a[d]) * (bv[d] - mu_b[d])) / power[d]);
+          sd[d] += (double)(((av[u][d] - mu_a[d]) * (bv[u][d] - mu_b[d])) / power[d]);
       }
     }
-    if (mode == 1) {
-      s = warp_sum(s);
-      if (lane == 0) part[ch] = s;
-    } else {
+  }
+  if (P.mode == 1) {
+    s = warp_sum(s);
+    if (lane == 0) out[0] = s;
+  } else {
 #pragma unroll
-      for (int d = 0; d < DIMS; ++d) {
-        const double v = warp_sum(sd[d]);
-        if (lane == 0) part[ch * DIMS + d] = v;
-      }
+    for (int d = 0; d < DIMS; ++d) {
+      const double v = warp_sum(sd[d]);
+      if (lane == 0) out[d] = v;
     }
   }
 }
 
-// One block per segment.  ncol partial columns per g-frame chunk:
-//   mode 0/1: 1 (the reduced signal)     mode 2: 5*dims (a, b, aa, bb, ab per column)
+// One correlation column, contiguous samples (lda == ldb == 1): four frames per 16-byte load,
+// two loads per lane in flight.  mode 1, reduction 'first'.
+__device__ __forceinline__ void chunk_vec_scalar(const CorrArgs& P, const float* A, const float* B,
+                                                 long long ch, float mu_a, float mu_b, float power,
+                                                 double* out, int lane) {
+  const long long g = P.g;
+  const float4* pa = reinterpret_cast<const float4*>(A + ch * g);
+  const float4* pb = reinterpret_cast<const float4*>(B + ch * g);
+  const long long nv = g >> 2;
+  double s = 0.0;
+  for (long long i = lane; i < nv; i += 64) {
+    const bool second = i + 32 < nv;
+    const float4 x0 = __ldg(pa + i), y0 = __ldg(pb + i);
+    const float4 x1 = __ldg(pa + (second ? i + 32 : i)), y1 = __ldg(pb + (second ? i + 32 : i));
+    // float32 per frame in the reference's order; the four frames are carried in float64 one by one
+    s += (double)(((x0.x - mu_a) * (y0.x - mu_b)) / power);
+    s += (double)(((x0.y - mu_a) * (y0.y - mu_b)) / power);
+    s += (double)(((x0.z - mu_a) * (y0.z - mu_b)) / power);
+    s += (double)(((x0.w - mu_a) * (y0.w - mu_b)) / power);
+    if (second) {
+      s += (double)(((x1.x - mu_a) * (y1.x - mu_b)) / power);
+      s += (double)(((x1.y - mu_a) * (y1.y - mu_b)) / power);
+      s += (double)(((x1.z - mu_a) * (y1.z - mu_b)) / power);
+      s += (double)(((x1.w - mu_a) * (y1.w - mu_b)) / power);
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[0] = s;
+}
+
 __global__ void __launch_bounds__(CORR_THREADS)
-windowed_corr_kernel(const float* __restrict__ a, long long lda_a, const float* __restrict__ b,
-                     long long ldb, int dims, const long long* __restrict__ seg_start,
-                     const long long* __restrict__ seg_len, WinSpec ws, int mode, int reduction,
-                     const float* __restrict__ mu_a, const float* __restrict__ mu_b,
-                     const float* __restrict__ power, const double* __restrict__ lda,
-                     const long long* __restrict__ win_base, int n_seg, double* __restrict__ out,
-                     int out_cols) {
-  extern __shared__ double part[];
-  const int seg = blockIdx.x;
-  const long long n = seg_len[seg];
-  const long long g = ws.g;
+corr_partials_kernel(const CorrArgs P) {
+  const int seg = P.blk_seg[blockIdx.x];
+  const long long ch0 = P.blk_ch0[blockIdx.x];
+  const long long n = P.seg_len[seg];
+  const long long g = P.g;
   const long long nchunk = n / g;
-  const int ncol = (mode == 2) ? 5 * dims : (mode == 3 ? dims : 1);
-  const float* A = a + seg_start[seg] * lda_a;
-  const float* B = b ? b + seg_start[seg] * ldb : nullptr;
+  const long long ch1 = min(nchunk, ch0 + (long long)P.chunks_per_block);
+  const int dims = P.dims, mode = P.mode, reduction = P.reduction, ncol = P.ncol;
+  const float* A = P.a + P.seg_start[seg] * P.lda_a;
+  const float* B = P.b ? P.b + P.seg_start[seg] * P.ldb : nullptr;
+  double* part = P.part + P.chunk_base[seg] * ncol;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
 
   // Global statistics (and LDA axis) staged once per block.
   __shared__ float s_mu_a[128], s_mu_b[128], s_power[128];
   __shared__ double s_lda[130];
+  const float *mu_a = P.mu_a, *mu_b = P.mu_b, *power = P.power;
+  const double* lda = P.lda;
   if (mode == 1 || mode == 3) {
     for (int d = threadIdx.x; d < dims; d += blockDim.x) {
       s_mu_a[d] = mu_a[d]; s_mu_b[d] = mu_b[d]; s_power[d] = power[d];
@@ -192,20 +271,28 @@ windowed_corr_kernel(const float* __restrict__ a, long long lda_a, const float* 
     if (lda) lda = s_lda;
   }
 
-  // ---- phase 1: partial sums per chunk ------------------------------------------------------
-  const bool vec_ok = (mode == 1 || mode == 3) && g >= 32 && (dims == 4 || dims == 8 || dims == 16) &&
-                      (lda_a % 4 == 0) && (ldb % 4 == 0) &&
-                      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0);
-  if (vec_ok) {
-    if (dims == 4) chunk_sums_vec<4>(A, lda_a, B, ldb, nchunk, g, mode, reduction, mu_a, mu_b, power, lda, part, warp, lane, nwarp);
-    else if (dims == 8) chunk_sums_vec<8>(A, lda_a, B, ldb, nchunk, g, mode, reduction, mu_a, mu_b, power, lda, part, warp, lane, nwarp);
-    else chunk_sums_vec<16>(A, lda_a, B, ldb, nchunk, g, mode, reduction, mu_a, mu_b, power, lda, part, warp, lane, nwarp);
+  const bool rows_vec = (mode == 1 || mode == 3) && g >= 32 && (dims == 4 || dims == 8 || dims == 16) &&
+                        (P.lda_a % 4 == 0) && (P.ldb % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0);
+  const bool scalar_vec = mode == 1 && reduction == 0 && dims == 1 && g >= 128 && (g % 4 == 0) &&
+                          P.lda_a == 1 && P.ldb == 1 &&
+                          ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0);
+  if (rows_vec) {
+    for (long long ch = ch0 + warp; ch < ch1; ch += nwarp) {
+      double* o = part + ch * ncol;
+      if (dims == 4) chunk_vec_rows<4>(P, A, B, ch, mu_a, mu_b, power, lda, o, lane);
+      else if (dims == 8) chunk_vec_rows<8>(P, A, B, ch, mu_a, mu_b, power, lda, o, lane);
+      else chunk_vec_rows<16>(P, A, B, ch, mu_a, mu_b, power, lda, o, lane);
+    }
+  } else if (scalar_vec) {
+    for (long long ch = ch0 + warp; ch < ch1; ch += nwarp)
+      chunk_vec_scalar(P, A, B, ch, mu_a[0], mu_b[0], power[0], part + ch, lane);
   } else if (g >= 32) {
-    for (long long ch = warp; ch < nchunk; ch += nwarp) {
+    for (long long ch = ch0 + warp; ch < ch1; ch += nwarp) {
       if (mode < 2) {
         double s = 0.0;
         for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32)
-          s += frame_signal(A + t * lda_a, B ? B + t * ldb : nullptr, dims, mode, reduction,
+          s += frame_signal(A + t * P.lda_a, B ? B + t * P.ldb : nullptr, dims, mode, reduction,
                             mu_a, mu_b, power, lda);
         s = warp_sum(s);
         if (lane == 0) part[ch] = s;
@@ -213,7 +300,7 @@ windowed_corr_kernel(const float* __restrict__ a, long long lda_a, const float* 
         for (int d = 0; d < dims; ++d) {
           double s = 0.0;
           for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32)
-            s += (double)(((A[t * lda_a + d] - mu_a[d]) * (B[t * ldb + d] - mu_b[d])) / power[d]);
+            s += (double)(((A[t * P.lda_a + d] - mu_a[d]) * (B[t * P.ldb + d] - mu_b[d])) / power[d]);
           s = warp_sum(s);
           if (lane == 0) part[ch * ncol + d] = s;
         }
@@ -221,7 +308,7 @@ windowed_corr_kernel(const float* __restrict__ a, long long lda_a, const float* 
         for (int d = 0; d < dims; ++d) {
           double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
           for (long long t = ch * g + lane; t < (ch + 1) * g; t += 32) {
-            const double x = (double)A[t * lda_a + d], y = (double)B[t * ldb + d];
+            const double x = (double)A[t * P.lda_a + d], y = (double)B[t * P.ldb + d];
             sa += x; sb += y; saa += x * x; sbb += y * y; sab += x * y;
           }
           sa = warp_sum(sa); sb = warp_sum(sb); saa = warp_sum(saa); sbb = warp_sum(sbb);
@@ -234,25 +321,25 @@ windowed_corr_kernel(const float* __restrict__ a, long long lda_a, const float* 
       }
     }
   } else {
-    for (long long ch = threadIdx.x; ch < nchunk; ch += blockDim.x) {
+    for (long long ch = ch0 + threadIdx.x; ch < ch1; ch += blockDim.x) {
       if (mode < 2) {
         double s = 0.0;
         for (long long t = ch * g; t < (ch + 1) * g; ++t)
-          s += frame_signal(A + t * lda_a, B ? B + t * ldb : nullptr, dims, mode, reduction,
+          s += frame_signal(A + t * P.lda_a, B ? B + t * P.ldb : nullptr, dims, mode, reduction,
                             mu_a, mu_b, power, lda);
         part[ch] = s;
       } else if (mode == 3) {
         for (int d = 0; d < dims; ++d) {
           double s = 0.0;
           for (long long t = ch * g; t < (ch + 1) * g; ++t)
-            s += (double)(((A[t * lda_a + d] - mu_a[d]) * (B[t * ldb + d] - mu_b[d])) / power[d]);
+            s += (double)(((A[t * P.lda_a + d] - mu_a[d]) * (B[t * P.ldb + d] - mu_b[d])) / power[d]);
           part[ch * ncol + d] = s;
         }
       } else {
         for (int d = 0; d < dims; ++d) {
           double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
           for (long long t = ch * g; t < (ch + 1) * g; ++t) {
-            const double x = (double)A[t * lda_a + d], y = (double)B[t * ldb + d];
+            const double x = (double)A[t * P.lda_a + d], y = (double)B[t * P.ldb + d];
             sa += x; sb += y; saa += x * x; sbb += y * y; sab += x * y;
           }
           double* p = part + ch * ncol + 5 * d;
@@ -261,65 +348,91 @@ windowed_corr_kernel(const float* __restrict__ a, long long lda_a, const float* 
       }
     }
   }
-  __syncthreads();
+}
 
-  // ---- phase 2: every window of every shape ---------------------------------------------------
-  for (int j = 0; j < ws.n_sizes; ++j) {
-    const long long W = ws.W[j], S = ws.S[j];
-    if (n < W) continue;
-    const long long nwin = (n - W) / S + 1;
-    const long long cw = W / g, cs = S / g;
-    const long long base = win_base[(long long)j * n_seg + seg];
-    if (mode < 2) {
-      for (long long i = threadIdx.x; i < nwin; i += blockDim.x) {
-        double s = 0.0;
-        for (long long c = i * cs; c < i * cs + cw; ++c) s += part[c];
-        out[(base + i) * out_cols] = s / (double)W;
-      }
-    } else if (mode == 3) {
-      for (long long e = threadIdx.x; e < nwin * dims; e += blockDim.x) {
-        const long long i = e / dims;
-        const int d = (int)(e - i * dims);
-        double s = 0.0;
-        for (long long c = i * cs; c < i * cs + cw; ++c) s += part[c * ncol + d];
-        out[(base + i) * out_cols + d] = s / (double)W;
-      }
-    } else {
-      // one warp per window: lanes over columns, then the all-columns zero rule
-      for (long long i = warp; i < nwin; i += nwarp) {
-        double prod_x = 1.0, prod_y = 1.0;
-        for (int d0 = 0; d0 < dims; d0 += 32) {
-          const int d = d0 + lane;
-          double r = 0.0, xp = 1.0, yp = 1.0;
-          if (d < dims) {
-            double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
-            for (long long c = i * cs; c < i * cs + cw; ++c) {
-              const double* p = part + c * ncol + 5 * d;
-              sa += p[0]; sb += p[1]; saa += p[2]; sbb += p[3]; sab += p[4];
-            }
-            const double inv = 1.0 / (double)W;
-            xp = saa - sa * sa * inv;
-            yp = sbb - sb * sb * inv;
-            // A constant column has zero power in the reference's centred float32 sums; raw
-            // float64 moments leave rounding dust instead.
-            if (xp <= saa * 1e-13) xp = 0.0;
-            if (yp <= sbb * 1e-13) yp = 0.0;
-            r = (sab - sa * sb * inv) / (sqrt(xp) * sqrt(yp));
-            out[(base + i) * out_cols + d] = r;
+// ---------------------------------------------------------------------------------------------
+// Phase 2: every window of every shape is a short sum of consecutive partials.  A block handles
+// 64 windows of ONE (shape, segment) pair (table blk_j / blk_seg / blk_w0).
+//   mode 0/1/3: one thread per (window, column);  mode 2: one warp per window (lanes over columns,
+//   then the all-columns zero rule of brain_model.py:72-79).
+// ---------------------------------------------------------------------------------------------
+constexpr int WIN_PER_BLOCK = 64;
+
+struct WinArgs {
+  const double* part;
+  const long long* seg_len;
+  const long long* chunk_base;
+  const long long* win_base;       // [n_sizes * n_seg]
+  const int* blk_j;
+  const int* blk_seg;
+  const long long* blk_w0;
+  WinSpec ws;
+  int n_seg, dims, mode, ncol, out_cols;
+  double* out;
+};
+
+__global__ void __launch_bounds__(CORR_THREADS)
+corr_windows_kernel(const WinArgs P) {
+  const int j = P.blk_j[blockIdx.x], seg = P.blk_seg[blockIdx.x];
+  const long long w0 = P.blk_w0[blockIdx.x];
+  const long long n = P.seg_len[seg];
+  const long long W = P.ws.W[j], S = P.ws.S[j], g = P.ws.g;
+  const long long nwin = (n - W) / S + 1;
+  const long long w1 = min(nwin, w0 + (long long)WIN_PER_BLOCK);
+  const long long cw = W / g, cs = S / g;
+  const long long base = P.win_base[(long long)j * P.n_seg + seg];
+  const int ncol = P.ncol, dims = P.dims, out_cols = P.out_cols;
+  const double* part = P.part + P.chunk_base[seg] * ncol;
+  double* out = P.out;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  if (P.mode < 2) {
+    for (long long i = w0 + threadIdx.x; i < w1; i += blockDim.x) {
+      double s = 0.0;
+      for (long long c = i * cs; c < i * cs + cw; ++c) s += part[c];
+      out[(base + i) * out_cols] = s / (double)W;
+    }
+  } else if (P.mode == 3) {
+    for (long long e = threadIdx.x; e < (w1 - w0) * dims; e += blockDim.x) {
+      const long long i = w0 + e / dims;
+      const int d = (int)(e % dims);
+      double s = 0.0;
+      for (long long c = i * cs; c < i * cs + cw; ++c) s += part[c * ncol + d];
+      out[(base + i) * out_cols + d] = s / (double)W;
+    }
+  } else {
+    for (long long i = w0 + warp; i < w1; i += nwarp) {
+      double prod_x = 1.0, prod_y = 1.0;
+      for (int d0 = 0; d0 < dims; d0 += 32) {
+        const int d = d0 + lane;
+        double r = 0.0, xp = 1.0, yp = 1.0;
+        if (d < dims) {
+          double sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
+          for (long long c = i * cs; c < i * cs + cw; ++c) {
+            const double* p = part + c * ncol + 5 * d;
+            sa += p[0]; sb += p[1]; saa += p[2]; sbb += p[3]; sab += p[4];
           }
-          // product over columns of the powers (brain_model.py:72-73)
+          const double inv = 1.0 / (double)W;
+          xp = saa - sa * sa * inv;
+          yp = sbb - sb * sb * inv;
+          // A constant column has zero power in the reference's centred float32 sums; raw
+          // float64 moments leave rounding dust instead.
+          if (xp <= saa * 1e-13) xp = 0.0;
+          if (yp <= sbb * 1e-13) yp = 0.0;
+          r = (sab - sa * sb * inv) / (sqrt(xp) * sqrt(yp));
+          out[(base + i) * out_cols + d] = r;
+        }
+        // product over columns of the powers (brain_model.py:72-73)
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            xp *= __shfl_xor_sync(0xffffffffu, xp, o);
-            yp *= __shfl_xor_sync(0xffffffffu, yp, o);
-          }
-          prod_x *= xp;
-          prod_y *= yp;
+        for (int o = 16; o > 0; o >>= 1) {
+          xp *= __shfl_xor_sync(0xffffffffu, xp, o);
+          yp *= __shfl_xor_sync(0xffffffffu, yp, o);
         }
-        if (!(prod_x > 0.0) || !(prod_y > 0.0)) {
-          __syncwarp();
-          for (int d = lane; d < dims; d += 32) out[(base + i) * out_cols + d] = 0.0;
-        }
+        prod_x *= xp;
+        prod_y *= yp;
+      }
+      if (!(prod_x > 0.0) || !(prod_y > 0.0)) {
+        __syncwarp();
+        for (int d = lane; d < dims; d += 32) out[(base + i) * out_cols + d] = 0.0;
       }
     }
   }
@@ -414,7 +527,6 @@ extern "C" int td_windowed_corr_f32(const float* a, int64_t lda, const float* b,
   ws.g = g;
   const int ncol = (mode == 2) ? 5 * dims : (mode == 3 ? dims : 1);
   const int out_cols = (mode >= 2) ? dims : 1;
-  int64_t max_chunks = 0;
   std::vector<long long> win_base((size_t)n_sizes * n_seg);
   int64_t total = 0;
   for (int j = 0; j < n_sizes; ++j) {
@@ -425,26 +537,58 @@ extern "C" int td_windowed_corr_f32(const float* a, int64_t lda, const float* b,
     }
   }
   if (out_offset) out_offset[n_sizes] = total;
-  for (int s = 0; s < n_seg; ++s) max_chunks = std::max<int64_t>(max_chunks, seg_len[s] / g);
   if (total == 0) return TD_OK;
   TD_REQUIRE(out != nullptr, "td_windowed_corr_f32: null output");
-  if (max_chunks * ncol > MAX_PARTIALS) {
-    set_error("td_windowed_corr_f32: %lld partial sums per segment exceed %d (segment too long for gcd(W,S)=%lld); split the segment",
-              (long long)(max_chunks * ncol), MAX_PARTIALS, (long long)g);
-    return TD_ERR_UNSUPPORTED;
+
+  // Phase-1 blocks: consecutive chunks of one segment.  One warp per chunk when g >= 32 (a few
+  // chunks per warp keep the grid near 16 blocks per SM), one thread per chunk otherwise.
+  std::vector<long long> chunk_base(n_seg);
+  long long n_chunks = 0;
+  for (int s = 0; s < n_seg; ++s) { chunk_base[s] = n_chunks; n_chunks += seg_len[s] / g; }
+  int cpb;
+  if (g >= 32) {
+    const long long want_blocks = 148LL * 16;
+    cpb = (int)std::min<long long>(64, std::max<long long>(CORR_THREADS / 32, ceil_div(n_chunks, want_blocks)));
+    cpb = (int)round_up(cpb, CORR_THREADS / 32);
+  } else {
+    cpb = CORR_THREADS * 4;
   }
+  std::vector<int> blk_seg, wblk_j, wblk_seg;
+  std::vector<long long> blk_ch0, wblk_w0;
+  for (int s = 0; s < n_seg; ++s)
+    for (long long c = 0; c < seg_len[s] / g; c += cpb) { blk_seg.push_back(s); blk_ch0.push_back(c); }
+  for (int j = 0; j < n_sizes; ++j)
+    for (int s = 0; s < n_seg; ++s) {
+      const long long nw = td_window_count(seg_len[s], W[j], S[j]);
+      for (long long w0 = 0; w0 < nw; w0 += WIN_PER_BLOCK) { wblk_j.push_back(j); wblk_seg.push_back(s); wblk_w0.push_back(w0); }
+    }
+  DevBufs bufs(st);
   std::vector<long long> ss(seg_start, seg_start + n_seg), sl(seg_len, seg_len + n_seg);
-  long long *ss_d, *sl_d, *wb_d;
-  int rc = upload(ss, &ss_d, st); if (rc) return rc;
-  rc = upload(sl, &sl_d, st); if (rc) return rc;
-  rc = upload(win_base, &wb_d, st); if (rc) return rc;
-  const size_t smem = (size_t)std::max<int64_t>(1, max_chunks * ncol) * sizeof(double);
-  TD_CHECK_CUDA(cudaFuncSetAttribute(windowed_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAX_PARTIALS * sizeof(double))));
-  windowed_corr_kernel<<<n_seg, CORR_THREADS, smem, st>>>(a, lda, b, ldb, dims, ss_d, sl_d, ws, mode, reduction, mu_a, mu_b, power, lda_params, wb_d, n_seg, out, out_cols);
+  long long *ss_d, *sl_d, *wb_d, *cb_d, *bc_d, *ww_d;
+  int *bs_d, *wj_d, *wsg_d;
+  double* part_d;
+  int rc;
+  if ((rc = bufs.put(ss, &ss_d)) || (rc = bufs.put(sl, &sl_d)) || (rc = bufs.put(win_base, &wb_d)) ||
+      (rc = bufs.put(chunk_base, &cb_d)) || (rc = bufs.put(blk_seg, &bs_d)) || (rc = bufs.put(blk_ch0, &bc_d)) ||
+      (rc = bufs.put(wblk_j, &wj_d)) || (rc = bufs.put(wblk_seg, &wsg_d)) || (rc = bufs.put(wblk_w0, &ww_d)) ||
+      (rc = bufs.alloc((size_t)std::max<long long>(1, n_chunks) * ncol, &part_d)))
+    return rc;
+  CorrArgs ca;
+  ca.a = a; ca.lda_a = lda; ca.b = b; ca.ldb = ldb;
+  ca.dims = dims; ca.mode = mode; ca.reduction = reduction; ca.ncol = ncol;
+  ca.seg_start = ss_d; ca.seg_len = sl_d; ca.chunk_base = cb_d; ca.blk_seg = bs_d; ca.blk_ch0 = bc_d;
+  ca.chunks_per_block = cpb; ca.g = g;
+  ca.mu_a = mu_a; ca.mu_b = mu_b; ca.power = power; ca.lda = lda_params; ca.part = part_d;
+  if (!blk_seg.empty()) {
+    corr_partials_kernel<<<(unsigned)blk_seg.size(), CORR_THREADS, 0, st>>>(ca);
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
+  WinArgs wa;
+  wa.part = part_d; wa.seg_len = sl_d; wa.chunk_base = cb_d; wa.win_base = wb_d;
+  wa.blk_j = wj_d; wa.blk_seg = wsg_d; wa.blk_w0 = ww_d; wa.ws = ws;
+  wa.n_seg = n_seg; wa.dims = dims; wa.mode = mode; wa.ncol = ncol; wa.out_cols = out_cols; wa.out = out;
+  corr_windows_kernel<<<(unsigned)wblk_j.size(), CORR_THREADS, 0, st>>>(wa);
   TD_CHECK_CUDA(cudaGetLastError());
-  cudaFreeAsync(ss_d, st);
-  cudaFreeAsync(sl_d, st);
-  cudaFreeAsync(wb_d, st);
   return TD_OK;
 }
 

@@ -468,23 +468,28 @@ extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const 
   TD_CHECK_CUDA(cudaMemsetAsync(xtv, 0, (size_t)Dx * Q * sizeof(double), st));
   TD_CHECK_CUDA(cudaMemsetAsync(vtv, 0, (size_t)Q * Q * sizeof(double), st));
   if (nblk > 0) {
-    double* slices = nullptr;
-    const size_t slice_bytes = (size_t)THIN_SLICES * Dx * Q * sizeof(double);
-    TD_CHECK_CUDA(cudaMallocAsync((void**)&slices, slice_bytes, st));
-    TD_CHECK_CUDA(cudaMemsetAsync(slices, 0, slice_bytes, st));
     const int L = lags_of(*x);
     const size_t smem = ((size_t)(THIN_TB + L - 1) * THIN_CB + (size_t)THIN_TB * Q) * sizeof(float);
     if (smem > 220 * 1024) {
       set_error("td_lagged_thin_f64: %d lags need %zu bytes of shared memory", L, smem);
       return TD_ERR_UNSUPPORTED;
     }
+    // Partial-sum slices: owned by a guard so that every error path below frees them.
+    struct Slices {
+      double* p = nullptr;
+      cudaStream_t st;
+      explicit Slices(cudaStream_t s) : st(s) {}
+      ~Slices() { if (p) cudaFreeAsync(p, st); }
+    } slices(st);
+    const size_t slice_bytes = (size_t)THIN_SLICES * Dx * Q * sizeof(double);
+    TD_CHECK_CUDA(cudaMallocAsync((void**)&slices.p, slice_bytes, st));
+    TD_CHECK_CUDA(cudaMemsetAsync(slices.p, 0, slice_bytes, st));
     TD_CHECK_CUDA(cudaFuncSetAttribute(thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)nblk, (unsigned)ceil_div(x->channels, THIN_CB));
-    thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, slices, vtv);
+    thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, slices.p, vtv);
     TD_CHECK_CUDA(cudaGetLastError());
-    thin_reduce_kernel<<<(unsigned)ceil_div(Dx * Q, 256), 256, 0, st>>>(slices, xtv, Dx * Q);
+    thin_reduce_kernel<<<(unsigned)ceil_div(Dx * Q, 256), 256, 0, st>>>(slices.p, xtv, Dx * Q);
     TD_CHECK_CUDA(cudaGetLastError());
-    TD_CHECK_CUDA(cudaFreeAsync(slices, st));
   }
   return TD_OK;
 }

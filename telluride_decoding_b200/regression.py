@@ -11,6 +11,7 @@ structure: `jackknife_over_regularizations` returns {lambda: (mean, std)} over f
 """
 
 import collections
+import re
 
 import numpy as np
 import torch
@@ -56,7 +57,7 @@ def get_brain_model(test_dataset, my_flags):
 def _single_file_dataset(brain_data_obj, name):
   saved = (brain_data_obj.train_file_pattern, brain_data_obj.validate_file_pattern,
            brain_data_obj.test_file_pattern)
-  pattern = '^%s$' % name.replace('.', r'\.')
+  pattern = '^%s$' % re.escape(name)
   brain_data_obj.set_file_patterns('', pattern, pattern)
   try:
     return brain_data_obj.create_dataset('test')
@@ -129,11 +130,13 @@ def jackknife_sweep(test_brain_data, my_flags, regularization_list, test_files=N
       test_brain_data.set_file_patterns(my_flags.train_file_pattern or 'allbut', name, name)
       train_ds = test_brain_data.create_dataset('train')
       test_ds = test_brain_data.create_dataset('test')
-      fold = total - per_file[name] if len(all_names) > 1 else total
-      # Files the train pattern excludes beyond the held-out one (allbut_NN, explicit regexps).
+      # The fold's training statistics = total - every file the train pattern leaves out (the
+      # held-out file under `allbut`, more under allbut_NN or an explicit regexp; an explicit pattern
+      # that does NOT exclude the held-out file keeps it, like the reference would).
       used = set(n for n, _, _ in train_ds.files)
+      fold = total
       for other in all_names:
-        if other != name and other not in used:
+        if other not in used:
           fold = fold - per_file[other]
       dropped = _dropped_rows_stats(train_ds, is_cca)
       if dropped is not None:

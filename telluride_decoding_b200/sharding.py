@@ -95,6 +95,20 @@ def needed_row_range(seg_start, seg_len, seg_rows, pre, post, rank, world):
   return (0, 0) if lo is None else (lo, hi)
 
 
+def _check_same_plan(dataset, group=None):
+  """Raises unless every rank holds the same row plan (file order, kept rows per segment)."""
+  import hashlib
+  desc = repr(([f[0] for f in dataset.files], dataset.passes())).encode()
+  mine = int(hashlib.sha1(desc).hexdigest()[:15], 16)
+  t = torch.tensor([mine, -mine], dtype=torch.int64,
+                   device='cuda' if dist.get_backend(group) == 'nccl' else 'cpu')
+  dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+  if int(t[0].item()) != -int(t[1].item()):
+    raise ValueError('sharded statistics: the ranks disagree on the file order / kept rows of the '
+                     'dataset; seed `random` identically on every rank before creating the BrainData '
+                     'object (its file list is shuffled once, like the reference\'s).')
+
+
 def sharded_regression_stats(dataset, gram_options=None, workspace=None, group=None, timings=None):
   """RegressionStats of the whole dataset, each rank accumulating its share of the frames.
 
@@ -113,10 +127,19 @@ def sharded_regression_stats(dataset, gram_options=None, workspace=None, group=N
       timings[name] = ev
 
   x, y = dataset.stream('x'), dataset.stream('y')
+  # Ranks share the frames in STORAGE order (segments sorted by their first raw row), which does not
+  # depend on the once-shuffled file list (brain_data.py:206-207); which rows drop_remainder keeps
+  # does depend on it, so the ranks must agree on that list (seed `random` identically).
+  order = sorted(range(len(x.seg_start)), key=lambda i: x.seg_start[i])
+  if world > 1:
+    _check_same_plan(dataset, group)
   mark('start')
   gram = xtv = vtv = None
   for weight, keep in dataset.passes():
-    first, mine = shard_rows(None, keep, rank, world)
+    f_sorted, k_sorted = shard_rows(None, [keep[i] for i in order], rank, world)
+    first, mine = [0] * len(keep), [0] * len(keep)
+    for pos, i in enumerate(order):
+      first[i], mine[i] = f_sorted[pos], k_sorted[pos]
     g = ops.lagged_gram([x], mine, options=gram_options, workspace=workspace, seg_first=first)
     t, v = ops.lagged_thin(x, y, mine, seg_first=first)
     if gram is None:

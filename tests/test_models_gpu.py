@@ -186,13 +186,30 @@ def test_multi_trial_interleaved_fit_and_evaluate():
     np.testing.assert_array_equal(gy.cpu().numpy(), oy)
 
 
-def _cca_compare(rot_x, rot_y, e, g):
-  # joint sign per component is arbitrary in the reference (SVD); align before comparing
+def _align(rot, ref):
+  """Joint sign per component is arbitrary in the reference (SVD): align before comparing."""
+  s = np.sign(np.sum(rot * ref, axis=0))
+  assert np.all(s != 0)
+  return rot * s
+
+
+def _cca_compare(rot_x, rot_y, e, g, twin):
+  """North-star contract: 1e-4 on the rotations and correlations.  The reference computes in the
+  float32 of its inputs (general `eig` twice + SVD, cca.py:345-362), which leaves rounding of that
+  order in ITS output, so the comparison has two parts: (i) against the float64 twin of the
+  reference's algorithm we are held to 1e-5; (ii) against the reference's own float32
+  output to 1e-4 plus the reference's measured distance from its twin."""
+  tx, ty, _, _, te = twin
   for i in range(rot_x.shape[1]):
-    s = np.sign(np.sum(rot_x[:, i] * g['rot_x'][:, i]))
-    assert s != 0
-    assert gpu_util.rel_fro(s * rot_x[:, i], g['rot_x'][:, i]) < 2e-4, i
-    assert gpu_util.rel_fro(s * rot_y[:, i], g['rot_y'][:, i]) < 2e-4, i
+    gx, gy = g['rot_x'][:, i:i + 1], g['rot_y'][:, i:i + 1]
+    ax, ay = _align(rot_x[:, i:i + 1], gx), _align(rot_y[:, i:i + 1], gy)
+    wx, wy = _align(tx[:, i:i + 1], gx), _align(ty[:, i:i + 1], gy)
+    assert gpu_util.rel_fro(ax, wx) < 1e-5, i
+    assert gpu_util.rel_fro(ay, wy) < 1e-5, i
+    ref_noise = max(gpu_util.rel_fro(gx, wx), gpu_util.rel_fro(gy, wy))
+    assert gpu_util.rel_fro(ax, gx) < W_TOL + ref_noise, (i, ref_noise)
+    assert gpu_util.rel_fro(ay, gy) < W_TOL + ref_noise, (i, ref_noise)
+  np.testing.assert_allclose(e, te, rtol=1e-5)
   np.testing.assert_allclose(e, g['e'], rtol=W_TOL)
 
 
@@ -205,7 +222,11 @@ def test_cca_matches_reference_fixture(golden_dir):
   ds = bd.create_dataset('train')
   rot_x, rot_y, mean_x, mean_y, e = cca.calculate_cca_parameters_from_dataset(
       ds, int(g['dim']), regularization=float(g['reg']), mini_batch_count=0)
-  _cca_compare(rot_x, rot_y, e, g)
+  batches = gpu_util.oracle_batches(g['x'], np.ones((n, 1), np.float32), g['x2'], None, 0,
+                                    int(g['post1']), 0, int(g['post2']), 0, int(g['batch']))
+  twin = ora.cca_from_batches(batches, int(g['dim']), float(g['reg']), mini_batch_count=0,
+                              dtype=np.float64)
+  _cca_compare(rot_x, rot_y, e, g, twin)
   np.testing.assert_allclose(mean_x, g['mean_x'], atol=1e-6)
   np.testing.assert_allclose(mean_y, g['mean_y'], atol=1e-6)
   assert rot_x.dtype == np.float32 and mean_x.shape == (1, rot_x.shape[0])
@@ -213,8 +234,6 @@ def test_cca_matches_reference_fixture(golden_dir):
   model = cca.BrainModelCCA(ds, cca_dims=int(g['dim']), regularization_lambda=float(g['reg']))
   assert model.fit(ds) == {}
   res = model.evaluate(bd.create_dataset('test'))
-  batches = gpu_util.oracle_batches(g['x'], np.ones((n, 1), np.float32), g['x2'], None, 0,
-                                    int(g['post1']), 0, int(g['post2']), 0, int(g['batch']))
   want = ora.evaluate_cca(batches, g['mean_x'], g['mean_y'], g['rot_x'], g['rot_y'])
   assert set(res) == {'loss', 'cca_pearson_correlation_first'}
   assert abs(res['cca_pearson_correlation_first'] - want['cca_pearson_correlation_first']) < W_TOL

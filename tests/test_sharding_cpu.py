@@ -84,3 +84,23 @@ def test_partial_statistics_allreduce_gloo(tmp_path, world):
   result = str(tmp_path / 'result.txt')
   mp.spawn(_worker, args=(world, _free_port(), result), nprocs=world, join=True)
   assert open(result).read() == 'ok'
+
+
+def test_needed_row_range_covers_rows_and_halo():
+  """Each rank uploads one contiguous range of raw rows: its design rows plus pre / post frames of
+  the SAME trial on either side, clipped at the trial edges (zero padding there, brain_data.py:448-455)."""
+  lens = [1000, 640, 2000]
+  starts = [0, 1000, 1640]
+  pre, post = 3, 17
+  for world in (1, 2, 3, 8):
+    for rank in range(world):
+      first, keep = sharding.shard_rows(None, lens, rank, world)
+      lo, hi = sharding.needed_row_range(starts, lens, lens, pre, post, rank, world)
+      touched = [(st + max(f - pre, 0), st + min(k + post, n))
+                 for st, n, f, k in zip(starts, lens, first, keep) if k > f]
+      if not touched:
+        assert (lo, hi) == (0, 0)
+        continue
+      assert lo == min(a for a, _ in touched) and hi == max(b for _, b in touched)
+      assert 0 <= lo < hi <= sum(lens)
+  assert sharding.needed_row_range(starts, lens, lens, pre, post, 0, 1) == (0, sum(lens))
