@@ -96,16 +96,36 @@ __device__ __forceinline__ double frame_signal(const float* a, const float* b, i
   return (double)(s / (float)dims);
 }
 
+// a / p, correctly rounded like the reference's float32 division, from a reciprocal computed once
+// per column: q = a*r, rem = a - q*p (exact in an FMA), q' = q + rem*r is RN(a/p) when r = RN(1/p)
+// and nothing leaves the normal range (Markstein's final step).  The callers sum |q'| over the
+// columns of a frame and redo the frame with real divisions when that sum is not below 1e30 (an
+// overflow, an infinity or a NaN -- including the NaN stored as r for a power outside
+// [1e-30, 1e30]); results below 1e-30 may differ from the division in their last bits, which is
+// 1e-18 of anything a float64 window mean of O(1) signals can see.
+__device__ __forceinline__ float div_fast(float a, float p, float r) {
+  const float q = a * r;
+  return fmaf(fmaf(-q, p, a), r, q);
+}
+
 // Same per-frame scalar from rows already held in registers (float4-loaded), DIMS known at compile
 // time.  mu / power / lda point to shared memory.
 template <int DIMS>
 __device__ __forceinline__ double frame_signal_regs(const float (&a)[DIMS], const float (&b)[DIMS],
                                                     int reduction, const float* mu_a,
                                                     const float* mu_b, const float* power,
-                                                    const double* lda) {
+                                                    const float* rcp, const double* lda) {
   float c[DIMS];
+  float mag = 0.0f;
 #pragma unroll
-  for (int d = 0; d < DIMS; ++d) c[d] = ((a[d] - mu_a[d]) * (b[d] - mu_b[d])) / power[d];
+  for (int d = 0; d < DIMS; ++d) {
+    c[d] = div_fast((a[d] - mu_a[d]) * (b[d] - mu_b[d]), power[d], rcp[d]);
+    mag += fabsf(c[d]);
+  }
+  if (!(mag < 1e30f)) {
+#pragma unroll
+    for (int d = 0; d < DIMS; ++d) c[d] = ((a[d] - mu_a[d]) * (b[d] - mu_b[d])) / power[d];
+  }
   if (reduction == 0) return (double)c[0];
   if (reduction == 1) return (double)c[1];
   if (reduction == 5) {
@@ -162,16 +182,16 @@ struct CorrArgs {
 };
 
 // Rows of DIMS floats (DIMS % 4 == 0), 16-byte loads, two frames per lane in flight.
-template <int DIMS>
+template <int DIMS, bool ALL_COLUMNS>
 __device__ __forceinline__ void chunk_vec_rows(const CorrArgs& P, const float* A, const float* B,
                                                long long ch, const float* mu_a, const float* mu_b,
-                                               const float* power, const double* lda, double* out,
-                                               int lane) {
+                                               const float* power, const float* rcp, const double* lda,
+                                               double* out, int lane) {
   const long long g = P.g;
   double s = 0.0;
-  double sd[DIMS];
+  double sd[ALL_COLUMNS ? DIMS : 1];
 #pragma unroll
-  for (int d = 0; d < DIMS; ++d) sd[d] = 0.0;
+  for (int d = 0; d < (ALL_COLUMNS ? DIMS : 1); ++d) sd[d] = 0.0;
   const long long t_end = (ch + 1) * g;
   for (long long t = ch * g + lane; t < t_end; t += 64) {
     float av[2][DIMS], bv[2][DIMS];
@@ -191,16 +211,26 @@ __device__ __forceinline__ void chunk_vec_rows(const CorrArgs& P, const float* A
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (u == 1 && !second) break;
-      if (P.mode == 1) {
-        s += frame_signal_regs<DIMS>(av[u], bv[u], P.reduction, mu_a, mu_b, power, lda);
+      if constexpr (!ALL_COLUMNS) {
+        s += frame_signal_regs<DIMS>(av[u], bv[u], P.reduction, mu_a, mu_b, power, rcp, lda);
       } else {
+        float c[DIMS];
+        float mag = 0.0f;
 #pragma unroll
-        for (int d = 0; d < DIMS; ++d)
-          sd[d] += (double)(((av[u][d] - mu_a[d]) * (bv[u][d] - mu_b[d])) / power[d]);
+        for (int d = 0; d < DIMS; ++d) {
+          c[d] = div_fast((av[u][d] - mu_a[d]) * (bv[u][d] - mu_b[d]), power[d], rcp[d]);
+          mag += fabsf(c[d]);
+        }
+        if (!(mag < 1e30f)) {
+#pragma unroll
+          for (int d = 0; d < DIMS; ++d) c[d] = ((av[u][d] - mu_a[d]) * (bv[u][d] - mu_b[d])) / power[d];
+        }
+#pragma unroll
+        for (int d = 0; d < DIMS; ++d) sd[d] += (double)c[d];
       }
     }
   }
-  if (P.mode == 1) {
+  if constexpr (!ALL_COLUMNS) {
     s = warp_sum(s);
     if (lane == 0) out[0] = s;
   } else {
@@ -216,7 +246,7 @@ __device__ __forceinline__ void chunk_vec_rows(const CorrArgs& P, const float* A
 // two loads per lane in flight.  mode 1, reduction 'first'.
 __device__ __forceinline__ void chunk_vec_scalar(const CorrArgs& P, const float* A, const float* B,
                                                  long long ch, float mu_a, float mu_b, float power,
-                                                 double* out, int lane) {
+                                                 float rcp, double* out, int lane) {
   const long long g = P.g;
   const float4* pa = reinterpret_cast<const float4*>(A + ch * g);
   const float4* pb = reinterpret_cast<const float4*>(B + ch * g);
@@ -226,23 +256,38 @@ __device__ __forceinline__ void chunk_vec_scalar(const CorrArgs& P, const float*
     const bool second = i + 32 < nv;
     const float4 x0 = __ldg(pa + i), y0 = __ldg(pb + i);
     const float4 x1 = __ldg(pa + (second ? i + 32 : i)), y1 = __ldg(pb + (second ? i + 32 : i));
-    // float32 per frame in the reference's order; the four frames are carried in float64 one by one
-    s += (double)(((x0.x - mu_a) * (y0.x - mu_b)) / power);
-    s += (double)(((x0.y - mu_a) * (y0.y - mu_b)) / power);
-    s += (double)(((x0.z - mu_a) * (y0.z - mu_b)) / power);
-    s += (double)(((x0.w - mu_a) * (y0.w - mu_b)) / power);
-    if (second) {
-      s += (double)(((x1.x - mu_a) * (y1.x - mu_b)) / power);
-      s += (double)(((x1.y - mu_a) * (y1.y - mu_b)) / power);
-      s += (double)(((x1.z - mu_a) * (y1.z - mu_b)) / power);
-      s += (double)(((x1.w - mu_a) * (y1.w - mu_b)) / power);
+    // float32 per frame in the reference's order; the frames are carried in float64 one by one
+    float c[8];
+    c[0] = div_fast((x0.x - mu_a) * (y0.x - mu_b), power, rcp);
+    c[1] = div_fast((x0.y - mu_a) * (y0.y - mu_b), power, rcp);
+    c[2] = div_fast((x0.z - mu_a) * (y0.z - mu_b), power, rcp);
+    c[3] = div_fast((x0.w - mu_a) * (y0.w - mu_b), power, rcp);
+    c[4] = div_fast((x1.x - mu_a) * (y1.x - mu_b), power, rcp);
+    c[5] = div_fast((x1.y - mu_a) * (y1.y - mu_b), power, rcp);
+    c[6] = div_fast((x1.z - mu_a) * (y1.z - mu_b), power, rcp);
+    c[7] = div_fast((x1.w - mu_a) * (y1.w - mu_b), power, rcp);
+    float mag = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mag += fabsf(c[e]);
+    if (!(mag < 1e30f)) {
+      c[0] = ((x0.x - mu_a) * (y0.x - mu_b)) / power; c[1] = ((x0.y - mu_a) * (y0.y - mu_b)) / power;
+      c[2] = ((x0.z - mu_a) * (y0.z - mu_b)) / power; c[3] = ((x0.w - mu_a) * (y0.w - mu_b)) / power;
+      c[4] = ((x1.x - mu_a) * (y1.x - mu_b)) / power; c[5] = ((x1.y - mu_a) * (y1.y - mu_b)) / power;
+      c[6] = ((x1.z - mu_a) * (y1.z - mu_b)) / power; c[7] = ((x1.w - mu_a) * (y1.w - mu_b)) / power;
     }
+    s += (double)c[0]; s += (double)c[1]; s += (double)c[2]; s += (double)c[3];
+    if (second) { s += (double)c[4]; s += (double)c[5]; s += (double)c[6]; s += (double)c[7]; }
   }
   s = warp_sum(s);
   if (lane == 0) out[0] = s;
 }
 
-__global__ void __launch_bounds__(CORR_THREADS)
+// PATH 0: generic (any dims / strides / g);  1 / 3: rows of DIMS floats, 16-byte loads (host checked
+// the alignment of every segment), reduced signal / every column;  2: one contiguous column, four
+// frames per load.  Separate
+// instantiations so that each path gets its own register allocation (occupancy).
+template <int PATH, int DIMS>
+__global__ void __launch_bounds__(CORR_THREADS, PATH == 0 ? 1 : (DIMS <= 8 ? 3 : 2))
 corr_partials_kernel(const CorrArgs P) {
   const int seg = P.blk_seg[blockIdx.x];
   const long long ch0 = P.blk_ch0[blockIdx.x];
@@ -257,13 +302,16 @@ corr_partials_kernel(const CorrArgs P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
 
   // Global statistics (and LDA axis) staged once per block.
-  __shared__ float s_mu_a[128], s_mu_b[128], s_power[128];
+  __shared__ float s_mu_a[128], s_mu_b[128], s_power[128], s_rcp[128];
   __shared__ double s_lda[130];
   const float *mu_a = P.mu_a, *mu_b = P.mu_b, *power = P.power;
+  const float* rcp = s_rcp;
   const double* lda = P.lda;
   if (mode == 1 || mode == 3) {
     for (int d = threadIdx.x; d < dims; d += blockDim.x) {
-      s_mu_a[d] = mu_a[d]; s_mu_b[d] = mu_b[d]; s_power[d] = power[d];
+      const float pw = power[d];
+      s_mu_a[d] = mu_a[d]; s_mu_b[d] = mu_b[d]; s_power[d] = pw;
+      s_rcp[d] = (fabsf(pw) >= 1e-30f && fabsf(pw) <= 1e30f) ? 1.0f / pw : __int_as_float(0x7fc00000);
     }
     if (lda) for (int d = threadIdx.x; d < dims + 2; d += blockDim.x) s_lda[d] = lda[d];
     __syncthreads();
@@ -271,22 +319,12 @@ corr_partials_kernel(const CorrArgs P) {
     if (lda) lda = s_lda;
   }
 
-  const bool rows_vec = (mode == 1 || mode == 3) && g >= 32 && (dims == 4 || dims == 8 || dims == 16) &&
-                        (P.lda_a % 4 == 0) && (P.ldb % 4 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0);
-  const bool scalar_vec = mode == 1 && reduction == 0 && dims == 1 && g >= 128 && (g % 4 == 0) &&
-                          P.lda_a == 1 && P.ldb == 1 &&
-                          ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16 == 0);
-  if (rows_vec) {
-    for (long long ch = ch0 + warp; ch < ch1; ch += nwarp) {
-      double* o = part + ch * ncol;
-      if (dims == 4) chunk_vec_rows<4>(P, A, B, ch, mu_a, mu_b, power, lda, o, lane);
-      else if (dims == 8) chunk_vec_rows<8>(P, A, B, ch, mu_a, mu_b, power, lda, o, lane);
-      else chunk_vec_rows<16>(P, A, B, ch, mu_a, mu_b, power, lda, o, lane);
-    }
-  } else if (scalar_vec) {
+  if constexpr (PATH == 1 || PATH == 3) {
     for (long long ch = ch0 + warp; ch < ch1; ch += nwarp)
-      chunk_vec_scalar(P, A, B, ch, mu_a[0], mu_b[0], power[0], part + ch, lane);
+      chunk_vec_rows<DIMS, PATH == 3>(P, A, B, ch, mu_a, mu_b, power, rcp, lda, part + ch * ncol, lane);
+  } else if constexpr (PATH == 2) {
+    for (long long ch = ch0 + warp; ch < ch1; ch += nwarp)
+      chunk_vec_scalar(P, A, B, ch, mu_a[0], mu_b[0], power[0], rcp[0], part + ch, lane);
   } else if (g >= 32) {
     for (long long ch = ch0 + warp; ch < ch1; ch += nwarp) {
       if (mode < 2) {
@@ -580,7 +618,24 @@ extern "C" int td_windowed_corr_f32(const float* a, int64_t lda, const float* b,
   ca.chunks_per_block = cpb; ca.g = g;
   ca.mu_a = mu_a; ca.mu_b = mu_b; ca.power = power; ca.lda = lda_params; ca.part = part_d;
   if (!blk_seg.empty()) {
-    corr_partials_kernel<<<(unsigned)blk_seg.size(), CORR_THREADS, 0, st>>>(ca);
+    // Vector paths need 16-byte aligned rows in every segment.
+    bool aligned = b != nullptr;
+    for (int s = 0; s < n_seg && aligned; ++s)
+      aligned = ((reinterpret_cast<uintptr_t>(a + seg_start[s] * lda) |
+                  reinterpret_cast<uintptr_t>(b + seg_start[s] * ldb)) % 16) == 0;
+    const bool rows_vec = aligned && (mode == 1 || mode == 3) && g >= 32 && (dims == 4 || dims == 8 || dims == 16) &&
+                          lda % 4 == 0 && ldb % 4 == 0;
+    const bool scalar_vec = aligned && mode == 1 && reduction == 0 && dims == 1 && g >= 128 && g % 4 == 0 &&
+                            lda == 1 && ldb == 1;
+    const unsigned nblk = (unsigned)blk_seg.size();
+    if (rows_vec && mode == 1 && dims == 4) corr_partials_kernel<1, 4><<<nblk, CORR_THREADS, 0, st>>>(ca);
+    else if (rows_vec && mode == 1 && dims == 8) corr_partials_kernel<1, 8><<<nblk, CORR_THREADS, 0, st>>>(ca);
+    else if (rows_vec && mode == 1) corr_partials_kernel<1, 16><<<nblk, CORR_THREADS, 0, st>>>(ca);
+    else if (rows_vec && dims == 4) corr_partials_kernel<3, 4><<<nblk, CORR_THREADS, 0, st>>>(ca);
+    else if (rows_vec && dims == 8) corr_partials_kernel<3, 8><<<nblk, CORR_THREADS, 0, st>>>(ca);
+    else if (rows_vec) corr_partials_kernel<3, 16><<<nblk, CORR_THREADS, 0, st>>>(ca);
+    else if (scalar_vec) corr_partials_kernel<2, 1><<<nblk, CORR_THREADS, 0, st>>>(ca);
+    else corr_partials_kernel<0, 1><<<nblk, CORR_THREADS, 0, st>>>(ca);
     TD_CHECK_CUDA(cudaGetLastError());
   }
   WinArgs wa;

@@ -1,0 +1,390 @@
+// CTA-pair Gram kernel that builds the lagged operand ON CHIP from a raw time tile + lag halo
+// (included by gram_umma.cu).  Method 4, the default for CTA pairs.
+//
+// The earlier kernels (gram_ts.cuh, lagged_gram_umma_kernel) fetch every (lag, channel-block) row
+// group of an operand tile as its own TMA box from four shifted channel-major copies of the
+// recording: 4x the recording in HBM, and each raw sample crosses L2 -> shared memory once per lag
+// and tile.  Here the recording stays as the caller has it -- time-major [frames, channels] -- and
+//
+//   * an operand row group is 32 rows = 4 consecutive lags x 8 channels of one stream.  What it needs
+//     for a 32-frame k-tile is ONE raw box [32 + halo frames, 8 channels] straight from the raw
+//     array (TMA, no swizzle, 32 bytes per frame); consecutive lag groups of the same channels share
+//     the box of the first one (16 lags -> 47 frames, boxes are 48 frames), so a 128-row operand
+//     tile needs 1.5 - 6 KB of raw samples instead of 16 KB;
+//   * the four converter warps (one per TMEM lane quadrant, lane = 4 lags x 8 channels) read their
+//     row's 16 frames at the row's own lag offset -- consecutive lanes hit 32 consecutive words, no
+//     bank conflicts -- zero what lies outside the trial (brain_data.py:448-452 pads with zeros at
+//     trial / chunk edges; a TMA box simply runs into the neighbouring trial) or outside this call's
+//     design rows, and write
+//         A: hi | lo straight into TENSOR memory (tcgen05.st), as in gram_ts.cuh,
+//         B: the hi tile and the lo tile in the K-major 128-byte-swizzled layout tcgen05.mma reads;
+//   * MMA issue, accumulator regions, epilogue and barriers are those of gram_ts.cuh.
+//
+// The Hankel matrix never exists anywhere: HBM holds the raw recording once (a padded copy only if
+// the caller's row stride is not a multiple of 16 bytes, which TMA requires).
+
+namespace hk {
+
+constexpr int STAGES = 4;
+constexpr int BOX_FRAMES = 48;                          // 32 frames + 15 frames of lag halo + 1
+constexpr int BOX_CH = 8;                               // channels per row group
+constexpr int BOX_BYTES = BOX_FRAMES * BOX_CH * 4;      // 1536
+constexpr int RG_ROWS = 32;                             // rows per row group: 4 lags x 8 channels
+constexpr int RG_LAGS = 4;
+constexpr int RG_PER_CTA = TILE_ROWS / RG_ROWS;         // 4
+constexpr int RAW_BYTES = RG_PER_CTA * BOX_BYTES;       // raw boxes of one operand tile
+constexpr int OFF_BHI = 0;
+constexpr int OFF_BLO = OPERAND_BYTES;
+constexpr int OFF_ARAW = 2 * OPERAND_BYTES;
+constexpr int OFF_BRAW = OFF_ARAW + RAW_BYTES;
+constexpr int STAGE_BYTES = 2 * OPERAND_BYTES + 2 * RAW_BYTES;     // 44 KiB
+static_assert(STAGE_BYTES % 1024 == 0, "stage must keep the 1024-byte alignment of the swizzled tiles");
+constexpr int NUM_THREADS = 512;
+constexpr int NUM_CONV = 4;                              // warps 4..7
+constexpr int EPI_WARP0 = 8, NUM_EPI = 8;
+constexpr uint32_t ACC_COLS = 128;
+constexpr uint32_t A_COL0 = 3 * ACC_COLS;
+constexpr uint32_t A_SLOT_COLS = 32;
+constexpr int A_SLOTS = 4;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int NACC = 128;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_BARRIERS = 2 * STAGES + 2 * A_SLOTS + 12;
+static_assert(8 * NUM_BARRIERS + 8 <= 256, "barrier block too small");
+
+struct HaloParams {
+  const int4* rgs;        // [Dpad / 32] {stream | issue << 1, first channel, lag shift k0 - pre, byte offset in the operand's raw region}
+  const int4* ktiles;     // [NK][2] {raw row of design row 0: stream 0, stream 1, begin | end << 8 | edge << 16, -t0}, {len0 - t0, len1 - t0, 0, 0}
+  const int* out_idx;     // [Dpad] tile-space row -> row/col of G, -1 for padding
+  float* G;
+  long long ldg;
+  int ntri;
+  long long NK;
+  int KS;
+  int chunk_kt;
+  long long total_steps;
+  long long* prof;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
+                        const __grid_constant__ CUtensorMap tmap1, const HaloParams P) {
+  constexpr uint32_t IDESC = ptx::umma_idesc_tf32(256, 128);
+  using ts::HalfRing;
+  using ts::lo_bits;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // raw boxes landed (local)
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };           // MMAs of the stage retired (both issuers)
+  auto ready_bar = [&](int j) { return bar_base + 8u * (2 * STAGES + j); };       // leader: A slot + B hi/lo of 16 frames built in both CTAs
+  auto aempty_bar = [&](int j) { return bar_base + 8u * (2 * STAGES + A_SLOTS + j); };   // MMAs reading the slot retired
+  auto tfull_bar = [&](int h, int r) { return bar_base + 8u * (2 * STAGES + 2 * A_SLOTS + 3 * h + r); };
+  auto tempty_bar = [&](int h, int r) { return bar_base + 8u * (2 * STAGES + 2 * A_SLOTS + 6 + 3 * h + r); };
+  const uint32_t tmem_slot = bar_base + 8u * NUM_BARRIERS;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int worker = blockIdx.x / 2;
+  const int n_workers = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap0);
+    ptx::prefetch_tmap(&tmap1);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 2);
+    }
+    for (int j = 0; j < A_SLOTS; ++j) {
+      ptx::mbar_init(ready_bar(j), 2 * NUM_CONV);
+      ptx::mbar_init(aempty_bar(j), 2);
+    }
+    for (int h = 0; h < 2; ++h)
+      for (int r = 0; r < 3; ++r) {
+        ptx::mbar_init(tfull_bar(h, r), 1);
+        ptx::mbar_init(tempty_bar(h, r), 2 * (NUM_EPI / 2));
+      }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<2>(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // Register budget per warpgroup: 128 x (72 + 104 + 168 + 168) = 65536.
+  const int wg = warp >> 2;
+  if (wg == 0) {
+    ptx::setmaxnreg_dec<72>();
+    if (warp == 0) {
+      // ===================== TMA producer: raw boxes of this CTA's A and B row groups =============
+      WorkIter wi(P, worker, n_workers);
+      WorkItem it;
+      int stage = 0;
+      uint32_t phase = 0;
+      while (wi.next(P, it)) {
+        const int ta = (it.tm * 2 + (int)rank) * RG_PER_CTA;
+        const int tb = (it.tn * 2 + (int)rank) * RG_PER_CTA;
+        int rq[2 * RG_PER_CTA], rc[2 * RG_PER_CTA], rd[2 * RG_PER_CTA];
+        uint32_t n_issue = 0;
+#pragma unroll
+        for (int i = 0; i < 2 * RG_PER_CTA; ++i) {
+          const int4 g = __ldg(&P.rgs[(i < RG_PER_CTA ? ta : tb) + (i & (RG_PER_CTA - 1))]);
+          rq[i] = g.x; rc[i] = g.y; rd[i] = g.z;
+          n_issue += (uint32_t)(g.x >> 1) & 1u;
+        }
+        int4 kn = __ldg(&P.ktiles[2 * it.kt_begin]);
+        for (long long kt = it.kt_begin; kt < it.kt_end; ++kt) {
+          const int4 kc = kn;
+          if (kt + 1 < it.kt_end) kn = __ldg(&P.ktiles[2 * (kt + 1)]);
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (ptx::elect_one()) {
+            const uint32_t fb = full_bar(stage);
+            ptx::mbar_expect_tx(fb, n_issue * BOX_BYTES);
+            const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+#pragma unroll
+            for (int i = 0; i < 2 * RG_PER_CTA; ++i) {
+              if (rq[i] & 2) {
+                const uint32_t dst = sbase + (i < RG_PER_CTA ? OFF_ARAW : OFF_BRAW) + (i & (RG_PER_CTA - 1)) * BOX_BYTES;
+                const int q = rq[i] & 1;
+                tma_load_2d(dst, q ? &tmap1 : &tmap0, fb, rc[i], (q ? kc.y : kc.x) + rd[i]);
+              }
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp <= 2 && rank == 0) {
+      // ===================== MMA issuers (pair leader): warp 1 -> half 0, warp 2 -> half 1 =========
+      const int h = warp - 1;
+      WorkIter wi(P, worker, n_workers);
+      WorkItem it;
+      int stage = 0;
+      uint32_t kcount = 0;                       // k-tiles issued so far: A slots 2*kcount, 2*kcount + 1
+      HalfRing ring;
+      while (wi.next(P, it)) {
+        int next_range = __ldg(&P.ktiles[2 * it.kt_begin]).z;
+        for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
+          const long long c1 = min(it.kt_end, c0 + (long long)P.chunk_kt);
+          ring.next_chunk(h);
+          for (long long kt = c0; kt < c1; ++kt, ++kcount) {
+            const int range = next_range;
+            if (kt + 1 < it.kt_end) next_range = __ldg(&P.ktiles[2 * (kt + 1)]).z;
+            const int ks0 = (range & 0xff) >> 3, ks1 = (((range >> 8) & 0xff) + 7) >> 3;
+            const bool whole = (ks0 == 0) && (ks1 == BK / 8);
+            const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+            const uint32_t first_acc = (kt > c0) ? 1u : 0u;
+            const int r = ring.r;
+            const uint32_t d = tmem_base + (uint32_t)r * ACC_COLS;
+            if (kt == c0) ptx::mbar_wait(tempty_bar(1 - h, r), ring.drained_parity(h));
+            const uint64_t b_hi = ptx::umma_desc_k_sw128(sbase + OFF_BHI + h * (OPERAND_BYTES / 2));
+            const uint64_t b_lo = ptx::umma_desc_k_sw128(sbase + OFF_BLO + h * (OPERAND_BYTES / 2));
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t use = 2u * kcount + hh;
+              const uint32_t slot = use & (A_SLOTS - 1);
+              ptx::mbar_wait(ready_bar(slot), (use >> 2) & 1u);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                const uint32_t a_base = tmem_base + A_COL0 + slot * A_SLOT_COLS;
+                if (whole) {
+#pragma unroll
+                  for (int q = 0; q < 2; ++q) {
+                    const uint64_t adv = (uint64_t)((hh * 2 + q) * 2);     // 8 frames = 32 B = 2 x 16 B
+                    const uint32_t a_hi = a_base + q * 8, a_lo = a_base + 16 + q * 8;
+                    ptx::mma_tf32_ts_pair(d, a_hi, b_hi + adv, IDESC, (hh + q) ? 1u : first_acc);
+                    ptx::mma_tf32_ts_pair(d, a_hi, b_lo + adv, IDESC, 1u);
+                    ptx::mma_tf32_ts_pair(d, a_lo, b_hi + adv, IDESC, 1u);
+                  }
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 2; ++q) {
+                    const int ks = hh * 2 + q;
+                    if (ks >= ks0 && ks < ks1) {
+                      const uint64_t adv = (uint64_t)(ks * 2);
+                      const uint32_t a_hi = a_base + q * 8, a_lo = a_base + 16 + q * 8;
+                      ptx::mma_tf32_ts_pair(d, a_hi, b_hi + adv, IDESC, (ks > ks0) ? 1u : first_acc);
+                      ptx::mma_tf32_ts_pair(d, a_hi, b_lo + adv, IDESC, 1u);
+                      ptx::mma_tf32_ts_pair(d, a_lo, b_hi + adv, IDESC, 1u);
+                    }
+                  }
+                }
+                ptx::mma_commit<2>(aempty_bar(slot));                        // A slot reusable
+                if (hh == 1) {
+                  ptx::mma_commit<2>(empty_bar(stage));                      // stage reusable in both CTAs
+                  if (kt == c1 - 1) ptx::mma_commit<2>(tfull_bar(h, r));
+                }
+              }
+              __syncwarp();
+            }
+            if (++stage == STAGES) stage = 0;
+          }
+        }
+      }
+    }
+  } else if (wg == 1) {
+    // ===================== converters: raw boxes -> A in TMEM (hi | lo), B hi / lo tiles ==========
+    ptx::setmaxnreg_dec<104>();
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                    // A row (= TMEM lane) and B row of this thread
+    const int kk = lane >> 3, cc = lane & 7;             // lag and channel of the row inside its row group
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t ready_leader0 = ptx::mapa(ready_bar(0), 0);
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + A_COL0;
+    WorkIter wi(P, worker, n_workers);
+    WorkItem it;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t kcount = 0;
+    while (wi.next(P, it)) {
+      const int4 ga = __ldg(&P.rgs[(it.tm * 2 + (int)rank) * RG_PER_CTA + quad]);
+      const int4 gb = __ldg(&P.rgs[(it.tn * 2 + (int)rank) * RG_PER_CTA + quad]);
+      const uint32_t a_rd = OFF_ARAW + (uint32_t)ga.w + (uint32_t)(kk * BOX_CH + cc) * 4u;
+      const uint32_t b_rd = OFF_BRAW + (uint32_t)gb.w + (uint32_t)(kk * BOX_CH + cc) * 4u;
+      const int a_d = ga.z + kk, b_d = gb.z + kk;        // lag shift k - pre of this thread's rows
+      const int a_q = ga.x & 1, b_q = gb.x & 1;
+      int4 kn0 = __ldg(&P.ktiles[2 * it.kt_begin]);
+      int4 kn1 = __ldg(&P.ktiles[2 * it.kt_begin + 1]);
+      for (long long kt = it.kt_begin; kt < it.kt_end; ++kt, ++kcount) {
+        const int4 k0 = kn0, k1 = kn1;
+        if (kt + 1 < it.kt_end) {
+          kn0 = __ldg(&P.ktiles[2 * (kt + 1)]);
+          kn1 = __ldg(&P.ktiles[2 * (kt + 1) + 1]);
+        }
+        const int begin = k0.z & 0xff, end = (k0.z >> 8) & 0xff;
+        const bool edge = (k0.z >> 16) != 0;
+        const bool partial = begin > 0 || end < BK;
+        // element e of the k-tile (design row t0 + e) at lag shift d reads frame t0 + e + d of the
+        // segment: inside the trial iff -t0 <= e + d < len - t0
+        const int a_lo_e = k0.w - a_d, a_hi_e = (a_q ? k1.y : k1.x) - a_d;
+        const int b_lo_e = k0.w - b_d, b_hi_e = (b_q ? k1.y : k1.x) - b_d;
+        const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+        const uint32_t bhi = sbase + OFF_BHI + row_off, blo = sbase + OFF_BLO + row_off;
+        ptx::mbar_wait(full_bar(stage), phase);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t use = 2u * kcount + hh;
+          const uint32_t slot = use & (A_SLOTS - 1);
+          uint32_t hi[16], lo[16], bv[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            hi[e] = lds32(sbase + a_rd + (uint32_t)((hh * 16 + e) * BOX_CH * 4));
+            bv[e] = lds32(sbase + b_rd + (uint32_t)((hh * 16 + e) * BOX_CH * 4));
+          }
+          if (edge) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int t = hh * 16 + e;
+              if (t < a_lo_e || t >= a_hi_e) hi[e] = 0u;
+              if (t < b_lo_e || t >= b_hi_e) bv[e] = 0u;
+            }
+          }
+          if (partial) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int t = hh * 16 + e;
+              if (t < begin || t >= end) hi[e] = 0u;
+            }
+          }
+          // B: hi tile (the raw bits) and lo tile, K-major with the 128-byte swizzle: frame t of a row
+          // sits in 16-byte chunk (t/4) ^ (row%8); lane-per-row 16-byte stores are conflict free.
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t off = ((uint32_t)(hh * 4 + i) ^ sw) << 4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bhi + off),
+                         "r"(bv[4 * i]), "r"(bv[4 * i + 1]), "r"(bv[4 * i + 2]), "r"(bv[4 * i + 3])
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blo + off),
+                         "r"(lo_bits(bv[4 * i])), "r"(lo_bits(bv[4 * i + 1])), "r"(lo_bits(bv[4 * i + 2])),
+                         "r"(lo_bits(bv[4 * i + 3]))
+                         : "memory");
+          }
+          ptx::fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor-core proxy
+#pragma unroll
+          for (int e = 0; e < 16; ++e) lo[e] = lo_bits(hi[e]);
+          ptx::mbar_wait(aempty_bar(slot), ((use >> 2) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          ptx::tmem_st16(tlane + slot * A_SLOT_COLS, hi);
+          ptx::tmem_st16(tlane + slot * A_SLOT_COLS + 16, lo);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_remote(ready_leader0 + 8u * slot);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM region -> fp32 registers -> red.add =====================
+    ptx::setmaxnreg_inc<168>();
+    const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - EPI_WARP0) >> 2;  // which 128-column half of the pair tile
+    const uint32_t tempty_leader0 = ptx::mapa(tempty_bar(half, 0), 0);
+    WorkIter wi(P, worker, n_workers);
+    WorkItem it;
+    HalfRing ring;
+    float acc[NACC];
+    while (wi.next(P, it)) {
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) acc[i] = 0.0f;
+      for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
+        ring.next_chunk(half);
+        const int r = ring.r;
+        ptx::mbar_wait(tfull_bar(half, r), ring.n);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)r * ACC_COLS;
+#pragma unroll
+        for (int j = 0; j < NACC / 32; ++j) {
+          float v[32];
+          ptx::tmem_ld32(taddr + j * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_remote(tempty_leader0 + 8u * r);
+      }
+      // Tile (tm, tn), tm >= tn: element (m, n), n <= m in TILE space, is added at G[n_out][m_out];
+      // that is either triangle of G (the tile-space row order is not the design's column order),
+      // fold_symmetric_kernel adds the two triangles afterwards.  The 32 lanes of a warp are the 32
+      // rows of one row group (4 lags x 8 channels): 4 runs of 8 consecutive addresses.  Accumulator
+      // column i of half h is B row h*64 + i%64 of CTA i/64.
+      const int m_row = (it.tm * 2 + (int)rank) * TILE_ROWS + quad * 32 + lane;
+      const int m_out = __ldg(&P.out_idx[m_row]);
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) {
+        const int n_row = it.tn * 256 + (i >> 6) * TILE_ROWS + half * 64 + (i & 63);
+        const int n_out = __ldg(&P.out_idx[n_row]);
+        if (m_out >= 0 && n_out >= 0 && (it.tm > it.tn || n_row <= m_row))
+          atomicAdd(P.G + (long long)n_out * P.ldg + m_out, acc[i]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) ptx::tmem_dealloc<2>(tmem_base, TMEM_COLS);
+}
+
+}  // namespace hk

@@ -90,7 +90,8 @@ struct WorkItem {
 struct WorkIter {
   long long sc, nsc, per_sc, p, hi;
   int worker, n_workers;
-  __device__ WorkIter(const GramParams& P, int worker_, int n_workers_) {
+  template <class PT>
+  __device__ WorkIter(const PT& P, int worker_, int n_workers_) {
     worker = worker_;
     n_workers = n_workers_;
     per_sc = (long long)P.ntri * P.KS;
@@ -98,7 +99,8 @@ struct WorkIter {
     sc = -1;
     p = hi = 0;
   }
-  __device__ bool next(const GramParams& P, WorkItem& it) {
+  template <class PT>
+  __device__ bool next(const PT& P, WorkItem& it) {
     for (;;) {
       if (p >= hi) {
         if (++sc >= nsc) return false;
@@ -174,6 +176,7 @@ __device__ __forceinline__ void split_tile(uint32_t raw, uint32_t lo, int begin,
 }
 
 #include "gram_ts.cuh"
+#include "gram_halo.cuh"
 
 // CG = 1: one CTA per 128x128 tile.  CG = 2: a CTA pair (cluster of 2) per 256x256 tile, each CTA
 // staging 128 rows of A and 128 rows of B; the pair leader issues tcgen05.mma.cta_group::2.
@@ -452,6 +455,46 @@ __global__ void symmetrize_kernel(float* __restrict__ G, int64_t n, int64_t ldg,
   }
 }
 
+// The halo kernel stores every unordered pair of design columns exactly once, at G[n][m] where (m, n)
+// is its position in TILE space -- which may be either triangle of G, because the tile-space row
+// order (stream, channel group, lag group) is not the column order of the design (lag-major).  G
+// starts from zero, so G[i][j] + G[j][i] is the pair's value; it is written to both positions
+// (exactly symmetric, like numpy's syrk path).
+__global__ void fold_symmetric_kernel(float* __restrict__ G, int64_t n, int64_t ldg) {
+  __shared__ float tu[32][33], tl[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj < bi) return;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t iu = (int64_t)bi * 32 + r, ju = (int64_t)bj * 32 + threadIdx.x;
+    const int64_t il = (int64_t)bj * 32 + r, jl = (int64_t)bi * 32 + threadIdx.x;
+    tu[r][threadIdx.x] = (iu < n && ju < n) ? G[iu * ldg + ju] : 0.0f;
+    tl[r][threadIdx.x] = (il < n && jl < n) ? G[il * ldg + jl] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = threadIdx.x;
+    const int64_t iu = (int64_t)bi * 32 + r, ju = (int64_t)bj * 32 + c;
+    const int64_t il = (int64_t)bj * 32 + r, jl = (int64_t)bi * 32 + c;
+    if (bi == bj) {
+      if (iu < n && ju < n) G[iu * ldg + ju] = (r == c) ? tu[r][c] : tu[r][c] + tu[c][r];
+    } else {
+      if (iu < n && ju < n) G[iu * ldg + ju] = tu[r][c] + tl[c][r];
+      if (il < n && jl < n) G[il * ldg + jl] = tl[r][c] + tu[c][r];
+    }
+  }
+}
+
+// Padded copy of a raw stream whose rows TMA cannot address (row stride or base not a multiple of
+// 16 bytes): rows [row0, row0 + n_rows) -> dst[n_rows][ldp], channels beyond C are zero.
+__global__ void pad_rows_kernel(const float* __restrict__ src, int64_t ld, int C, int64_t row0,
+                                int64_t n_rows, float* __restrict__ dst, int ldp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * ldp) return;
+  const int64_t r = i / ldp;
+  const int c = (int)(i - r * ldp);
+  dst[i] = (c < C) ? src[(row0 + r) * ld + c] : 0.0f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-side plan.
 // ---------------------------------------------------------------------------------------------
@@ -609,6 +652,295 @@ int make_tmap(CUtensorMap* m, float* planes, int64_t Tp, int Cpad, int CB, int n
   return TD_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Halo kernel (method 4): plan, tables, launch.
+// ---------------------------------------------------------------------------------------------
+struct HaloPlan {
+  int n_streams = 0, n_seg = 0;
+  int L[2] = {0, 0}, C[2] = {0, 0}, pre[2] = {0, 0}, post[2] = {0, 0}, ncg[2] = {0, 0}, nlg[2] = {0, 0};
+  int64_t Dz = 0, Dpad = 0, NK = 0;
+  int nt = 0, ntri = 0, n_rg = 0;
+  bool staged[2] = {false, false};
+  int64_t ld_eff[2] = {0, 0}, row_lo[2] = {0, 0}, n_rows[2] = {0, 0};
+  size_t off_stage[2] = {0, 0}, off_rgs = 0, off_ktiles = 0, off_outidx = 0, total = 0;
+};
+
+int make_halo_plan(const td_stream* streams, int n_streams, const int64_t* seg_first,
+                   const int64_t* seg_keep, int n_seg, HaloPlan* pl) {
+  TD_REQUIRE(n_streams == 1 || n_streams == 2, "td_lagged_gram: n_streams must be 1 or 2, not %d", n_streams);
+  TD_REQUIRE(n_seg > 0, "td_lagged_gram: no segments");
+  pl->n_streams = n_streams;
+  pl->n_seg = n_seg;
+  int64_t n_rg = 0;
+  for (int q = 0; q < n_streams; ++q) {
+    int rc = check_stream(&streams[q], seg_keep, n_seg, "td_lagged_gram");
+    if (rc) return rc;
+    pl->L[q] = lags_of(streams[q]);
+    pl->C[q] = streams[q].channels;
+    pl->pre[q] = streams[q].pre;
+    pl->post[q] = streams[q].post;
+    pl->ncg[q] = (int)ceil_div(pl->C[q], hk::BOX_CH);
+    pl->nlg[q] = (int)ceil_div(pl->L[q], hk::RG_LAGS);
+    n_rg += (int64_t)pl->ncg[q] * pl->nlg[q];
+    pl->Dz += width_of(streams[q]);
+  }
+  pl->n_rg = (int)n_rg;
+  pl->Dpad = round_up(n_rg * hk::RG_ROWS, 2 * TILE_ROWS);
+  pl->nt = (int)(pl->Dpad / (2 * TILE_ROWS));
+  pl->ntri = pl->nt * (pl->nt + 1) / 2;
+  TD_REQUIRE(pl->Dpad < (1LL << 30), "td_lagged_gram: design too wide");
+  int64_t nk = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t f = first_of(seg_first, s);
+    TD_REQUIRE(f >= 0, "td_lagged_gram: negative first row at segment %d", s);
+    if (seg_keep[s] > f) nk += ceil_div(seg_keep[s], BK) - f / BK;
+  }
+  pl->NK = nk;
+  size_t off = 0;
+  for (int q = 0; q < n_streams; ++q) {
+    // Raw rows this call can touch: design rows [first, keep) of every used segment +- the lag halo.
+    int64_t lo = -1, hi = 0, extent = 0;
+    for (int s = 0; s < n_seg; ++s) {
+      extent = std::max(extent, streams[q].seg_start[s] + streams[q].seg_len[s]);
+      const int64_t f = first_of(seg_first, s);
+      if (seg_keep[s] <= f) continue;
+      const int64_t a = streams[q].seg_start[s] + std::max<int64_t>(f - pl->pre[q], 0);
+      const int64_t b = streams[q].seg_start[s] + std::min<int64_t>(seg_keep[s] + pl->post[q], streams[q].seg_len[s]);
+      lo = (lo < 0) ? a : std::min(lo, a);
+      hi = std::max(hi, b);
+    }
+    if (lo < 0) lo = hi = 0;
+    // TMA needs a 16-byte aligned base and row stride; otherwise the touched rows are copied once
+    // into a padded buffer (1x the touched part of the recording, not the 4 shifted planes of the
+    // earlier kernels).
+    const bool aligned = (streams[q].ld % 4 == 0) && (reinterpret_cast<uintptr_t>(streams[q].data_dev) % 16 == 0);
+    pl->staged[q] = !aligned;
+    if (aligned) {
+      pl->ld_eff[q] = streams[q].ld;
+      pl->row_lo[q] = 0;
+      pl->n_rows[q] = extent;
+    } else {
+      pl->ld_eff[q] = round_up(pl->C[q], 4);
+      pl->row_lo[q] = lo;
+      pl->n_rows[q] = hi - lo;
+      pl->off_stage[q] = off;
+      off += (size_t)round_up(std::max<int64_t>(pl->n_rows[q], 1) * pl->ld_eff[q] * (int64_t)sizeof(float), 1024);
+    }
+    TD_REQUIRE(pl->n_rows[q] < (1LL << 31) - 4096, "td_lagged_gram: more than 2^31 raw rows");
+  }
+  pl->off_rgs = off;     off += (size_t)round_up((pl->Dpad / hk::RG_ROWS) * (int64_t)sizeof(int4), 1024);
+  pl->off_ktiles = off;  off += (size_t)round_up(std::max<int64_t>(nk, 1) * 2 * (int64_t)sizeof(int4), 1024);
+  pl->off_outidx = off;  off += (size_t)round_up(pl->Dpad * (int64_t)sizeof(int), 1024);
+  pl->total = off;
+  return TD_OK;
+}
+
+int make_tmap_raw(CUtensorMap* m, const float* base, int64_t n_rows, int C, int64_t ld) {
+  EncodeTiledFn enc;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)std::max<int64_t>(n_rows, 1)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)hk::BOX_CH, (cuuint32_t)hk::BOX_FRAMES};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (raw stream) failed with CUresult %d (rows=%lld C=%d ld=%lld)", (int)r,
+              (long long)n_rows, C, (long long)ld);
+    return TD_ERR_CUDA;
+  }
+  return TD_OK;
+}
+
+int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, const int64_t* seg_keep,
+             int n_seg, float* G, int64_t ldg, const td_gram_options* opt, void* workspace,
+             size_t workspace_bytes, cudaStream_t st) {
+  HaloPlan pl;
+  int rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &pl);
+  if (rc) return rc;
+  TD_REQUIRE(ldg >= pl.Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)pl.Dz);
+  if (workspace_bytes < pl.total || !workspace) {
+    set_error("td_lagged_gram_f32: workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
+    return TD_ERR_WORKSPACE;
+  }
+  int dev = 0, sms = 0, cc_major = 0;
+  TD_CHECK_CUDA(cudaGetDevice(&dev));
+  TD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  TD_CHECK_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_major != 10) {
+    set_error("td_lagged_gram_f32: the tcgen05 kernel needs an sm_100 device (found sm_%d)", cc_major * 10);
+    return TD_ERR_UNSUPPORTED;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+
+  // ---- row groups: (stream, channel group, lag group), lag group fastest, so that the row groups of
+  // a 128-row operand tile are mostly consecutive lags of the same 8 channels and share one raw box.
+  const int n_rg_pad = (int)(pl.Dpad / hk::RG_ROWS);
+  std::vector<int4> rgs(n_rg_pad, make_int4(0, 0, 0, 0));
+  std::vector<int> out_idx(pl.Dpad, -1);
+  {
+    struct Key { int q, cg, lg; };
+    std::vector<Key> keys;
+    keys.reserve(pl.n_rg);
+    for (int q = 0; q < n_streams; ++q)
+      for (int cg = 0; cg < pl.ncg[q]; ++cg)
+        for (int lg = 0; lg < pl.nlg[q]; ++lg) keys.push_back({q, cg, lg});
+    int64_t col0[2] = {0, n_streams == 2 ? width_of(streams[0]) : 0};
+    int head = -1;                                        // index of the run head inside the CTA tile
+    for (int i = 0; i < pl.n_rg; ++i) {
+      const Key& k = keys[i];
+      const int r = i % hk::RG_PER_CTA;
+      const bool follows = r > 0 && head >= 0 && keys[i - 1].q == k.q && keys[i - 1].cg == k.cg &&
+                           keys[i - 1].lg + 1 == k.lg;
+      if (!follows) head = i;
+      const int head_r = head % hk::RG_PER_CTA;
+      const int off = head_r * hk::BOX_BYTES + (k.lg - keys[head].lg) * hk::RG_LAGS * hk::BOX_CH * 4;
+      rgs[i] = make_int4(k.q | ((follows ? 0 : 1) << 1), k.cg * hk::BOX_CH,
+                         k.lg * hk::RG_LAGS - pl.pre[k.q], off);
+      for (int kk = 0; kk < hk::RG_LAGS; ++kk)
+        for (int cc = 0; cc < hk::BOX_CH; ++cc) {
+          const int lag = k.lg * hk::RG_LAGS + kk, c = k.cg * hk::BOX_CH + cc;
+          if (lag < pl.L[k.q] && c < pl.C[k.q])
+            out_idx[(int64_t)i * hk::RG_ROWS + kk * hk::BOX_CH + cc] = (int)(col0[k.q] + (int64_t)lag * pl.C[k.q] + c);
+        }
+      if (r == hk::RG_PER_CTA - 1) head = -1;
+    }
+  }
+  std::vector<int4> ktiles;
+  ktiles.reserve((size_t)pl.NK * 2);
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t f = first_of(seg_first, s);
+    for (int64_t j = f / BK; j * BK < seg_keep[s] && seg_keep[s] > f; ++j) {
+      const int64_t t0 = j * BK;
+      const int begin = (int)std::max<int64_t>(0, f - t0);
+      const int end = (int)std::min<int64_t>(BK, seg_keep[s] - t0);
+      int row0[2] = {0, 0}, hi[2] = {0, 0};
+      int edge = 0;
+      for (int q = 0; q < n_streams; ++q) {
+        row0[q] = (int)(streams[q].seg_start[s] + t0 - pl.row_lo[q]);
+        const int64_t len = streams[q].seg_len[s];
+        hi[q] = (int)std::max<int64_t>(std::min<int64_t>(len - t0, 1 << 24), -(1 << 24));
+        if (t0 - pl.pre[q] < 0 || t0 + BK - 1 + pl.post[q] >= len) edge = 1;
+      }
+      const int neg_t0 = (int)std::max<int64_t>(-t0, -(1 << 24));
+      ktiles.push_back(make_int4(row0[0], row0[1], begin | (end << 8) | (edge << 16), neg_t0));
+      ktiles.push_back(make_int4(hi[0], hi[1], 0, 0));
+    }
+  }
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_rgs, rgs.data(), rgs.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  if (!ktiles.empty())
+    TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_ktiles, ktiles.data(), ktiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_outidx, out_idx.data(), out_idx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+
+  // ---- tensor maps over the raw streams (a padded copy only where TMA cannot address the rows) ----
+  CUtensorMap tmaps[2];
+  for (int q = 0; q < n_streams; ++q) {
+    const float* base = streams[q].data_dev;
+    if (pl.staged[q]) {
+      float* dst = reinterpret_cast<float*>(ws + pl.off_stage[q]);
+      const int64_t total = pl.n_rows[q] * pl.ld_eff[q];
+      if (total > 0) {
+        pad_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(streams[q].data_dev, streams[q].ld, pl.C[q],
+                                                                      pl.row_lo[q], pl.n_rows[q], dst, (int)pl.ld_eff[q]);
+        TD_CHECK_CUDA(cudaGetLastError());
+      }
+      base = dst;
+    }
+    rc = make_tmap_raw(&tmaps[q], base, pl.n_rows[q], pl.C[q], pl.ld_eff[q]);
+    if (rc) return rc;
+  }
+  if (n_streams == 1) tmaps[1] = tmaps[0];
+  if ((rc = debug_sync(st, "halo stage"))) return rc;
+
+  TD_CHECK_CUDA(cudaMemset2DAsync(G, (size_t)ldg * sizeof(float), 0, (size_t)pl.Dz * sizeof(float), (size_t)pl.Dz, st));
+  if (pl.NK > 0) {
+    hk::HaloParams P;
+    P.rgs = reinterpret_cast<const int4*>(ws + pl.off_rgs);
+    P.ktiles = reinterpret_cast<const int4*>(ws + pl.off_ktiles);
+    P.out_idx = reinterpret_cast<const int*>(ws + pl.off_outidx);
+    P.G = G;
+    P.ldg = ldg;
+    P.ntri = pl.ntri;
+    P.NK = pl.NK;
+    const int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 128;
+    P.chunk_kt = std::max(1, chunk_rows / BK);
+    // Superchunk: the raw frames all tiles sweep together; sized to stay L2 resident (~24 MB).
+    int64_t sc_rows = (opt && opt->superchunk_rows > 0) ? opt->superchunk_rows : 0;
+    if (sc_rows == 0) {
+      int64_t row_bytes = 0;
+      for (int q = 0; q < n_streams; ++q) row_bytes += pl.ld_eff[q] * 4;
+      sc_rows = std::max<int64_t>((24LL << 20) / row_bytes, 4096);
+    }
+    int64_t ks = std::max<int64_t>(P.chunk_kt, round_up(ceil_div(sc_rows, BK), P.chunk_kt));
+    ks = std::min<int64_t>(ks, round_up(pl.NK, P.chunk_kt));
+    P.KS = (int)ks;
+    const int64_t nsc = ceil_div(pl.NK, ks);
+    P.total_steps = nsc * pl.ntri * ks;
+    int workers = sms / 2;
+    if (opt && opt->max_ctas > 0) workers = std::max(1, std::min(workers, opt->max_ctas / 2));
+    workers = (int)std::max<int64_t>(1, std::min<int64_t>(workers, ceil_div((int64_t)pl.ntri * ks, P.chunk_kt)));
+    P.prof = nullptr;
+    const bool timed = opt && opt->reserved[0] == 1;
+    if (timed) {
+      if (!g_ev_start) {
+        TD_CHECK_CUDA(cudaEventCreate(&g_ev_start));
+        TD_CHECK_CUDA(cudaEventCreate(&g_ev_stop));
+      }
+      TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
+    }
+    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::SMEM_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers * 2);
+    cfg.blockDim = dim3(hk::NUM_THREADS);
+    cfg.dynamicSmemBytes = hk::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel, tmaps[0], tmaps[1], P));
+    TD_CHECK_CUDA(cudaGetLastError());
+    if (timed) {
+      TD_CHECK_CUDA(cudaEventRecord(g_ev_stop, st));
+      g_ev_valid = true;
+    }
+    if (debug_enabled())
+      fprintf(stderr, "[tdgram] halo launch: workers=%d Dz=%lld Dpad=%lld ntri=%d NK=%lld KS=%d chunk_kt=%d staged=%d/%d\n",
+              workers, (long long)pl.Dz, (long long)pl.Dpad, pl.ntri, (long long)pl.NK, P.KS, P.chunk_kt,
+              (int)pl.staged[0], (int)pl.staged[1]);
+    if ((rc = debug_sync(st, "halo gram kernel"))) return rc;
+  }
+  const int nb = (int)ceil_div(pl.Dz, 32);
+  fold_symmetric_kernel<<<dim3(nb, nb), dim3(32, 8), 0, st>>>(G, pl.Dz, ldg);
+  TD_CHECK_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+// Does this call run the halo kernel (method 4)?  Explicitly, or automatically (method 0) when the
+// design is wide enough for CTA pairs (>= 512 tile rows) and DEFAULT_PAIR_METHOD says so.
+constexpr int DEFAULT_PAIR_METHOD = 3;
+int use_halo(const td_stream* streams, int n_streams, const td_gram_options* opt, bool* halo) {
+  const int m = opt ? opt->method : 0;
+  const int cg = opt ? opt->cta_group : 0;
+  TD_REQUIRE(m >= 0 && m <= 4, "td_lagged_gram: unknown method %d", m);
+  TD_REQUIRE(cg >= 0 && cg <= 2, "td_lagged_gram: cta_group must be 0, 1 or 2");
+  TD_REQUIRE(!(m == 4 && cg == 1), "td_lagged_gram: method 4 (operand built on chip) needs CTA pairs");
+  *halo = (m == 4);
+  if (m == 0 && DEFAULT_PAIR_METHOD == 4 && cg != 1 && streams) {
+    int64_t rows = 0;
+    for (int q = 0; q < n_streams && q < 2; ++q)
+      rows += ceil_div(streams[q].channels, hk::BOX_CH) * hk::BOX_CH * ceil_div(lags_of(streams[q]), hk::RG_LAGS) * hk::RG_LAGS;
+    *halo = cg == 2 || rows >= 512;
+  }
+  return TD_OK;
+}
+
 }  // namespace
 }  // namespace td
 
@@ -619,10 +951,18 @@ extern "C" int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_st
                                               int n_seg, const td_gram_options* opt, size_t* bytes) {
   TD_REQUIRE(streams && seg_keep && bytes, "td_lagged_gram_workspace_bytes: null argument");
   if (opt && opt->method == 1) { *bytes = 0; return TD_OK; }
-  TD_REQUIRE(opt == nullptr || (opt->method >= 0 && opt->method <= 3),
-             "td_lagged_gram_workspace_bytes: unknown method %d", opt->method);
+  bool halo = false;
+  int rc = use_halo(streams, n_streams, opt, &halo);
+  if (rc) return rc;
+  if (halo) {
+    HaloPlan hp;
+    rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &hp);
+    if (rc) return rc;
+    *bytes = hp.total;
+    return TD_OK;
+  }
   GramPlan pl;
-  int rc = make_plan(streams, n_streams, seg_first, seg_keep, n_seg, opt, &pl);
+  rc = make_plan(streams, n_streams, seg_first, seg_keep, n_seg, opt, &pl);
   if (rc) return rc;
   *bytes = pl.total;
   return TD_OK;
@@ -661,10 +1001,13 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
     TD_REQUIRE(ldg >= Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)Dz);
     return launch_gram_simt(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, st);
   }
-  TD_REQUIRE(opt == nullptr || (opt->method >= 0 && opt->method <= 3),
-             "td_lagged_gram_f32: unknown method %d", opt->method);
+  bool halo = false;
+  int rc = use_halo(streams, n_streams, opt, &halo);
+  if (rc) return rc;
+  if (halo)
+    return run_halo(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, opt, workspace, workspace_bytes, st);
   GramPlan pl;
-  int rc = make_plan(streams, n_streams, seg_first, seg_keep, n_seg, opt, &pl);
+  rc = make_plan(streams, n_streams, seg_first, seg_keep, n_seg, opt, &pl);
   if (rc) return rc;
   // Kernel flavour: 2 = operands from shared memory, 3 = A operand from tensor memory (CTA pairs
   // only); 0 picks 3 whenever the plan uses CTA pairs.  TD_GRAM_METHOD overrides 0 (experiments).
