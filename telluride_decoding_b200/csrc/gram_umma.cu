@@ -876,8 +876,11 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
     }
     int64_t ks = std::max<int64_t>(P.chunk_kt, round_up(ceil_div(sc_rows, BK), P.chunk_kt));
     ks = std::min<int64_t>(ks, round_up(pl.NK, P.chunk_kt));
+    // Equal superchunks: a short last one would leave part of the workers idle for its whole sweep.
+    int64_t nsc = ceil_div(pl.NK, ks);
+    ks = round_up(ceil_div(pl.NK, nsc), P.chunk_kt);
+    nsc = ceil_div(pl.NK, ks);
     P.KS = (int)ks;
-    const int64_t nsc = ceil_div(pl.NK, ks);
     P.total_steps = nsc * pl.ntri * ks;
     int workers = sms / 2;
     if (opt && opt->max_ctas > 0) workers = std::max(1, std::min(workers, opt->max_ctas / 2));
@@ -924,7 +927,7 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
 
 // Does this call run the halo kernel (method 4)?  Explicitly, or automatically (method 0) when the
 // design is wide enough for CTA pairs (>= 512 tile rows) and DEFAULT_PAIR_METHOD says so.
-constexpr int DEFAULT_PAIR_METHOD = 3;
+constexpr int DEFAULT_PAIR_METHOD = 4;
 int use_halo(const td_stream* streams, int n_streams, const td_gram_options* opt, bool* halo) {
   const int m = opt ? opt->method : 0;
   const int cg = opt ? opt->cta_group : 0;

@@ -26,9 +26,10 @@ def _dataset(n, c, pre, post, batch, seed, c2=1, pre2=0, post2=0, offset=0, chun
   return ds, batches
 
 
-# (cta_group, method): 128x128 tiles; CTA pairs with the A operand in tensor memory (the default
-# for pairs); CTA pairs with both operands in shared memory.
-@pytest.mark.parametrize('cta_group,method', [(1, 0), (2, 0), (2, 2)])
+# (cta_group, method): 128x128 tiles; CTA pairs with the lagged operand built on chip from a raw tile +
+# lag halo (method 4, the default for pairs); CTA pairs with staged planes and the A operand in tensor
+# memory (3); CTA pairs with both operands in shared memory (2).
+@pytest.mark.parametrize('cta_group,method', [(1, 0), (2, 0), (2, 3), (2, 2)])
 @pytest.mark.parametrize('n,c,pre,post,batch', [
     (1000, 2, 1, 1, 100),       # C=2, L=3 (SURVEY build-plan shape)
     (1000, 3, 1, 2, 100),       # golden ridge_small shape
@@ -54,7 +55,7 @@ def test_gram_matches_oracle(n, c, pre, post, batch, cta_group, method):
   assert gpu_util.rel_fro(g, ref32) < GRAM_TOL
 
 
-@pytest.mark.parametrize('method', [0, 2])
+@pytest.mark.parametrize('method', [0, 3, 2])
 @pytest.mark.parametrize('chunk_rows,superchunk_rows', [(32, 4096), (64, 1024), (96, 2048), (128, 512)])
 def test_pair_kernels_with_short_chunks_and_many_work_items(method, chunk_rows, superchunk_rows):
   """Schedule stress for the CTA-pair kernels: one-k-tile flush periods and tiny superchunks make
@@ -76,7 +77,7 @@ def test_pair_kernels_with_short_chunks_and_many_work_items(method, chunk_rows, 
     assert gpu_util.rel_fro(got.cpu().numpy(), want.cpu().numpy()) < GRAM_TOL
 
 
-@pytest.mark.parametrize('method', [0, 2])
+@pytest.mark.parametrize('method', [0, 3, 2])
 def test_two_stream_gram_on_the_pair_kernels(method):
   """Z = [X | X2] wide enough for CTA pairs (two tensor maps, channel padding 40 -> 64 and 6 -> 8
   boxes, different contexts per stream, ragged kept rows) against the fp32 cross-check kernel."""
@@ -250,3 +251,45 @@ def test_argument_errors_surface_as_exceptions():
     ops.lagged_gram([s, s, s], [100])
   with pytest.raises(ValueError, match='weights have'):
     ops.lagged_predict(ops.Stream(x, 0, 1, [0], [100]), [100], [0], torch.zeros((3, 1), device='cuda'))
+
+
+@pytest.mark.parametrize('case', [
+    dict(lens=[2000, 1777], c=10, pre=3, post=56),                  # row stride 40 B: TMA cannot address it -> padded copy
+    dict(lens=[1500], c=306, pre=0, post=9),                        # cfg4 channel count (ld = 306)
+    dict(lens=[2200, 900], c=60, pre=2, post=9, ld_pad=4),          # strided view of a wider array, zero-copy TMA
+    dict(lens=[2048, 2048], c=32, pre=1, post=17),                  # 19 lags: last lag group has one real lag
+    dict(lens=[700, 33, 5, 1200], c=16, pre=40, post=50),           # trials shorter than the lag span; masks over several k-tiles
+    dict(lens=[3000, 2500], c=40, pre=5, post=26, keep=[2900, 2500], first=[37, 1024]),
+    dict(lens=[64] * 200, c=24, pre=4, post=19),                    # hundreds of tiny trials
+])
+def test_operand_built_on_chip_masks_and_layouts(case):
+  """Method 4 specifics against the ORACLE's lagged design: zero padding at trial edges rebuilt by
+  masks (the raw TMA box runs into the neighbouring trial; brain_data.py:448-452), row ranges,
+  channel / lag padding of the 4-lag x 8-channel row groups, unaligned and strided inputs."""
+  lens, c, pre, post = case['lens'], case['c'], case['pre'], case['post']
+  keep = case.get('keep', lens)
+  first = case.get('first')
+  rng = np.random.RandomState(c + len(lens))
+  x = (rng.randn(sum(lens), c + case.get('ld_pad', 0)) + 0.1).astype(np.float32)
+  xd = torch.as_tensor(x, device='cuda')[:, :c]
+  starts = np.concatenate(([0], np.cumsum(lens)[:-1])).tolist()
+  stream = ops.Stream(xd, pre, post, starts, lens)
+  got = ops.lagged_gram([stream], keep, options=ops.gram_options(method=4), seg_first=first)
+  parts = []
+  for s, n, k, f in zip(starts, lens, keep, first or [0] * len(lens)):
+    parts.append(ora.add_context(x[s:s + n, :c], pre, post)[f:k].astype(np.float64))
+  design = np.concatenate(parts, axis=0)
+  assert gpu_util.rel_fro(got.cpu().numpy(), design.T @ design) < GRAM_TOL
+  assert torch.equal(got, got.t())
+
+
+def test_operand_built_on_chip_two_streams_with_offset():
+  """Z = [X | X2] through method 4 with input_offset (the streams start at different raw rows and
+  have different lengths per segment, brain_data.py:466-475) and chunk edges."""
+  for offset, chunk in ((3, 1000000), (-2, 700)):
+    ds, batches = _dataset(2600, 40, 1, 14, 100, seed=9, c2=5, pre2=2, post2=1, offset=offset, chunk=chunk)
+    (w, keep), = ds.passes()
+    g = ops.lagged_gram([ds.stream('x'), ds.stream('x2')], keep,
+                        options=ops.gram_options(method=4)).cpu().numpy()
+    z = np.concatenate([gpu_util.design64(batches), gpu_util.design64(batches, 'input_2')], axis=1)
+    assert gpu_util.rel_fro(g, z.T @ z) < GRAM_TOL
