@@ -33,5 +33,9 @@ if which in ('all', 'cfg2'):
   run('cfg2 64ch x 32 lags, 460800 frames', 60, 7680, 64, 32, [3, 4], reps=5)
 if which in ('all', 'cfg4'):
   run('cfg4 slice 306ch x 100 lags, 300000 frames', 3, 100000, 306, 100, [3, 4], reps=2)
+if which == 'sc':
+  for sc in (0, 39200, 78400, 156800):
+    print('superchunk_rows', sc)
+    run('cfg4 slice 306ch x 100 lags, 300000 frames', 3, 100000, 306, 100, [4], reps=2, superchunk_rows=sc)
 if which in ('all', 'cfg3'):
   run('cfg3-like 64ch x 40 lags', 60, 7680, 64, 40, [3, 4], reps=3)
