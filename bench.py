@@ -685,6 +685,7 @@ def main():
 
   if rank != 0:
     if world > 1:
+      sharding.close_native_comms()
       dist.destroy_process_group()
     return
 
@@ -697,7 +698,7 @@ def main():
   peak = (peaks['bf16_sustained'] if long_step else peaks['bf16']) / 6.0
   roofline = dict(
       bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
-      traffic=None, kernel='ts::lagged_gram_ts_kernel', flops_per_launch=f_alg,
+      traffic=None, kernel='hk::lagged_gram_halo_kernel' if args.gram_method in (0, 4) else 'ts::lagged_gram_ts_kernel', flops_per_launch=f_alg,
       frames_per_launch=rows0, kernel_ms=kernel_ms, kernel_ms_max_over_ranks=gram_kernel_ms_max,
       peak_source='%s bf16_tflops%s / 2 (tf32 rate) / 3 (3xTF32): the %s figure, the kernel runs for '
                   '%.2f s' % (peaks['source'], '_sustained' if long_step else '',
@@ -764,8 +765,8 @@ def main():
 
   par = ('single GPU' if world == 1 else
          'one recording time-sharded x%d (sharding.shard_rows: contiguous frame ranges, cuts on 32-frame '
-         'tiles inside trials, lag halo from the same trial), 1 NCCL allreduce of the fp32 Gram + 1 of the '
-         'packed f64 thin sums' % world)
+         'tiles inside trials, lag halo from the same trial), 1 NCCL allreduce of the fp32 Gram\'s upper '
+         'triangle (libtdgram.so\'s own communicator) + 1 of the packed f64 thin sums' % world)
   line = dict(
       metric=METRIC, value=frames / (ms_per_step * 1e-3), unit='frames/s', n_gpus=world,
       steps=args.steps, warmup=warmup, ms_per_step=ms_per_step, higher_is_better=True,
@@ -781,6 +782,7 @@ def main():
       roofline=roofline, e2e=e2e, clocks=clocks, cpu_baseline=cpu, parity=parity, legs=legs)
   print(json.dumps(line))
   if world > 1:
+    sharding.close_native_comms()
     dist.destroy_process_group()
 
 

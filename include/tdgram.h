@@ -61,6 +61,10 @@ const char* td_last_error(void);
 int td_version(void);
 /* Number of SMs / compute capability of the current device (for the bench's roofline). */
 int td_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Releases what the library keeps between calls (the calling thread's timing events, cuSOLVER /
+ * cuBLAS handles, their side streams and events).  The caller's streams must be idle; the library
+ * stays usable (everything is recreated on demand). */
+int td_shutdown(void);
 
 /* ---------------------------------------------------------------------------------------
  * Lagged Gram.  Replaces the minibatch loop `sum_xtx += np.matmul(x.T, x)`
@@ -68,16 +72,23 @@ int td_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *
  * The design is Z = [X_0 | X_1 | ...] over n_streams (1 or 2) lagged streams sharing the
  * segment table; G = Z'Z, [Dz, Dz] with Dz = sum_q channels_q * (pre_q+1+post_q), full
- * symmetric, row stride ldg.  method 0: tcgen05 3xTF32 implicit-Hankel kernel (raw tiles TMA-staged,
- * hi/lo split built on chip, TMEM fp32 accumulation flushed every `chunk_rows` frames into fp32
- * registers); it picks between the two flavours that can also be forced: method 2 = both operands
- * from shared memory (the only one for cta_group 1), method 3 = A operand in tensor memory (CTA pairs
- * only; the default whenever the plan uses CTA pairs).
+ * symmetric, row stride ldg.  method 0: tcgen05 3xTF32 implicit-Hankel kernel (hi/lo split built on
+ * chip, TMEM fp32 accumulation flushed every `chunk_rows` frames into fp32 registers); it picks
+ * between the flavours that can also be forced:
+ *   4  CTA pairs; the lagged operand is built ON CHIP: one raw [32 + halo frames, 8 channels] TMA box
+ *      per 4-lag x 8-channel row group straight from the caller's time-major array, converter warps
+ *      read every row at its own lag offset, rebuild the zero padding of the trial edges with masks and
+ *      write A into tensor memory and B into swizzled shared memory.  Default for designs of >= 512
+ *      columns.  Workspace: tables only (plus one padded copy of the touched rows when the row stride
+ *      or base address is not a multiple of 16 bytes).
+ *   3  CTA pairs, A operand in tensor memory, operands fetched as (lag, channel-block) TMA boxes from
+ *      four shifted channel-major copies of the recording staged in the workspace (round-1 kernel).
+ *   2  both operands from shared memory (the only flavour for cta_group 1, i.e. narrow designs).
  * method 1: fp32 CUDA-core kernel kept as an on-device cross-check.
  * Workspace: td_lagged_gram_workspace_bytes bytes of device memory.
  * ------------------------------------------------------------------------------------- */
 typedef struct td_gram_options {
-  int32_t method;        /* 0 = tcgen05 3xTF32 (default), 1 = fp32 SIMT cross-check, 2 / 3 = force a tcgen05 flavour */
+  int32_t method;        /* 0 = tcgen05 3xTF32 (default), 1 = fp32 SIMT cross-check, 2 / 3 / 4 = force a tcgen05 flavour */
   int32_t cta_group;     /* 0 = auto, 1 = 128x128 tiles per CTA, 2 = CTA-pair 256x256 tiles */
   int32_t chunk_rows;    /* TMEM flush period in frames (0 = default 128) */
   int32_t superchunk_rows; /* L2 working-set period in frames (0 = auto) */
@@ -207,6 +218,30 @@ int td_wta_decide_u8(const double* r1_dev, const double* r2_dev, int64_t n, uint
 
 /* Utility: out[j, i] = out[i, j] for j > i (mirror the computed triangle). */
 int td_symmetrize_f32(float* G_dev, int64_t n, int64_t ldg, int from_upper, void* cuda_stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, every rank accumulates the statistics of its share of the frames
+ * (seg_first / seg_keep above) and ONE allreduce over NVLink combines them.  Replaces nothing in the
+ * reference line by line -- it has no multi-device path; the sharded pass stands in for its
+ * per-(lambda, fold) re-read of the data (regression.py:381-409).
+ * NCCL is bound at run time (dlopen of libnccl.so.2; the copy the process has already loaded if any).
+ *   td_comm_unique_id  128 bytes to hand to every rank (rank 0 makes it, the host distributes it)
+ *   td_comm_init       collective over `world` ranks; the current CUDA device is the rank's GPU
+ *   td_allreduce_sum_* in place, on `cuda_stream`
+ *   td_allreduce_sym_f32  symmetric [n, n] matrix: packs the upper triangle (n(n+1)/2 floats) into
+ *                      packed_dev, reduces that, unpacks into both triangles -- half the bytes on the wire
+ * ------------------------------------------------------------------------------------- */
+typedef struct td_comm td_comm;
+int td_comm_unique_id(void* id128);
+int td_comm_init(td_comm** comm, const void* id128, int rank, int world);
+int td_comm_destroy(td_comm* comm);
+int td_comm_nccl_version(int* version);
+int td_allreduce_sum_f32(td_comm* comm, float* buf_dev, int64_t n, void* cuda_stream);
+int td_allreduce_sum_f64(td_comm* comm, double* buf_dev, int64_t n, void* cuda_stream);
+int td_allreduce_sym_f32(td_comm* comm, float* G_dev, int64_t n, int64_t ldg, float* packed_dev,
+                         size_t packed_bytes, void* cuda_stream);
+int td_pack_upper_f32(const float* G_dev, int64_t n, int64_t ldg, float* packed_dev, void* cuda_stream);
+int td_unpack_upper_f32(const float* packed_dev, int64_t n, int64_t ldg, float* G_dev, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------
  * TFRecord / tf.train.Example reader (HOST code, no GPU needed).  Replaces

@@ -9,6 +9,7 @@ import ctypes
 import os
 
 import torch
+import torch.utils.dlpack
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libtdgram.so')
@@ -42,7 +43,9 @@ EXPORTS = (
     'td_lagged_gram_f32', 'td_last_gram_kernel_ms', 'td_lagged_gram_range_f32', 'td_lagged_thin_f64', 'td_lagged_predict_f32', 'td_lagged_rows_f32',
     'td_ridge_solve', 'td_cca_solve', 'td_column_moments_f64', 'td_windowed_corr_f32',
     'td_window_count', 'td_wta_decide_u8', 'td_symmetrize_f32', 'td_tfrecord_count',
-    'td_tfrecord_features', 'td_tfrecord_read_f32')
+    'td_tfrecord_features', 'td_tfrecord_read_f32', 'td_shutdown', 'td_comm_unique_id', 'td_comm_init',
+    'td_comm_destroy', 'td_comm_nccl_version', 'td_allreduce_sum_f32', 'td_allreduce_sum_f64',
+    'td_allreduce_sym_f32', 'td_pack_upper_f32', 'td_unpack_upper_f32')
 
 _lib = None
 
@@ -99,15 +102,26 @@ def ptr(t):
   return ctypes.c_void_p(t.data_ptr())
 
 
+def _is_dlpack_capsule(obj):
+  return type(obj).__name__ == 'PyCapsule'
+
+
 def as_device_f32(array, device=None):
-  """Anything array-like (numpy, torch, DLPack capsule provider) -> contiguous CUDA float32."""
+  """Anything array-like -> contiguous CUDA float32 tensor.
+
+  torch tensors are taken as they are; any other object that speaks the DLPack protocol
+  (`__dlpack__` / `__dlpack_device__`: cupy, jax, another framework's GPU array) and raw DLPack
+  capsules cross without a copy through torch.from_dlpack; numpy arrays and everything else go
+  through numpy (host memory, one upload)."""
   require_cuda()
+  import numpy as np
   if isinstance(array, torch.Tensor):
     t = array
-  elif hasattr(array, '__dlpack__') and not hasattr(array, '__array__'):
+  elif _is_dlpack_capsule(array):
+    t = torch.utils.dlpack.from_dlpack(array)
+  elif hasattr(array, '__dlpack__') and not isinstance(array, np.ndarray):
     t = torch.from_dlpack(array)
   else:
-    import numpy as np
     t = torch.from_numpy(np.ascontiguousarray(np.asarray(array, dtype=np.float32)))
   t = t.to(device=device or 'cuda', dtype=torch.float32)
   return t.contiguous()

@@ -39,3 +39,12 @@ extern "C" int td_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_minor) TD_CHECK_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
   return TD_OK;
 }
+
+// Releases what the library keeps between calls: the calling thread's timing events, the
+// cuSOLVER / cuBLAS handles with their side streams and events.  Call once the caller's streams
+// are idle; the library can be used again afterwards (everything is recreated on demand).
+extern "C" int td_shutdown(void) {
+  td::release_gram_events();
+  td::release_solver_handles();
+  return TD_OK;
+}

@@ -45,6 +45,10 @@ inline int64_t width_of(const td_stream& s) { return (int64_t)s.channels * lags_
 // threshold of 0 hands the memory back to the driver at every synchronisation).
 int ensure_mempool_config();
 
+// td_shutdown helpers (gram_umma.cu, solve.cu).
+void release_gram_events();
+void release_solver_handles();
+
 // Small host->device table upload into stream-ordered memory (freed with cudaFreeAsync).
 template <typename T>
 int upload(const std::vector<T>& host, T** dev, cudaStream_t st) {

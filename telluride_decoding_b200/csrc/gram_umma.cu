@@ -972,6 +972,15 @@ extern "C" int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_st
   return TD_OK;
 }
 
+namespace td {
+void release_gram_events() {
+  if (g_ev_start) cudaEventDestroy(g_ev_start);
+  if (g_ev_stop) cudaEventDestroy(g_ev_stop);
+  g_ev_start = g_ev_stop = nullptr;
+  g_ev_valid = false;
+}
+}  // namespace td
+
 extern "C" float td_last_gram_kernel_ms(void) {
   if (!g_ev_valid) return -1.0f;
   float ms = -1.0f;
@@ -1013,14 +1022,9 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
   GramPlan pl;
   rc = make_plan(streams, n_streams, seg_first, seg_keep, n_seg, opt, &pl);
   if (rc) return rc;
-  // Kernel flavour: 2 = operands from shared memory, 3 = A operand from tensor memory (CTA pairs
-  // only); 0 picks 3 whenever the plan uses CTA pairs.  TD_GRAM_METHOD overrides 0 (experiments).
+  // Kernel flavour here: 2 = operands from shared memory, 3 = A operand from tensor memory (CTA pairs
+  // only).  (Method 4 / the automatic choice for CTA pairs went to run_halo above.)
   int flavour = opt ? opt->method : 0;
-  if (flavour == 0) {
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("TD_GRAM_METHOD"); env = e ? atoi(e) : 0; }
-    flavour = (env == 2 || env == 3) ? env : 0;
-  }
   if (flavour == 0) flavour = (pl.cg == 2) ? 3 : 2;
   TD_REQUIRE(flavour == 2 || pl.cg == 2,
              "td_lagged_gram_f32: method 3 (A operand in tensor memory) needs cta_group 2");
@@ -1163,10 +1167,7 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
     if (flavour == 3) {
-      // One or two MMA issuing warps (development switch TD_TS_ISSUERS, default 2).
-      static int issuers = 0;
-      if (!issuers) { const char* e = getenv("TD_TS_ISSUERS"); issuers = (e && atoi(e) == 1) ? 1 : 2; }
-      auto kernel = (issuers == 1) ? ts::lagged_gram_ts_kernel<1> : ts::lagged_gram_ts_kernel<2>;
+      auto kernel = ts::lagged_gram_ts_kernel<2>;          // two MMA issuing warps
       TD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts::SMEM_BYTES));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(workers * 2);

@@ -34,8 +34,10 @@ struct Handles {
   cudaEvent_t ev_done[MAX_LANES] = {};
 };
 
+Handles g_handles[64];
+
 int get_handles(Handles** out) {
-  static Handles per_device[64];
+  Handles* per_device = g_handles;
   int dev = 0;
   TD_CHECK_CUDA(cudaGetDevice(&dev));
   Handles& h = per_device[dev & 63];
@@ -71,6 +73,36 @@ int get_handles(Handles** out) {
   *out = &h;
   return TD_OK;
 }
+
+}  // namespace
+
+// td_shutdown: cuSOLVER / cuBLAS handles, side streams and events of every device that used a solve.
+void release_solver_handles() {
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int dev = 0; dev < 64; ++dev) {
+    Handles& h = g_handles[dev];
+    if (!h.solver) continue;
+    cudaSetDevice(dev);
+    for (int i = 0; i < MAX_LANES; ++i) {
+      if (h.lane_solver[i]) cusolverDnDestroy(h.lane_solver[i]);
+      if (h.ev_done[i]) cudaEventDestroy(h.ev_done[i]);
+      if (h.lane_stream[i]) cudaStreamDestroy(h.lane_stream[i]);
+    }
+    for (int i = 0; i < 8; ++i) {
+      if (h.ev_panel[i]) cudaEventDestroy(h.ev_panel[i]);
+      if (h.ev_wide[i]) cudaEventDestroy(h.ev_wide[i]);
+    }
+    if (h.ev_ready) cudaEventDestroy(h.ev_ready);
+    if (h.blas_side) cublasDestroy(h.blas_side);
+    if (h.blas) cublasDestroy(h.blas);
+    cusolverDnDestroy(h.solver);
+    h = Handles();
+  }
+  cudaSetDevice(cur);
+}
+
+namespace {
 
 #define TD_CHECK_SOLVER(expr)                                                         \
   do {                                                                                \

@@ -4,12 +4,17 @@ The Gram is a sum over frames, so the frame axis is split into `world` contiguou
 ranges (cut at 32-frame tile boundaries inside a trial; the lag halo around a cut is re-read from
 the same trial, never exchanged and never zero padded).  Every rank runs the identical tile
 schedule over its share and the partial statistics are combined with one NCCL allreduce of the
-float32 Gram (plus one of the few float64 thin sums).  One process per GPU, torch.distributed
-for the plumbing (nccl on GPUs, gloo in the CPU tests).
+float32 Gram's upper triangle (plus one of the few float64 thin sums), issued through libtdgram.so's
+own communicator (td_comm_*, include/tdgram.h).  One process per GPU; torch.distributed is the
+bootstrap channel (and the whole transport in the gloo CPU tests).
 """
+
+import ctypes
 
 import torch
 import torch.distributed as dist
+
+from telluride_decoding_b200 import _lib
 
 
 def shard_rows(seg_first, seg_keep, rank, world, align=32):
@@ -59,18 +64,109 @@ def is_distributed():
   return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
-def allreduce_sum_(tensors, group=None):
-  """In-place sum over ranks of a list of tensors: float32 tensors (the Gram) are reduced as they
-  are, everything float64 is packed into ONE buffer first."""
+class NativeComm(object):
+  """NCCL communicator owned by libtdgram.so (td_comm_init / td_allreduce_* / td_comm_destroy,
+  include/tdgram.h).  torch.distributed is only the bootstrap channel for the 128-byte unique id."""
+
+  def __init__(self, group=None):
+    _lib.require_cuda()
+    self._lib = _lib.load()
+    self.rank = dist.get_rank(group)
+    self.world = dist.get_world_size(group)
+    on_gpu = dist.get_backend(group) == 'nccl'
+    ident = torch.zeros(128, dtype=torch.uint8)
+    if self.rank == 0:
+      buf = (ctypes.c_ubyte * 128)()
+      _lib.check(self._lib.td_comm_unique_id(buf))
+      ident = torch.tensor(list(buf), dtype=torch.uint8)
+    if on_gpu:
+      ident = ident.cuda()
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(ident, src=src, group=group)
+    raw = (ctypes.c_ubyte * 128)(*[int(v) for v in ident.cpu().tolist()])
+    self._comm = ctypes.c_void_p()
+    _lib.check(self._lib.td_comm_init(ctypes.byref(self._comm), raw, self.rank, self.world))
+    self._packed = None
+
+  def allreduce_(self, t):
+    """In-place sum of a contiguous float32 / float64 CUDA tensor."""
+    if not (t.is_cuda and t.is_contiguous()):
+      raise ValueError('NativeComm.allreduce_ needs a contiguous CUDA tensor')
+    fn = {torch.float32: self._lib.td_allreduce_sum_f32,
+          torch.float64: self._lib.td_allreduce_sum_f64}[t.dtype]
+    with torch.cuda.device(t.device):
+      _lib.check(fn(self._comm, _lib.ptr(t), ctypes.c_int64(t.numel()), _lib.current_stream_ptr()))
+    return t
+
+  def allreduce_sym_(self, g):
+    """In-place sum of a symmetric float32 [n, n] CUDA matrix; only the upper triangle travels."""
+    n = int(g.shape[0])
+    if g.dim() != 2 or g.shape[1] != n or g.dtype != torch.float32 or g.stride(1) != 1:
+      raise ValueError('NativeComm.allreduce_sym_ needs a square float32 matrix with unit column stride')
+    need = n * (n + 1) // 2
+    if self._packed is None or self._packed.numel() < need or self._packed.device != g.device:
+      self._packed = None
+      self._packed = torch.empty(need, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+      _lib.check(self._lib.td_allreduce_sym_f32(
+          self._comm, _lib.ptr(g), ctypes.c_int64(n), ctypes.c_int64(g.stride(0)),
+          _lib.ptr(self._packed), ctypes.c_size_t(self._packed.numel() * 4), _lib.current_stream_ptr()))
+    return g
+
+  def release_buffers(self):
+    self._packed = None
+
+  def close(self):
+    if self._comm:
+      _lib.check(self._lib.td_comm_destroy(self._comm))
+      self._comm = ctypes.c_void_p()
+    self._packed = None
+
+
+_native_comms = {}
+
+
+def native_comm(group=None):
+  """The library-owned NCCL communicator of `group` (created on first use, collectively), or None
+  when the job is not distributed over GPUs."""
+  if not is_distributed() or not torch.cuda.is_available() or dist.get_backend(group) != 'nccl':
+    return None
+  key = id(group) if group is not None else 0
+  if key not in _native_comms:
+    _native_comms[key] = NativeComm(group)
+  return _native_comms[key]
+
+
+def close_native_comms():
+  for comm in _native_comms.values():
+    comm.close()
+  _native_comms.clear()
+
+
+def allreduce_sum_(tensors, group=None, symmetric=()):
+  """In-place sum over ranks of a list of tensors.  float32 tensors (the Gram) are reduced as they
+  are -- those also listed in `symmetric` (square, symmetric) send their upper triangle only --
+  everything float64 is packed into ONE buffer first.  On GPUs the collectives run in
+  libtdgram.so's own NCCL communicator; on CPU tensors (gloo tests) through torch.distributed."""
   if not is_distributed():
     return tensors
+  comm = native_comm(group) if all(t.is_cuda for t in tensors) else None
   small = [t for t in tensors if t.dtype == torch.float64]
   for t in tensors:
-    if t.dtype != torch.float64:
+    if t.dtype == torch.float64:
+      continue
+    if comm is not None and any(t is s for s in symmetric):
+      comm.allreduce_sym_(t)
+    elif comm is not None and t.is_contiguous():
+      comm.allreduce_(t)
+    else:
       dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
   if small:
     flat = torch.cat([t.reshape(-1) for t in small])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if comm is not None:
+      comm.allreduce_(flat)
+    else:
+      dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     o = 0
     for t in small:
       t.copy_(flat[o:o + t.numel()].reshape(t.shape))
@@ -149,6 +245,6 @@ def sharded_regression_stats(dataset, gram_options=None, workspace=None, group=N
       gram = gram + g * weight
       xtv, vtv = xtv + t * weight, vtv + v * weight
   mark('stats_done')
-  allreduce_sum_([gram, xtv, vtv], group=group)
+  allreduce_sum_([gram, xtv, vtv], group=group, symmetric=(gram,))
   mark('allreduce_done')
   return brain_model.RegressionStats(gram, xtv, vtv)

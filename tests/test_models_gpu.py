@@ -358,3 +358,41 @@ def test_pinned_host_trials_are_uploaded_in_chunks_and_give_the_same_fit():
   ref = brain_model.BrainModelLinearRegression(ds_r, regularization_lambda=0.1)
   ref.fit(ds_r)
   assert gpu_util.rel_fro(model.weight_matrices[0], ref.weight_matrices[0]) < 1e-5
+
+
+def test_inputs_cross_by_dlpack_and_shutdown_releases_handles():
+  """north_star: tensors cross the boundary by DLPack.  A non-torch producer (an object exposing only
+  `__dlpack__` / `__dlpack_device__`) and a raw DLPack capsule reach the kernels without a host
+  copy and give the same fit as the numpy path; td_shutdown releases the library's handles and the
+  next call recreates them."""
+  from telluride_decoding_b200 import _lib, brain_data
+
+  class Producer(object):          # what cupy / jax arrays look like to a consumer
+    def __init__(self, t):
+      self._t = t
+
+    def __dlpack__(self, stream=None):
+      return self._t.__dlpack__(stream=stream)
+
+    def __dlpack_device__(self):
+      return self._t.__dlpack_device__()
+
+  rng = np.random.RandomState(3)
+  x = rng.randn(2000, 6).astype(np.float32)
+  y = (x[:, :1] - 0.5 * x[:, 2:3] + 0.1 * rng.randn(2000, 1)).astype(np.float32)
+  xd, yd = torch.as_tensor(x, device='cuda'), torch.as_tensor(y, device='cuda')
+  got = _lib.as_device_f32(Producer(xd))
+  assert got.data_ptr() == xd.data_ptr()              # zero copy
+  cap = torch.utils.dlpack.to_dlpack(yd)
+  assert _lib.as_device_f32(cap).data_ptr() == yd.data_ptr()
+  weights = []
+  for xin, yin in ((x, y), (Producer(xd), torch.utils.dlpack.to_dlpack(yd))):
+    bd = brain_data.TestBrainData('input_1', 'output', 100.0, pre_context=1, post_context=2,
+                                  final_batch_size=100, shuffle_buffer_size=0)
+    bd.preserve_test_data(xin, yin)
+    ds = bd.create_dataset('train')
+    model = brain_model.BrainModelLinearRegression(ds, regularization_lambda=0.01)
+    model.fit(ds)
+    weights.append(model.w_estimate.copy())
+    assert _lib.load().td_shutdown() == 0             # handles are recreated on the next solve
+  np.testing.assert_array_equal(weights[0], weights[1])

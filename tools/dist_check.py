@@ -27,5 +27,6 @@ et = float(torch.linalg.norm(shard.xtv - full.xtv) / torch.linalg.norm(full.xtv)
 ew = float(torch.linalg.norm(w1 - w2) / torch.linalg.norm(w1))
 ok = eg < 5e-6 and et < 1e-12 and ew < 1e-4 and shard.n == full.n
 print('rank %d/%d: gram %.2e thin %.2e weights %.2e n %d -> %s' % (rank, world, eg, et, ew, shard.n, 'OK' if ok else 'FAIL'))
+sharding.close_native_comms()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
