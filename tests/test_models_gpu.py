@@ -395,4 +395,5 @@ def test_inputs_cross_by_dlpack_and_shutdown_releases_handles():
     model.fit(ds)
     weights.append(model.w_estimate.copy())
     assert _lib.load().td_shutdown() == 0             # handles are recreated on the next solve
-  np.testing.assert_array_equal(weights[0], weights[1])
+  # (the Gram's partial tiles are combined with fp32 atomics, so two runs differ in the last bits)
+  np.testing.assert_allclose(weights[0], weights[1], rtol=1e-4, atol=1e-6)
