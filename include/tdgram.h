@@ -106,6 +106,13 @@ int td_lagged_gram_f32(const td_stream* streams, int n_streams,
                        const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
                        float* G_dev, int64_t ldg, const td_gram_options* opt,
                        void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
+/* One Gram PER SEGMENT from one launch (method 4): G_dev [n_seg][Dz][ldg].  What leave-one-trial-out
+ * needs (regression.py:197-214, infer.py: each held-out trial's fold = total - trial): every
+ * segment must span the same, non-zero number of 32-frame k-tiles. */
+int td_lagged_gram_batched_f32(const td_stream* streams, int n_streams,
+                               const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
+                               float* G_dev, int64_t ldg, const td_gram_options* opt,
+                               void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
 /* Device time (ms) of the most recent tcgen05 Gram kernel launched by this thread with
  * opt->reserved[0] = 1 (CUDA events on the caller's stream; synchronises on the stop event).
  * Negative if none was recorded.  For the bench's roofline line. */
@@ -123,6 +130,11 @@ float td_last_gram_kernel_ms(void);
 int td_lagged_thin_f64(const td_stream* x, const td_stream* v,
                        const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
                        double* xtv_dev, double* vtv_dev, void* cuda_stream);
+
+/* The same per segment: xtv_dev [n_seg][Dx][Q], vtv_dev [n_seg][Q][Q]. */
+int td_lagged_thin_per_segment_f64(const td_stream* x, const td_stream* v,
+                                   const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
+                                   double* xtv_dev, double* vtv_dev, void* cuda_stream);
 
 /* Gram over the row ranges [seg_first[s], seg_keep[s]) of each segment (seg_first NULL = 0), on
  * CUDA cores in fp32 with float64 carry.  Used for the small leave-one-out corrections: the
@@ -144,6 +156,13 @@ int td_lagged_predict_f32(const td_stream* x, const int64_t* seg_keep, const int
                           const float* mean_dev, int Dy, float* out_dev, int64_t ldo,
                           void* cuda_stream);
 
+/* The same with ONE weight matrix per segment: W_dev [n_seg][Dx][Dy], bias_dev [n_seg][Dy] or NULL
+ * (every held-out trial is predicted by the model that never saw it). */
+int td_lagged_predict_per_segment_f32(const td_stream* x, const int64_t* seg_keep,
+                                      const int64_t* out_row, int n_seg, const float* W_dev,
+                                      const float* bias_dev, int Dy, float* out_dev, int64_t ldo,
+                                      void* cuda_stream);
+
 /* The lagged rows themselves (compatibility iterator / tests only; brain_data.py:453-455). */
 int td_lagged_rows_f32(const td_stream* x, const int64_t* seg_keep, const int64_t* out_row,
                        int n_seg, float* out_dev, int64_t ldo, void* cuda_stream);
@@ -163,6 +182,14 @@ int td_lagged_rows_f32(const td_stream* x, const int64_t* seg_keep, const int64_
 int td_ridge_solve(const double* G_aug_dev, const double* C_aug_dev, int Da, int Dy, double n,
                    const double* lambdas, int n_lambda, int method, float* W_out_dev,
                    void* cuda_stream);
+
+/* td_ridge_solve_batched: n_batch DIFFERENT systems (leave-one-trial-out folds), one lambda each, in
+ * one batched blocked Cholesky: G_aug_dev [n_batch][Da][Da], C_aug_dev [n_batch][Da][Dy] double
+ * (un-normalised sums), n and lambdas HOST arrays [n_batch]; W_out_dev [n_batch][Da][Dy] float32.
+ * A system that is not positive definite is an error.  Synchronises the stream. */
+int td_ridge_solve_batched(const double* G_aug_dev, const double* C_aug_dev, int Da, int Dy,
+                           const double* n, const double* lambdas, int n_batch, float* W_out_dev,
+                           void* cuda_stream);
 
 /* td_cca_solve: cca.py:337-367.  Inputs are raw sums (double): Gxx [D1,D1], Gyy [D2,D2],
  * Gxy [D1,D2], sum_x [D1], sum_y [D2]; n_frames = total rows, n_norm = n_batches*n_row - 1.

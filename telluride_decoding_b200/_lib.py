@@ -45,7 +45,8 @@ EXPORTS = (
     'td_window_count', 'td_wta_decide_u8', 'td_symmetrize_f32', 'td_tfrecord_count',
     'td_tfrecord_features', 'td_tfrecord_read_f32', 'td_shutdown', 'td_comm_unique_id', 'td_comm_init',
     'td_comm_destroy', 'td_comm_nccl_version', 'td_allreduce_sum_f32', 'td_allreduce_sum_f64',
-    'td_allreduce_sym_f32', 'td_pack_upper_f32', 'td_unpack_upper_f32')
+    'td_allreduce_sym_f32', 'td_pack_upper_f32', 'td_unpack_upper_f32', 'td_lagged_gram_batched_f32',
+    'td_lagged_thin_per_segment_f64', 'td_lagged_predict_per_segment_f32', 'td_ridge_solve_batched')
 
 _lib = None
 

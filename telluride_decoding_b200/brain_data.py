@@ -232,8 +232,11 @@ class LaggedDataset(object):
     return torch.from_numpy(idx).to(self.x.device)
 
   def unlagged_rows(self, which):
-    """Rows of an un-lagged stream ('y' or 'a') in file-major order, [total_rows, channels]."""
+    """Rows of an un-lagged stream ('y', 'a', or 'x2' when it has no context) in file-major order,
+    [total_rows, channels]."""
     s = self.stream(which)
+    if s.pre or s.post:
+      raise ValueError('stream %s has temporal context; its rows are not a slice of the raw data' % which)
     parts = [s.data[st:st + n] for st, n in zip(s.seg_start, self.seg_rows)]
     return torch.cat(parts, dim=0) if len(parts) != 1 else parts[0]
 

@@ -58,6 +58,7 @@ struct HaloParams {
   const int* out_idx;     // [Dpad] tile-space row -> row/col of G, -1 for padding
   float* G;
   long long ldg;
+  long long batch_stride; // 0: one Gram; else superchunk sc (= one segment) accumulates into G + sc * batch_stride
   int ntri;
   long long NK;
   int KS;
@@ -372,12 +373,13 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
       // column i of half h is B row h*64 + i%64 of CTA i/64.
       const int m_row = (it.tm * 2 + (int)rank) * TILE_ROWS + quad * 32 + lane;
       const int m_out = __ldg(&P.out_idx[m_row]);
+      float* Gout = P.G + (it.kt_begin / P.KS) * P.batch_stride;      // batched: one Gram per superchunk
 #pragma unroll
       for (int i = 0; i < NACC; ++i) {
         const int n_row = it.tn * 256 + (i >> 6) * TILE_ROWS + half * 64 + (i & 63);
         const int n_out = __ldg(&P.out_idx[n_row]);
         if (m_out >= 0 && n_out >= 0 && (it.tm > it.tn || n_row <= m_row))
-          atomicAdd(P.G + (long long)n_out * P.ldg + m_out, acc[i]);
+          atomicAdd(Gout + (long long)n_out * P.ldg + m_out, acc[i]);
       }
     }
   }

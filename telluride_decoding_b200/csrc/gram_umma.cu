@@ -460,10 +460,11 @@ __global__ void symmetrize_kernel(float* __restrict__ G, int64_t n, int64_t ldg,
 // order (stream, channel group, lag group) is not the column order of the design (lag-major).  G
 // starts from zero, so G[i][j] + G[j][i] is the pair's value; it is written to both positions
 // (exactly symmetric, like numpy's syrk path).
-__global__ void fold_symmetric_kernel(float* __restrict__ G, int64_t n, int64_t ldg) {
+__global__ void fold_symmetric_kernel(float* __restrict__ G, int64_t n, int64_t ldg, int64_t batch_stride) {
   __shared__ float tu[32][33], tl[32][33];
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bj < bi) return;
+  G += (int64_t)blockIdx.z * batch_stride;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int64_t iu = (int64_t)bi * 32 + r, ju = (int64_t)bj * 32 + threadIdx.x;
     const int64_t il = (int64_t)bj * 32 + r, jl = (int64_t)bi * 32 + threadIdx.x;
@@ -755,12 +756,27 @@ int make_tmap_raw(CUtensorMap* m, const float* base, int64_t n_rows, int C, int6
   return TD_OK;
 }
 
+// batched: one Gram per segment, G [n_seg][Dz][ldg]; every segment must span the same number of
+// k-tiles (then a superchunk is exactly one segment and the epilogue picks the output by superchunk).
 int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, const int64_t* seg_keep,
              int n_seg, float* G, int64_t ldg, const td_gram_options* opt, void* workspace,
-             size_t workspace_bytes, cudaStream_t st) {
+             size_t workspace_bytes, cudaStream_t st, bool batched = false) {
   HaloPlan pl;
   int rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &pl);
   if (rc) return rc;
+  int64_t kt_per_seg = 0;
+  if (batched) {
+    for (int s = 0; s < n_seg; ++s) {
+      const int64_t f = first_of(seg_first, s);
+      const int64_t k = seg_keep[s] > f ? ceil_div(seg_keep[s], BK) - f / BK : 0;
+      if (s == 0) kt_per_seg = k;
+      if (k != kt_per_seg || k == 0) {
+        set_error("td_lagged_gram_batched_f32: segment %d spans %lld k-tiles, segment 0 spans %lld (one launch needs equal, non-empty segments)",
+                  s, (long long)k, (long long)kt_per_seg);
+        return TD_ERR_UNSUPPORTED;
+      }
+    }
+  }
   TD_REQUIRE(ldg >= pl.Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)pl.Dz);
   if (workspace_bytes < pl.total || !workspace) {
     set_error("td_lagged_gram_f32: workspace has %zu bytes, %zu needed", workspace_bytes, pl.total);
@@ -855,9 +871,11 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
   if (n_streams == 1) tmaps[1] = tmaps[0];
   if ((rc = debug_sync(st, "halo stage"))) return rc;
 
-  TD_CHECK_CUDA(cudaMemset2DAsync(G, (size_t)ldg * sizeof(float), 0, (size_t)pl.Dz * sizeof(float), (size_t)pl.Dz, st));
+  const int64_t n_out = batched ? n_seg : 1;
+  TD_CHECK_CUDA(cudaMemset2DAsync(G, (size_t)ldg * sizeof(float), 0, (size_t)pl.Dz * sizeof(float), (size_t)(pl.Dz * n_out), st));
   if (pl.NK > 0) {
     hk::HaloParams P;
+    P.batch_stride = batched ? pl.Dz * ldg : 0;
     P.rgs = reinterpret_cast<const int4*>(ws + pl.off_rgs);
     P.ktiles = reinterpret_cast<const int4*>(ws + pl.off_ktiles);
     P.out_idx = reinterpret_cast<const int*>(ws + pl.off_outidx);
@@ -881,6 +899,7 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
     int64_t nsc = ceil_div(pl.NK, ks);
     ks = round_up(ceil_div(pl.NK, nsc), P.chunk_kt);
     nsc = ceil_div(pl.NK, ks);
+    if (batched) { ks = kt_per_seg; nsc = n_seg; }
     P.KS = (int)ks;
     P.total_steps = nsc * pl.ntri * ks;
     int workers = sms / 2;
@@ -921,8 +940,11 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
     if ((rc = debug_sync(st, "halo gram kernel"))) return rc;
   }
   const int nb = (int)ceil_div(pl.Dz, 32);
-  fold_symmetric_kernel<<<dim3(nb, nb), dim3(32, 8), 0, st>>>(G, pl.Dz, ldg);
-  TD_CHECK_CUDA(cudaGetLastError());
+  for (int64_t o0 = 0; o0 < n_out; o0 += 32768) {
+    const unsigned nz = (unsigned)std::min<int64_t>(32768, n_out - o0);
+    fold_symmetric_kernel<<<dim3(nb, nb, nz), dim3(32, 8), 0, st>>>(G + o0 * pl.Dz * ldg, pl.Dz, ldg, pl.Dz * ldg);
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
   return TD_OK;
 }
 
@@ -1235,4 +1257,17 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
     if ((rc = debug_sync(st, "gram kernel"))) return rc;
   }
   return td_symmetrize_f32(G, pl.Dz, ldg, /*from_upper=*/1, stream);
+}
+
+extern "C" int td_lagged_gram_batched_f32(const td_stream* streams, int n_streams, const int64_t* seg_first,
+                                          const int64_t* seg_keep, int n_seg, float* G, int64_t ldg,
+                                          const td_gram_options* opt, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  TD_REQUIRE(streams && seg_keep && G, "td_lagged_gram_batched_f32: null argument");
+  td_gram_options o = opt ? *opt : td_gram_options{};
+  TD_REQUIRE(o.method == 0 || o.method == 4, "td_lagged_gram_batched_f32: only method 4 (0 = default) writes per-segment Grams");
+  o.method = 4;
+  o.cta_group = 2;
+  return run_halo(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, &o, workspace, workspace_bytes,
+                  (cudaStream_t)stream, /*batched=*/true);
 }

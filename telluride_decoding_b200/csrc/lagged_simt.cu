@@ -159,7 +159,7 @@ __device__ __forceinline__ void thin_fast(const float* __restrict__ xs, const fl
 __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, int has_v, int Q,
                                                    const int64_t* seg_keep, const int* blk_seg,
                                                    const int64_t* blk_t0, double* xtv_slices,
-                                                   double* vtv) {
+                                                   double* vtv, int per_segment) {
   extern __shared__ float thin_sm[];
   const int seg = blk_seg[blockIdx.x];
   const int64_t t0 = blk_t0[blockIdx.x];
@@ -189,7 +189,10 @@ __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, i
   }
   __syncthreads();
   const int64_t Dx = (int64_t)x.channels * L;
-  double* xtv = xtv_slices + (size_t)((blockIdx.x + blockIdx.y) % THIN_SLICES) * Dx * Q;
+  // One output per segment (leave-one-trial-out statistics), or 64 slices that a second kernel adds up.
+  double* xtv = per_segment ? xtv_slices + (size_t)seg * Dx * Q
+                            : xtv_slices + (size_t)((blockIdx.x + blockIdx.y) % THIN_SLICES) * Dx * Q;
+  if (per_segment) vtv += (size_t)seg * Q * Q;
   // Thread = (channel, group of THIN_KT consecutive lags): the frames x[r+k .. r+k+KT) slide
   // through registers, so one shared-memory load of x and Q of the targets feed KT*Q FMAs.
   const int n_kg = (L + THIN_KT - 1) / THIN_KT;
@@ -261,8 +264,11 @@ __global__ void __launch_bounds__(256) predict_kernel(StreamView x, const int64_
                                                       const float* __restrict__ W,
                                                       const float* __restrict__ bias,
                                                       const float* __restrict__ mean, int Dy,
-                                                      float* out, int64_t ldo) {
+                                                      float* out, int64_t ldo, int64_t w_seg_stride,
+                                                      int64_t b_seg_stride) {
   const int seg = blk_seg[blockIdx.x];
+  W += (int64_t)seg * w_seg_stride;            // one weight matrix per segment (leave-one-trial-out), or shared
+  if (bias) bias += (int64_t)seg * b_seg_stride;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t keep = seg_keep[seg];
   const int64_t t0 = blk_t0[blockIdx.x] + (int64_t)warp * PR_ROWS;
@@ -434,9 +440,25 @@ extern "C" int td_lagged_gram_range_f32(const td_stream* streams, int n_streams,
   return launch_gram_simt(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, (cudaStream_t)stream);
 }
 
+static int thin_impl(const td_stream* x, const td_stream* v, const int64_t* seg_first,
+                     const int64_t* seg_keep, int n_seg, double* xtv, double* vtv, void* stream,
+                     int per_segment);
+
 extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const int64_t* seg_first,
                                   const int64_t* seg_keep, int n_seg, double* xtv, double* vtv,
                                   void* stream) {
+  return thin_impl(x, v, seg_first, seg_keep, n_seg, xtv, vtv, stream, 0);
+}
+
+extern "C" int td_lagged_thin_per_segment_f64(const td_stream* x, const td_stream* v,
+                                              const int64_t* seg_first, const int64_t* seg_keep,
+                                              int n_seg, double* xtv, double* vtv, void* stream) {
+  return thin_impl(x, v, seg_first, seg_keep, n_seg, xtv, vtv, stream, 1);
+}
+
+static int thin_impl(const td_stream* x, const td_stream* v, const int64_t* seg_first,
+                     const int64_t* seg_keep, int n_seg, double* xtv, double* vtv, void* stream,
+                     int per_segment) {
   cudaStream_t st = (cudaStream_t)stream;
   TD_REQUIRE(x && seg_keep && xtv && vtv && n_seg > 0, "td_lagged_thin_f64: null argument");
   int rc = check_stream(x, seg_keep, n_seg, "td_lagged_thin_f64");
@@ -465,8 +487,9 @@ extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const 
   rc = make_blocks(seg_keep, n_seg, THIN_TB, tabs, &blk_seg, &blk_t0, &nblk, seg_first);
   if (rc) return rc;
   const int64_t Dx = width_of(*x);
-  TD_CHECK_CUDA(cudaMemsetAsync(xtv, 0, (size_t)Dx * Q * sizeof(double), st));
-  TD_CHECK_CUDA(cudaMemsetAsync(vtv, 0, (size_t)Q * Q * sizeof(double), st));
+  const size_t n_out = per_segment ? (size_t)n_seg : 1;
+  TD_CHECK_CUDA(cudaMemsetAsync(xtv, 0, n_out * Dx * Q * sizeof(double), st));
+  TD_CHECK_CUDA(cudaMemsetAsync(vtv, 0, n_out * Q * Q * sizeof(double), st));
   if (nblk > 0) {
     const int L = lags_of(*x);
     const size_t smem = ((size_t)(THIN_TB + L - 1) * THIN_CB + (size_t)THIN_TB * Q) * sizeof(float);
@@ -481,23 +504,53 @@ extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const 
       explicit Slices(cudaStream_t s) : st(s) {}
       ~Slices() { if (p) cudaFreeAsync(p, st); }
     } slices(st);
-    const size_t slice_bytes = (size_t)THIN_SLICES * Dx * Q * sizeof(double);
-    TD_CHECK_CUDA(cudaMallocAsync((void**)&slices.p, slice_bytes, st));
-    TD_CHECK_CUDA(cudaMemsetAsync(slices.p, 0, slice_bytes, st));
     TD_CHECK_CUDA(cudaFuncSetAttribute(thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)nblk, (unsigned)ceil_div(x->channels, THIN_CB));
-    thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, slices.p, vtv);
-    TD_CHECK_CUDA(cudaGetLastError());
-    thin_reduce_kernel<<<(unsigned)ceil_div(Dx * Q, 256), 256, 0, st>>>(slices.p, xtv, Dx * Q);
-    TD_CHECK_CUDA(cudaGetLastError());
+    if (per_segment) {
+      thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, xtv, vtv, 1);
+      TD_CHECK_CUDA(cudaGetLastError());
+    } else {
+      const size_t slice_bytes = (size_t)THIN_SLICES * Dx * Q * sizeof(double);
+      TD_CHECK_CUDA(cudaMallocAsync((void**)&slices.p, slice_bytes, st));
+      TD_CHECK_CUDA(cudaMemsetAsync(slices.p, 0, slice_bytes, st));
+      thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, slices.p, vtv, 0);
+      TD_CHECK_CUDA(cudaGetLastError());
+      thin_reduce_kernel<<<(unsigned)ceil_div(Dx * Q, 256), 256, 0, st>>>(slices.p, xtv, Dx * Q);
+      TD_CHECK_CUDA(cudaGetLastError());
+    }
   }
   return TD_OK;
+}
+
+namespace td {
+namespace {
+int predict_impl(const td_stream* x, const int64_t* seg_keep, const int64_t* out_row, int n_seg, const float* W,
+                 const float* bias, const float* mean, int Dy, float* out, int64_t ldo, void* stream,
+                 int64_t w_seg_stride, int64_t b_seg_stride);
+}
 }
 
 extern "C" int td_lagged_predict_f32(const td_stream* x, const int64_t* seg_keep,
                                      const int64_t* out_row, int n_seg, const float* W,
                                      const float* bias, const float* mean, int Dy, float* out,
                                      int64_t ldo, void* stream) {
+  return predict_impl(x, seg_keep, out_row, n_seg, W, bias, mean, Dy, out, ldo, stream, 0, 0);
+}
+
+extern "C" int td_lagged_predict_per_segment_f32(const td_stream* x, const int64_t* seg_keep,
+                                                 const int64_t* out_row, int n_seg, const float* W,
+                                                 const float* bias, int Dy, float* out, int64_t ldo,
+                                                 void* stream) {
+  TD_REQUIRE(x != nullptr, "td_lagged_predict_per_segment_f32: null argument");
+  return predict_impl(x, seg_keep, out_row, n_seg, W, bias, nullptr, Dy, out, ldo, stream,
+                      width_of(*x) * (int64_t)Dy, Dy);
+}
+
+namespace td {
+namespace {
+int predict_impl(const td_stream* x, const int64_t* seg_keep, const int64_t* out_row, int n_seg, const float* W,
+                 const float* bias, const float* mean, int Dy, float* out, int64_t ldo, void* stream,
+                 int64_t w_seg_stride, int64_t b_seg_stride) {
   cudaStream_t st = (cudaStream_t)stream;
   TD_REQUIRE(x && seg_keep && out_row && W && out && n_seg > 0, "td_lagged_predict_f32: null argument");
   TD_REQUIRE(Dy >= 1 && Dy <= 64 && ldo >= Dy, "td_lagged_predict_f32: Dy=%d ldo=%lld out of range", Dy, (long long)ldo);
@@ -515,11 +568,13 @@ extern "C" int td_lagged_predict_f32(const td_stream* x, const int64_t* seg_keep
   rc = make_blocks(seg_keep, n_seg, rows_per_block, tabs, &blk_seg, &blk_t0, &nblk);
   if (rc) return rc;
   if (nblk > 0) {
-    predict_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, W, bias, mean, Dy, out, ldo);
+    predict_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, W, bias, mean, Dy, out, ldo, w_seg_stride, b_seg_stride);
     TD_CHECK_CUDA(cudaGetLastError());
   }
   return TD_OK;
 }
+}  // namespace
+}  // namespace td
 
 extern "C" int td_lagged_rows_f32(const td_stream* x, const int64_t* seg_keep, const int64_t* out_row,
                                   int n_seg, float* out, int64_t ldo, void* stream) {

@@ -267,6 +267,25 @@ __global__ void chol_build(const double* __restrict__ A0, const double* __restri
   Ml[c * Nt + r] = v;
 }
 
+// The same working matrices for a batch of DIFFERENT systems (leave-one-trial-out folds): entry b is
+// [[G_b / n_b + lambda_b I, .], [C_b' / n_b, .]] from row-major G [batch][Da][Da] (symmetric) and
+// C [batch][Da][Dy].
+__global__ void chol_build_folds(const double* __restrict__ G, const double* __restrict__ C, int Da, int Dy,
+                                 const double* __restrict__ inv_n_dev, const double* __restrict__ lambdas_dev,
+                                 int l0, double* __restrict__ M) {
+  const long long Nt = Da + Dy;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nt * Da) return;
+  const long long c = i / Nt, r = i - c * Nt;
+  const int b = l0 + blockIdx.y;
+  double* Ml = M + (size_t)blockIdx.y * Nt * Nt;
+  const double inv_n = inv_n_dev[b];
+  double v;
+  if (r < Da) v = G[(size_t)b * Da * Da + c * Da + r] * inv_n + (r == c ? lambdas_dev[b] : 0.0);
+  else v = C[(size_t)b * Da * Dy + c * Dy + (r - Da)] * inv_n;
+  Ml[c * Nt + r] = v;
+}
+
 // Factor the jb x jb diagonal block at (j0, j0) of every working matrix M, store the factor (lower)
 // at the same place of L and write the inverse of the factor, Linv [batch][64][64] column-major (zero padded), for the panel solve.
 // info[l] = first non-positive pivot (1-based, global column) or unchanged.
@@ -466,9 +485,11 @@ __global__ void chol_store(const double* __restrict__ Y, int Da, int Dy, float* 
   W[(size_t)blockIdx.y * Da * Dy + i] = (float)Y[((size_t)blockIdx.y * Dy + q) * Da + r];
 }
 
+// folds_inv_n != nullptr: A0 / B0 are the batched fold inputs G [n_lambda][Da][Da], C [n_lambda][Da][Dy]
+// (row-major, un-normalised) and folds_inv_n [n_lambda] (host) their 1 / n.
 int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const double* A0, const double* B0,
                            int Da, int Dy, const double* lambdas, int n_lambda, float* W_out,
-                           std::vector<int>* failed) {
+                           std::vector<int>* failed, const double* folds_inv_n = nullptr) {
   int rc;
   const long long Nt = (long long)Da + Dy;
   const size_t per = (size_t)Nt * Nt * sizeof(double);
@@ -483,6 +504,11 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
     return rc;
   TD_CHECK_CUDA(cudaMemcpyAsync(lam_dev, lambdas, n_lambda * sizeof(double), cudaMemcpyHostToDevice, st));
   TD_CHECK_CUDA(cudaMemsetAsync(info, 0, n_lambda * sizeof(int), st));
+  double* inv_n_dev = nullptr;
+  if (folds_inv_n) {
+    if ((rc = sc.get(n_lambda, &inv_n_dev))) return rc;
+    TD_CHECK_CUDA(cudaMemcpyAsync(inv_n_dev, folds_inv_n, n_lambda * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
   const double minus_one = -1.0, one = 1.0, zero = 0.0;
   const int potf2_smem = (2 * CH_NB * (CH_NB + 1) + CH_NB * (CH_SB + 1)) * (int)sizeof(double);
   TD_CHECK_CUDA(cudaFuncSetAttribute(chol_potf2, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem));
@@ -493,7 +519,10 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
   for (int l0 = 0; l0 < n_lambda; l0 += batch_max) {
     const int nbat = std::min(batch_max, n_lambda - l0);
     if (dbg) cudaEventRecord(ev[0], st);
-    chol_build<<<dim3(blocks_for(Nt * Da), nbat), 256, 0, st>>>(A0, B0, Da, Dy, lam_dev, l0, M);
+    if (folds_inv_n)
+      chol_build_folds<<<dim3(blocks_for(Nt * Da), nbat), 256, 0, st>>>(A0, B0, Da, Dy, inv_n_dev, lam_dev, l0, M);
+    else
+      chol_build<<<dim3(blocks_for(Nt * Da), nbat), 256, 0, st>>>(A0, B0, Da, Dy, lam_dev, l0, M);
     if (dbg) cudaEventRecord(ev[1], st);
     // Two 64-column panels form a 128-column block.  The serial chain -- potf2, panel solve, the
     // rank-64 update of the block's second panel, potf2, panel solve, then the rank-128 update of
@@ -711,6 +740,35 @@ extern "C" int td_ridge_solve(const double* G_aug, const double* C_aug, int Da, 
   rc = td_ridge_solve_scaled(h, sc, st, A0, B0, Da, Dy, lambdas, n_lambda, W_out);
   if (rc) return rc;
   TD_CHECK_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
+// Leave-one-trial-out: a batch of different systems, one lambda each, in one blocked Cholesky.
+extern "C" int td_ridge_solve_batched(const double* G_aug, const double* C_aug, int Da, int Dy,
+                                      const double* n, const double* lambdas, int n_batch, float* W_out,
+                                      void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_REQUIRE(G_aug && C_aug && n && lambdas && W_out, "td_ridge_solve_batched: null argument");
+  TD_REQUIRE(Da >= 1 && Dy >= 1 && n_batch >= 1, "td_ridge_solve_batched: Da=%d Dy=%d n_batch=%d", Da, Dy, n_batch);
+  Handles* h;
+  int rc = get_handles(&h);
+  if (rc) return rc;
+  TD_CHECK_SOLVER(cusolverDnSetStream(h->solver, st));
+  TD_CHECK_SOLVER(cublasSetStream(h->blas, st));
+  Scratch sc(st);
+  std::vector<double> inv_n(n_batch);
+  for (int b = 0; b < n_batch; ++b) {
+    TD_REQUIRE(n[b] > 0, "td_ridge_solve_batched: system %d has n = %g rows", b, n[b]);
+    inv_n[b] = 1.0 / n[b];
+  }
+  std::vector<int> failed;
+  rc = batched_cholesky_sweep(h, sc, st, G_aug, C_aug, Da, Dy, lambdas, n_batch, W_out, &failed, inv_n.data());
+  if (rc) return rc;
+  if (!failed.empty()) {
+    set_error("td_ridge_solve_batched: system %d of %d is not positive definite (lambda = %g)", failed[0], n_batch,
+              lambdas[failed[0]]);
+    return TD_ERR_SOLVER;
+  }
   return TD_OK;
 }
 

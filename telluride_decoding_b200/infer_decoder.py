@@ -193,10 +193,14 @@ class Decoder(object):
 
   def train_statistics(self, *datasets):
     """Global means and power from one pass over the datasets (infer_decoder.py:366-371)."""
+    self.add_statistics(*[self.decode_dataset(ds) for ds in datasets])
+
+  def add_statistics(self, *pairs):
+    """Adds (result1, result2) CUDA [rows, dims] pairs to the running correlator statistics -- what
+    add_data_correlator (infer_decoder.py:288-310) does minibatch by minibatch, in one kernel pass."""
     sums = None
     count = 0
-    for ds in datasets:
-      r1, r2 = self.decode_dataset(ds)
+    for r1, r2 in pairs:
       sums = ops.column_moments(r1, r2, sums)
       count += int(r1.shape[0])
     s = sums.cpu().numpy().astype(np.float32)   # the reference keeps float32 sums

@@ -52,13 +52,19 @@ _default_workspaces = {}
 
 
 def _default_workspace_for(device):
-  """One cached workspace per (device, stream): calls on the same stream are ordered, calls on
-  different streams must not share staging memory."""
-  key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-  ws = _default_workspaces.get(key)
-  if ws is None:
-    ws = _default_workspaces[key] = GramWorkspace()
-  return ws
+  """The cached workspace of (device, current stream): calls on the same stream are ordered, calls
+  on different streams must not share scratch memory.  ONE entry per device is kept (a call on
+  another stream replaces it), so that dead or recycled stream handles cannot pile up buffers."""
+  stream = torch.cuda.current_stream(device).cuda_stream
+  entry = _default_workspaces.get(device.index)
+  if entry is None or entry[0] != stream:
+    entry = _default_workspaces[device.index] = (stream, GramWorkspace())
+  return entry[1]
+
+
+def release_workspaces():
+  """Drops the cached Gram workspaces (tables; for method 3 also the staged planes of the recording)."""
+  _default_workspaces.clear()
 
 
 def lagged_gram(streams, seg_keep, out=None, options=None, workspace=None, seg_first=None):
@@ -85,6 +91,44 @@ def lagged_gram(streams, seg_keep, out=None, options=None, workspace=None, seg_f
                                       ctypes.c_int64(out.stride(0)), ctypes.byref(options),
                                       _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
                                       _lib.current_stream_ptr()))
+  return out
+
+
+def lagged_gram_per_segment(streams, seg_keep, options=None, workspace=None, seg_first=None):
+  """One Gram per segment, float32 [n_seg, Dz, Dz], from ONE launch of the tcgen05 kernel when every
+  segment spans the same number of 32-frame k-tiles (leave-one-trial-out statistics: fold = total -
+  trial, regression.py:197-214); otherwise one launch per segment."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = streams[0].data.device
+  dz = sum(s.width for s in streams)
+  n_seg = len(seg_keep)
+  first_l = [0] * n_seg if seg_first is None else [int(v) for v in seg_first]
+  tiles = set((int(k) + 31) // 32 - f // 32 if k > f else 0 for f, k in zip(first_l, seg_keep))
+  out = torch.empty((n_seg, dz, dz), dtype=torch.float32, device=device)
+  if len(tiles) != 1 or 0 in tiles:
+    for i in range(n_seg):
+      sub = [Stream(s.data, s.pre, s.post, [s.seg_start[i]], [s.seg_len[i]]) for s in streams]
+      if seg_keep[i] > first_l[i]:
+        lagged_gram(sub, [seg_keep[i]], out=out[i], options=options, workspace=workspace,
+                    seg_first=[first_l[i]])
+      else:
+        out[i].zero_()
+    return out
+  options = options or gram_options()
+  carr = _streams_array(streams)
+  keep = _lib.i64_array(seg_keep)
+  first = _lib.i64_array(seg_first) if seg_first is not None else None
+  opt4 = _lib.TdGramOptions(4, 2, options.chunk_rows, 0, options.max_ctas)
+  opt4.reserved[0] = options.reserved[0]
+  nbytes = ctypes.c_size_t(0)
+  _lib.check(lib.td_lagged_gram_workspace_bytes(carr, len(streams), first, keep, n_seg,
+                                                ctypes.byref(opt4), ctypes.byref(nbytes)))
+  ws = (workspace or _default_workspace_for(device)).get(nbytes.value, device)
+  with torch.cuda.device(device):
+    _lib.check(lib.td_lagged_gram_batched_f32(carr, len(streams), first, keep, n_seg, _lib.ptr(out),
+                                              ctypes.c_int64(dz), ctypes.byref(opt4), _lib.ptr(ws),
+                                              ctypes.c_size_t(ws.numel()), _lib.current_stream_ptr()))
   return out
 
 
@@ -121,6 +165,49 @@ def lagged_thin(x, v, seg_keep, seg_first=None):
                                       _lib.i64_array(seg_keep), len(seg_keep), _lib.ptr(xtv),
                                       _lib.ptr(vtv), _lib.current_stream_ptr()))
   return xtv, vtv
+
+
+def lagged_thin_per_segment(x, v, seg_keep, seg_first=None):
+  """(X'[v|1] [n_seg, Dx, Q], [v|1]'[v|1] [n_seg, Q, Q]) in float64, one pair per segment."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = x.data.device
+  q = (v.channels if v is not None else 0) + 1
+  n_seg = len(seg_keep)
+  xtv = torch.empty((n_seg, x.width, q), dtype=torch.float64, device=device)
+  vtv = torch.empty((n_seg, q, q), dtype=torch.float64, device=device)
+  xs = x.c_struct()
+  vs = v.c_struct() if v is not None else None
+  with torch.cuda.device(device):
+    _lib.check(lib.td_lagged_thin_per_segment_f64(
+        ctypes.byref(xs), ctypes.byref(vs) if vs is not None else None,
+        _lib.i64_array(seg_first) if seg_first is not None else None, _lib.i64_array(seg_keep), n_seg,
+        _lib.ptr(xtv), _lib.ptr(vtv), _lib.current_stream_ptr()))
+  return xtv, vtv
+
+
+def lagged_predict_per_segment(x, seg_keep, out_row, weights, bias=None, out=None, total_rows=None):
+  """out rows of segment s = X_s W[s] + b[s]: weights [n_seg, Dx, Dy], bias [n_seg, Dy] -- every
+  held-out trial predicted by the model that never saw it."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = x.data.device
+  weights = weights.to(torch.float32).contiguous()
+  n_seg, dx, dy = (int(v) for v in weights.shape)
+  if n_seg != len(seg_keep) or dx != x.width:
+    raise ValueError('weights are %s, expected [%d, %d, Dy]' % (tuple(weights.shape), len(seg_keep), x.width))
+  if bias is not None:
+    bias = bias.to(torch.float32).contiguous()
+  if out is None:
+    if total_rows is None:
+      total_rows = max([r + k for r, k in zip(out_row, seg_keep)] + [0])
+    out = torch.empty((total_rows, dy), dtype=torch.float32, device=device)
+  xs = x.c_struct()
+  with torch.cuda.device(device):
+    _lib.check(lib.td_lagged_predict_per_segment_f32(
+        ctypes.byref(xs), _lib.i64_array(seg_keep), _lib.i64_array(out_row), n_seg, _lib.ptr(weights),
+        _lib.ptr(bias), dy, _lib.ptr(out), ctypes.c_int64(out.stride(0)), _lib.current_stream_ptr()))
+  return out
 
 
 def lagged_predict(x, seg_keep, out_row, weights, bias=None, mean=None, out=None, total_rows=None):
@@ -172,6 +259,26 @@ def ridge_solve(g_aug, c_aug, n, lambdas, method=2):
     _lib.check(lib.td_ridge_solve(_lib.ptr(g_aug), _lib.ptr(c_aug), da, dy, ctypes.c_double(n),
                                   _lib.f64_array(lambdas), len(lambdas), int(method),
                                   _lib.ptr(out), _lib.current_stream_ptr()))
+  return out
+
+
+def ridge_solve_batched(g_aug, c_aug, n, lambdas):
+  """[n_batch, Da, Dy] float32 solutions of (G_b/n_b + lambda_b I) W_b = C_b/n_b for a batch of
+  different systems in one batched Cholesky (the folds of a leave-one-trial-out fit)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  g_aug = g_aug.to(torch.float64).contiguous()
+  c_aug = c_aug.to(torch.float64).contiguous()
+  nb, da, dy = int(c_aug.shape[0]), int(c_aug.shape[1]), int(c_aug.shape[2])
+  n = [float(v) for v in n]
+  lambdas = [float(l) for l in lambdas]
+  if len(n) != nb or len(lambdas) != nb or tuple(g_aug.shape) != (nb, da, da):
+    raise ValueError('ridge_solve_batched: inconsistent batch shapes')
+  out = torch.empty((nb, da, dy), dtype=torch.float32, device=g_aug.device)
+  with torch.cuda.device(g_aug.device):
+    _lib.check(lib.td_ridge_solve_batched(_lib.ptr(g_aug), _lib.ptr(c_aug), da, dy, _lib.f64_array(n),
+                                          _lib.f64_array(lambdas), nb, _lib.ptr(out),
+                                          _lib.current_stream_ptr()))
   return out
 
 

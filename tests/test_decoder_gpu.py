@@ -214,3 +214,91 @@ def test_lda_training_and_windows_match_reference(golden_dir):
   ref = infer_decoder.Decoder(lambda d: None, reduction='lda')
   want = ref.compute_lda_model(c0, c1)
   assert abs(d2 - want) < 1e-3 * abs(want) and d2 > 1.0
+
+
+def _aad_trials(seed, lens, c, gain_unattended=0.1):
+  """Two speakers per trial; the attended one drives the EEG (test/decoding_test.py:134-216 style),
+  the label alternates between trials."""
+  rng = np.random.RandomState(seed)
+  trials = []
+  taps = rng.randn(5, c).astype(np.float32) / 3
+  for i, n in enumerate(lens):
+    s1 = rng.randn(n, 1).astype(np.float32)
+    s2 = rng.randn(n, 1).astype(np.float32)
+    label = i % 2                                   # 0: speaker 1 attended
+    att, un = (s1, s2) if label == 0 else (s2, s1)
+    eeg = 0.8 * rng.randn(n, c).astype(np.float32)
+    for k in range(5):                              # the EEG lags the audio: decode with post context
+      eeg[k:] += att[:n - k] * taps[k] + gain_unattended * un[:n - k] * taps[k]
+    trials.append(dict(eeg=eeg, att=att.astype(np.float32), s1=s1, s2=s2,
+                       label=np.full((n, 1), label, np.float32)))
+  return trials
+
+
+def _oracle_loo_aad(trials, order, pre, post, batch, lam, windows, reduction):
+  """The reference's loop structure run with the oracle: one complete fit per held-out trial
+  (regression.py:197-214), held-out prediction, pooled correlator (infer_decoder.py:288-328),
+  windows inside each trial (result_store.py:262-271), winner-take-all, accuracy (infer.py:399-407)."""
+  rows = {}
+  for name in order:
+    t = trials[name]
+    z = np.zeros((t['eeg'].shape[0], 1), np.float32)
+    rows[name] = ora.file_rows(t['eeg'], z, t['att'], z, pre, post)
+  preds = {}
+  for held in order:
+    batches = ora.batches_from_files([rows[n] for n in order if n != held], batch)
+    w, b, _, _, _ = ora.linear_regressor_from_batches(batches, lam)
+    preds[held] = (np.matmul(rows[held][0], w) + np.reshape(b, (1, -1))).astype(np.float32)
+  corr = ora.Correlator()
+  pred_all = np.concatenate([preds[n] for n in order])
+  corr.add(np.concatenate([trials[n]['s1'] for n in order]), pred_all)
+  corr.add(np.concatenate([trials[n]['s2'] for n in order]), pred_all)
+  out = {}
+  for w_ in windows:
+    r1, r2, lab = [], [], []
+    for n in order:
+      t = trials[n]
+      c1 = ora.reduce_correlations(corr.correlate(t['s1'], preds[n]), reduction)
+      c2 = ora.reduce_correlations(corr.correlate(t['s2'], preds[n]), reduction)
+      a, l = ora.windowed_means(c1, t['label'], w_)
+      b2, _ = ora.windowed_means(c2, t['label'], w_)
+      r1.append(a); r2.append(b2); lab.append(l)
+    r1, r2, lab = np.concatenate(r1), np.concatenate(r2), np.concatenate(lab)
+    att = ora.wta_attention(r1, r2)
+    out[w_] = dict(r1=r1, r2=r2, labels=lab, attention=att, accuracy=ora.aad_accuracy(att, lab))
+  return out, preds
+
+
+@pytest.mark.parametrize('lens,batch', [
+    ([1500] * 20, 100),                               # 20 trials, no row is dropped in any fold
+    ([1300, 900, 1111, 1200, 777, 1024], 128),        # ragged trials: every fold drops a different tail
+])
+def test_leave_one_trial_out_aad_matches_the_reference_loop(lens, batch):
+  """BASELINE.json configs[4] end to end on a subset the oracle can loop over: per-trial statistics
+  from one launch, batched fold solves, held-out predictions, correlator, windows, decisions --
+  decisions bit-identical, correlations within 1e-4."""
+  from telluride_decoding_b200 import brain_data, infer
+  c, pre, post, lam = 8, 0, 7, 0.1
+  trials_l = _aad_trials(11, lens, c)
+  names = ['trial_%02d' % i for i in range(len(lens))]
+  trials = dict(zip(names, trials_l))
+  bd = brain_data.TrialBrainData('eeg', 'attended', 100.0, pre_context=pre, post_context=post,
+                                 in2_fields='speakers', attended_field='label',
+                                 final_batch_size=batch, shuffle_buffer_size=0)
+  for n in names:
+    t = trials[n]
+    bd.add_trial(n, t['eeg'], t['att'], np.concatenate([t['s1'], t['s2']], axis=1), t['label'])
+  windows = [50, 100, 200]
+  acc, det = infer.leave_one_trial_out_test(bd, regularization_lambda=lam, window_list=windows,
+                                            reduction='first', decoder_type='wta', return_details=True)
+  order = bd.all_files()
+  want, preds = _oracle_loo_aad(trials, order, pre, post, batch, lam, windows, 'first')
+  pred_want = np.concatenate([preds[n] for n in order])
+  assert gpu_util.rel_fro(det['prediction'].cpu().numpy(), pred_want) < 1e-4
+  for w_ in windows:
+    np.testing.assert_allclose(det[w_]['r1'], want[w_]['r1'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(det[w_]['r2'], want[w_]['r2'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_array_equal(det[w_]['labels'], want[w_]['labels'])
+    np.testing.assert_array_equal(det[w_]['attention'], want[w_]['attention'])      # bit-identical decisions
+    assert acc[w_] == want[w_]['accuracy']
+  assert acc[200] > 0.8                                # the attended speaker is decodable
