@@ -397,3 +397,31 @@ def test_inputs_cross_by_dlpack_and_shutdown_releases_handles():
     assert _lib.load().td_shutdown() == 0             # handles are recreated on the next solve
   # (the Gram's partial tiles are combined with fp32 atomics, so two runs differ in the last bits)
   np.testing.assert_allclose(weights[0], weights[1], rtol=1e-4, atol=1e-6)
+
+
+def test_long_streams_with_small_batches_and_unit_windows():
+  """The windowed-correlation kernel keeps its per-chunk partial sums in global memory: no limit on
+  segment length x columns (the round-1 kernel held them in 192 KB of shared memory and refused
+  evaluate() at the regression preset's batch_size = 100 beyond ~98 k rows with 5 CCA dimensions, and
+  Decoder.train(window_size=0) beyond ~4.9 k rows).  cfg2 length: 460 800 rows."""
+  from telluride_decoding_b200 import infer_decoder
+  rng = np.random.RandomState(8)
+  n = 460800
+  x = rng.randn(n, 4).astype(np.float32)
+  y = (x[:, :1] + 0.5 * rng.randn(n, 1)).astype(np.float32)
+  bd = gpu_util.make_test_data(x, y, post_context=3, final_batch_size=100)
+  ds = bd.create_dataset('train')
+  model = brain_model.BrainModelLinearRegression(ds, regularization_lambda=0.1)
+  model.fit(ds)
+  res = model.evaluate(bd.create_dataset('test'))
+  # Keras semantics: mean over the 4608 minibatches of the per-batch Pearson r
+  pred = model.predict(bd.create_dataset('test'))
+  r = [np.corrcoef(pred[i:i + 100, 0], y[i:i + 100, 0])[0, 1] for i in range(0, n, 100)]
+  assert abs(res['pearson_correlation_first'] - np.mean(r)) < 1e-5
+  # unit windows over five columns: the per-frame signal itself, 2.3 M values
+  a = torch.as_tensor(rng.randn(n, 5).astype(np.float32), device='cuda')
+  b = torch.as_tensor(rng.randn(n, 5).astype(np.float32), device='cuda')
+  mu = torch.zeros(5, device='cuda'); pw = torch.full((5,), 2.0, device='cuda')
+  vals, _ = ops.windowed_corr(a, b, [0], [n], [1], [1], 'global_all', mu_a=mu, mu_b=mu, power=pw)
+  want = (a * b / 2.0).double()
+  assert torch.equal(vals, want)
