@@ -422,6 +422,7 @@ def test_long_streams_with_small_batches_and_unit_windows():
   a = torch.as_tensor(rng.randn(n, 5).astype(np.float32), device='cuda')
   b = torch.as_tensor(rng.randn(n, 5).astype(np.float32), device='cuda')
   mu = torch.zeros(5, device='cuda'); pw = torch.full((5,), 2.0, device='cuda')
+  from telluride_decoding_b200 import ops
   vals, _ = ops.windowed_corr(a, b, [0], [n], [1], [1], 'global_all', mu_a=mu, mu_b=mu, power=pw)
   want = (a * b / 2.0).double()
   assert torch.equal(vals, want)
