@@ -289,6 +289,14 @@ class ClockSampler(object):
                 samples=len(sm), sampled='inside the timed regions' if in_window else 'whole run')
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the Gram kernel on the full cfg 4 recording
+# (ncu, mean of 5 launches of this very command, profiles/r02_ncu_launches_summary.txt): 1481 GB read +
+# 308 GB written.  Algorithmic bytes are 8.15 GB (raw 4.41 + G 3.75): G (3.75 GB) fits no on-chip memory,
+# so every (tile, superchunk) partial goes through L2 into HBM, and ~11 % of the raw boxes miss L2.
+# 137 GB/s, 2 % of the HBM bandwidth of a tensor-bound kernel.
+GRAM_DRAM_TRAFFIC_BYTES_CFG4 = 1788808138547
+
+
 def load_peaks():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(path):
@@ -711,7 +719,10 @@ def main():
   peak = (peaks['bf16_sustained'] if long_step else peaks['bf16']) / 6.0
   roofline = dict(
       bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
-      traffic=None, kernel='hk::lagged_gram_halo_kernel' if args.gram_method in (0, 4) else 'ts::lagged_gram_ts_kernel', flops_per_launch=f_alg,
+      traffic=GRAM_DRAM_TRAFFIC_BYTES_CFG4 if (world == 1 and args.minutes == 60.0 and args.gram_method in (0, 4)) else None,
+      traffic_source='profiles/r02_ncu_launches_summary.txt (ncu dram__bytes_read/write.sum of this command, per launch); '
+                     'algorithmic bytes per launch %.2f GB' % ((float(rows0) * c * 4 + float(d) * d * 4) / 1e9),
+      kernel='hk::lagged_gram_halo_kernel' if args.gram_method in (0, 4) else 'ts::lagged_gram_ts_kernel', flops_per_launch=f_alg,
       frames_per_launch=rows0, kernel_ms=kernel_ms, kernel_ms_max_over_ranks=gram_kernel_ms_max,
       peak_source='%s bf16_tflops%s / 2 (tf32 rate) / 3 (3xTF32): the %s figure, the kernel runs for '
                   '%.2f s' % (peaks['source'], '_sustained' if long_step else '',

@@ -136,6 +136,21 @@ int td_lagged_thin_per_segment_f64(const td_stream* x, const td_stream* v,
                                    const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
                                    double* xtv_dev, double* vtv_dev, void* cuda_stream);
 
+/* Ledoit-Wolf shrinkage statistics (brain_model.py:438-443, :457-465), from the implicit design.
+ * Segments here are the PIECES of the minibatches (a minibatch of the interleaved stream is a
+ * contiguous row range of each file); seg_slot[i] (HOST) is the minibatch piece i belongs to.
+ *   td_lagged_column_sums_f64  sums_dev [n_slots][Dx], rows_dev [n_slots] double: np.sum(x, axis=0) and
+ *                              the row count of every minibatch
+ *   td_lagged_lw_stat_f64      out_dev[0] = sum_t (sum_i (X[t,i] - mean_dev[slot(t)][i])^2)^2, i.e. the sum
+ *                              of all entries of the reference's sum_x2tx2 (the only thing it uses),
+ *                              mean_dev [n_slots][Dx] float32 = the running mean after each minibatch */
+int td_lagged_column_sums_f64(const td_stream* x, const int64_t* seg_first, const int64_t* seg_keep,
+                              const int32_t* seg_slot, int n_seg, int n_slots, double* sums_dev,
+                              double* rows_dev, void* cuda_stream);
+int td_lagged_lw_stat_f64(const td_stream* x, const int64_t* seg_first, const int64_t* seg_keep,
+                          const int32_t* seg_slot, int n_seg, int n_slots, const float* mean_dev,
+                          double* out_dev, void* cuda_stream);
+
 /* Gram over the row ranges [seg_first[s], seg_keep[s]) of each segment (seg_first NULL = 0), on
  * CUDA cores in fp32 with float64 carry.  Used for the small leave-one-out corrections: the
  * < batch_size rows that `drop_remainder` (brain_data.py:369-370) removes from a fold's training

@@ -46,7 +46,8 @@ EXPORTS = (
     'td_tfrecord_features', 'td_tfrecord_read_f32', 'td_shutdown', 'td_comm_unique_id', 'td_comm_init',
     'td_comm_destroy', 'td_comm_nccl_version', 'td_allreduce_sum_f32', 'td_allreduce_sum_f64',
     'td_allreduce_sym_f32', 'td_pack_upper_f32', 'td_unpack_upper_f32', 'td_lagged_gram_batched_f32',
-    'td_lagged_thin_per_segment_f64', 'td_lagged_predict_per_segment_f32', 'td_ridge_solve_batched')
+    'td_lagged_thin_per_segment_f64', 'td_lagged_predict_per_segment_f32', 'td_ridge_solve_batched',
+    'td_lagged_column_sums_f64', 'td_lagged_lw_stat_f64')
 
 _lib = None
 
@@ -87,6 +88,11 @@ def current_stream_ptr():
 def i64_array(values):
   values = [int(v) for v in values]
   return (ctypes.c_int64 * max(len(values), 1))(*values)
+
+
+def i32_array(values):
+  values = [int(v) for v in values]
+  return (ctypes.c_int32 * max(len(values), 1))(*values)
 
 
 def f64_array(values):

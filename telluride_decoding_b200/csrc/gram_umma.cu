@@ -959,10 +959,14 @@ int use_halo(const td_stream* streams, int n_streams, const td_gram_options* opt
   TD_REQUIRE(!(m == 4 && cg == 1), "td_lagged_gram: method 4 (operand built on chip) needs CTA pairs");
   *halo = (m == 4);
   if (m == 0 && DEFAULT_PAIR_METHOD == 4 && cg != 1 && streams) {
-    int64_t rows = 0;
-    for (int q = 0; q < n_streams && q < 2; ++q)
+    // Row groups are 4 lags x 8 channels: a design with very few lags (or channels) would mostly
+    // multiply padding (one lag fills a quarter of its row groups); those go to the staged kernels.
+    int64_t rows = 0, cols = 0;
+    for (int q = 0; q < n_streams && q < 2; ++q) {
       rows += ceil_div(streams[q].channels, hk::BOX_CH) * hk::BOX_CH * ceil_div(lags_of(streams[q]), hk::RG_LAGS) * hk::RG_LAGS;
-    *halo = cg == 2 || rows >= 512;
+      cols += width_of(streams[q]);
+    }
+    *halo = (cg == 2 || rows >= 512) && cols * 5 >= rows * 4;
   }
   return TD_OK;
 }

@@ -159,7 +159,8 @@ __device__ __forceinline__ void thin_fast(const float* __restrict__ xs, const fl
 __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, int has_v, int Q,
                                                    const int64_t* seg_keep, const int* blk_seg,
                                                    const int64_t* blk_t0, double* xtv_slices,
-                                                   double* vtv, int per_segment) {
+                                                   double* vtv, int per_segment,
+                                                   const int* __restrict__ seg_slot) {
   extern __shared__ float thin_sm[];
   const int seg = blk_seg[blockIdx.x];
   const int64_t t0 = blk_t0[blockIdx.x];
@@ -190,9 +191,10 @@ __global__ void __launch_bounds__(256) thin_kernel(StreamView x, StreamView v, i
   __syncthreads();
   const int64_t Dx = (int64_t)x.channels * L;
   // One output per segment (leave-one-trial-out statistics), or 64 slices that a second kernel adds up.
-  double* xtv = per_segment ? xtv_slices + (size_t)seg * Dx * Q
+  const int slot = seg_slot ? seg_slot[seg] : seg;
+  double* xtv = per_segment ? xtv_slices + (size_t)slot * Dx * Q
                             : xtv_slices + (size_t)((blockIdx.x + blockIdx.y) % THIN_SLICES) * Dx * Q;
-  if (per_segment) vtv += (size_t)seg * Q * Q;
+  if (per_segment) vtv += (size_t)slot * Q * Q;
   // Thread = (channel, group of THIN_KT consecutive lags): the frames x[r+k .. r+k+KT) slide
   // through registers, so one shared-memory load of x and Q of the targets feed KT*Q FMAs.
   const int n_kg = (L + THIN_KT - 1) / THIN_KT;
@@ -332,6 +334,49 @@ __global__ void rows_kernel(StreamView x, const int64_t* seg_keep, const int64_t
   }
 }
 
+// Ledoit-Wolf statistic (brain_model.py:440-443, :457-465).  The reference accumulates the Gram of the
+// squared, running-mean-centred minibatch, z = (x - mean_b)^2, and then uses only the SUM of all its
+// entries: sum_ij sum_t z_ti z_tj = sum_t (sum_i z_ti)^2.  One warp per design row computes the row
+// sum over the implicit lagged design (lanes stride the columns), the block adds the squares.
+__global__ void __launch_bounds__(256) lw_stat_kernel(StreamView x, const int64_t* seg_keep, const int* blk_seg,
+                                                      const int64_t* blk_t0, int rows_per_block,
+                                                      const int* __restrict__ seg_slot,
+                                                      const float* __restrict__ mean, double* out) {
+  __shared__ double part[8];
+  const int seg = blk_seg[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t keep = seg_keep[seg];
+  const int64_t len = x.seg_len[seg];
+  const float* base = x.data + x.seg_start[seg] * x.ld;
+  const int64_t Dx = (int64_t)x.channels * x.lags;
+  const float* mu = mean + (int64_t)seg_slot[seg] * Dx;
+  double acc = 0.0;
+  for (int r = warp; r < rows_per_block; r += 8) {
+    const int64_t t = blk_t0[blockIdx.x] + r;
+    if (t >= keep) break;
+    float s = 0.0f;
+    int k = lane / x.channels, c = lane % x.channels;
+    for (int64_t j = lane; j < Dx; j += 32) {
+      const int64_t u = t - x.pre + k;
+      const float xv = (u >= 0 && u < len) ? __ldg(base + u * x.ld + c) : 0.0f;
+      const float dlt = xv - __ldg(mu + j);
+      s = fmaf(dlt, dlt, s);
+      c += 32;
+      while (c >= x.channels) { c -= x.channels; ++k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    acc += (double)s * (double)s;
+  }
+  if (lane == 0) part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += part[w];
+    atomicAdd(out, tot);
+  }
+}
+
 // Device copies of the segment tables of one stream (+ keep, out_row), stream-ordered.
 struct DevTables {
   std::vector<void*> ptrs;
@@ -442,7 +487,7 @@ extern "C" int td_lagged_gram_range_f32(const td_stream* streams, int n_streams,
 
 static int thin_impl(const td_stream* x, const td_stream* v, const int64_t* seg_first,
                      const int64_t* seg_keep, int n_seg, double* xtv, double* vtv, void* stream,
-                     int per_segment);
+                     int per_segment, const int32_t* seg_slot = nullptr, int n_slots = 0);
 
 extern "C" int td_lagged_thin_f64(const td_stream* x, const td_stream* v, const int64_t* seg_first,
                                   const int64_t* seg_keep, int n_seg, double* xtv, double* vtv,
@@ -456,9 +501,21 @@ extern "C" int td_lagged_thin_per_segment_f64(const td_stream* x, const td_strea
   return thin_impl(x, v, seg_first, seg_keep, n_seg, xtv, vtv, stream, 1);
 }
 
+// Column sums of the lagged design per OUTPUT SLOT: segment i (rows [first, keep)) adds into slot
+// seg_slot[i].  With the pieces of the minibatches as segments this gives `np.sum(x, axis=0)` of every
+// minibatch (brain_model.py:438) in one launch.
+extern "C" int td_lagged_column_sums_f64(const td_stream* x, const int64_t* seg_first, const int64_t* seg_keep,
+                                         const int32_t* seg_slot, int n_seg, int n_slots, double* sums_dev,
+                                         double* rows_dev, void* stream) {
+  TD_REQUIRE(seg_slot && n_slots > 0 && sums_dev && rows_dev, "td_lagged_column_sums_f64: null argument");
+  for (int i = 0; i < n_seg; ++i)
+    TD_REQUIRE(seg_slot[i] >= 0 && seg_slot[i] < n_slots, "td_lagged_column_sums_f64: slot %d of segment %d out of range", seg_slot[i], i);
+  return thin_impl(x, nullptr, seg_first, seg_keep, n_seg, sums_dev, rows_dev, stream, 1, seg_slot, n_slots);
+}
+
 static int thin_impl(const td_stream* x, const td_stream* v, const int64_t* seg_first,
                      const int64_t* seg_keep, int n_seg, double* xtv, double* vtv, void* stream,
-                     int per_segment) {
+                     int per_segment, const int32_t* seg_slot, int n_slots) {
   cudaStream_t st = (cudaStream_t)stream;
   TD_REQUIRE(x && seg_keep && xtv && vtv && n_seg > 0, "td_lagged_thin_f64: null argument");
   int rc = check_stream(x, seg_keep, n_seg, "td_lagged_thin_f64");
@@ -487,7 +544,9 @@ static int thin_impl(const td_stream* x, const td_stream* v, const int64_t* seg_
   rc = make_blocks(seg_keep, n_seg, THIN_TB, tabs, &blk_seg, &blk_t0, &nblk, seg_first);
   if (rc) return rc;
   const int64_t Dx = width_of(*x);
-  const size_t n_out = per_segment ? (size_t)n_seg : 1;
+  const size_t n_out = per_segment ? (size_t)(seg_slot ? n_slots : n_seg) : 1;
+  const int* slot_dev = nullptr;
+  if (seg_slot && (rc = tabs.put(seg_slot, (size_t)n_seg, &slot_dev))) return rc;
   TD_CHECK_CUDA(cudaMemsetAsync(xtv, 0, n_out * Dx * Q * sizeof(double), st));
   TD_CHECK_CUDA(cudaMemsetAsync(vtv, 0, n_out * Q * Q * sizeof(double), st));
   if (nblk > 0) {
@@ -507,13 +566,13 @@ static int thin_impl(const td_stream* x, const td_stream* v, const int64_t* seg_
     TD_CHECK_CUDA(cudaFuncSetAttribute(thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)nblk, (unsigned)ceil_div(x->channels, THIN_CB));
     if (per_segment) {
-      thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, xtv, vtv, 1);
+      thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, xtv, vtv, 1, slot_dev);
       TD_CHECK_CUDA(cudaGetLastError());
     } else {
       const size_t slice_bytes = (size_t)THIN_SLICES * Dx * Q * sizeof(double);
       TD_CHECK_CUDA(cudaMallocAsync((void**)&slices.p, slice_bytes, st));
       TD_CHECK_CUDA(cudaMemsetAsync(slices.p, 0, slice_bytes, st));
-      thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, slices.p, vtv, 0);
+      thin_kernel<<<grid, 256, smem, st>>>(xv, vv, v ? 1 : 0, Q, keep_dev, blk_seg, blk_t0, slices.p, vtv, 0, nullptr);
       TD_CHECK_CUDA(cudaGetLastError());
       thin_reduce_kernel<<<(unsigned)ceil_div(Dx * Q, 256), 256, 0, st>>>(slices.p, xtv, Dx * Q);
       TD_CHECK_CUDA(cudaGetLastError());
@@ -596,6 +655,36 @@ extern "C" int td_lagged_rows_f32(const td_stream* x, const int64_t* seg_keep, c
   if (rc) return rc;
   if (nblk > 0) {
     rows_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, out, ldo);
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
+  return TD_OK;
+}
+
+extern "C" int td_lagged_lw_stat_f64(const td_stream* x, const int64_t* seg_first, const int64_t* seg_keep,
+                                     const int32_t* seg_slot, int n_seg, int n_slots, const float* mean_dev,
+                                     double* out_dev, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_REQUIRE(x && seg_keep && seg_slot && mean_dev && out_dev && n_seg > 0 && n_slots > 0,
+             "td_lagged_lw_stat_f64: null argument");
+  int rc = check_stream(x, seg_keep, n_seg, "td_lagged_lw_stat_f64");
+  if (rc) return rc;
+  for (int i = 0; i < n_seg; ++i)
+    TD_REQUIRE(seg_slot[i] >= 0 && seg_slot[i] < n_slots, "td_lagged_lw_stat_f64: slot %d of segment %d out of range", seg_slot[i], i);
+  DevTables tabs(st);
+  StreamView xv;
+  rc = make_view(x, n_seg, tabs, &xv);
+  if (rc) return rc;
+  const int64_t* keep_dev;
+  const int* slot_dev;
+  rc = tabs.put(seg_keep, n_seg, &keep_dev); if (rc) return rc;
+  rc = tabs.put(seg_slot, (size_t)n_seg, &slot_dev); if (rc) return rc;
+  const int rows_per_block = 32;
+  const int* blk_seg; const int64_t* blk_t0; int64_t nblk;
+  rc = make_blocks(seg_keep, n_seg, rows_per_block, tabs, &blk_seg, &blk_t0, &nblk, seg_first);
+  if (rc) return rc;
+  TD_CHECK_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), st));
+  if (nblk > 0) {
+    lw_stat_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, blk_seg, blk_t0, rows_per_block, slot_dev, mean_dev, out_dev);
     TD_CHECK_CUDA(cudaGetLastError());
   }
   return TD_OK;
