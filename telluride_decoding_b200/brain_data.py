@@ -173,6 +173,23 @@ class LaggedDataset(object):
       out.append((1.0, self.seg_keep_for_prefix(self.partial_rows)))
     return out
 
+  def batch_pieces(self):
+    """[(segment, first row, end row, minibatch)]: the contiguous row range of every segment that
+    falls into each minibatch of the (un-shuffled, un-repeated) interleaved stream -- a minibatch is
+    `final_batch_size` consecutive stream elements, i.e. a few consecutive rows of every file
+    (brain_data.py:725-728, :369-370)."""
+    pieces = []
+    prev = [0] * len(self.seg_rows)
+    b = self.final_batch_size
+    n_batches = self.total_rows // b if b > 0 else 0
+    for batch in range(n_batches):
+      cur = self.seg_keep_for_prefix((batch + 1) * b)
+      for s, (lo, hi) in enumerate(zip(prev, cur)):
+        if hi > lo:
+          pieces.append((s, lo, hi, batch))
+      prev = cur
+    return pieces
+
   def wait_ready(self):
     """Makes the current stream wait for every pending host-to-device copy of the trials."""
     if self.ready:

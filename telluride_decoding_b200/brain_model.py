@@ -188,11 +188,41 @@ def solve_regression(stats, lambdas, use_offset=True, method=2):
 
 
 def _ledoit_wolf_shrinkage(dataset, use_offset, g_aug, mean_x, mu, n):
-  """Shrinkage of brain_model.py:457-465 (float64).  sum_x2tx2 follows :440-443: every batch is
-  centred by the mean of all rows seen up to and including it, squared elementwise, and its Gram
-  is accumulated -- an order-dependent statistic, so the batches are walked in the reference's order."""
+  """Shrinkage of brain_model.py:457-465 (float64).
+
+  The reference accumulates `sum_x2tx2` (:440-443): every minibatch is centred by the mean of all
+  rows seen up to and including it, squared elementwise, and its Gram is added up -- and then uses
+  only `np.sum` of that matrix, which is sum_t (sum_i z[t, i])^2 with z the squared centred design.
+  Two kernels over the implicit lagged design do the same without building a row: the column sums of
+  every minibatch (-> the running means), then the row-wise statistic.  The ones column of the
+  augmented design centres to exactly zero and contributes nothing.  The minibatches are those of
+  the un-shuffled stream; repeated epochs fall back to walking the materialised minibatches."""
+  if dataset.repeat_count != 1:
+    return _ledoit_wolf_shrinkage_from_batches(dataset, use_offset, g_aug, mean_x, mu, n)
+  pieces = dataset.batch_pieces()
+  x = dataset.stream('x')
+  px = ops.Stream(x.data, x.pre, x.post, [x.seg_start[s] for s, _, _, _ in pieces],
+                  [x.seg_len[s] for s, _, _, _ in pieces])
+  first = [lo for _, lo, _, _ in pieces]
+  keep = [hi for _, _, hi, _ in pieces]
+  slot = [b for _, _, _, b in pieces]
+  n_batches = dataset.total_rows // dataset.final_batch_size
+  sums, rows = ops.lagged_column_sums(px, first, keep, slot, n_batches)
+  running_mean = torch.cumsum(sums, dim=0) / torch.cumsum(rows, dim=0).unsqueeze(1)
+  stat = ops.lagged_lw_stat(px, first, keep, slot, running_mean)
+  d = g_aug.shape[0]
+  cov_x_zc = g_aug - torch.outer(mean_x, mean_x)
+  delta_ = cov_x_zc.clone()
+  delta_.diagonal().sub_(mu)
+  delta = float((delta_ ** 2).sum().item()) / d
+  beta_ = (stat / n - float((cov_x_zc ** 2).sum().item())) / (d * n)
+  return min(beta_, delta) / delta
+
+
+def _ledoit_wolf_shrinkage_from_batches(dataset, use_offset, g_aug, mean_x, mu, n):
+  """The same statistic from the materialised minibatches, in the reference's order (repeated epochs)."""
   sum_x = None
-  sum_x2tx2 = None
+  stat = 0.0
   rows_seen = 0
   for inputs, _ in dataset:
     x = inputs['input_1'].to(torch.float64)
@@ -202,14 +232,13 @@ def _ledoit_wolf_shrinkage(dataset, use_offset, g_aug, mean_x, mu, n):
     batch_sum = x.sum(dim=0, keepdim=True)
     sum_x = batch_sum if sum_x is None else sum_x + batch_sum
     centred_sq = (x - sum_x / rows_seen) ** 2
-    gram = centred_sq.t() @ centred_sq
-    sum_x2tx2 = gram if sum_x2tx2 is None else sum_x2tx2 + gram
+    stat += float((centred_sq.sum(dim=1) ** 2).sum().item())
   d = g_aug.shape[0]
   cov_x_zc = g_aug - torch.outer(mean_x, mean_x)
   delta_ = cov_x_zc.clone()
   delta_.diagonal().sub_(mu)
   delta = float((delta_ ** 2).sum().item()) / d
-  beta_ = float((sum_x2tx2 / n - cov_x_zc ** 2).sum().item()) / (d * n)
+  beta_ = (stat / n - float((cov_x_zc ** 2).sum().item())) / (d * n)
   return min(beta_, delta) / delta
 
 
@@ -220,9 +249,9 @@ def calculate_linear_regressor_parameters_from_dataset(dataset, lamb=0.1, use_of
   Returns (W [D, Dy], b [1, Dy] (zeros((1,)) without offset), cov_x, cov_xy, shrinkage) as numpy
   float32 arrays like the reference.  `use_ridge=False` is the Blankertz shrinkage of :456-476
   with a fixed lambda in [0, 1] or, for lamb == -1, the Ledoit-Wolf estimate of :440-443, :457-465.
-  Ledoit-Wolf needs the Gram of the squared design centred by the RUNNING mean of the batches seen
-  so far, which is not a lagged stream: that one statistic is accumulated from the materialised
-  minibatches (td_lagged_rows_f32 + a library GEMM), everything else comes from the lagged kernels.
+  Ledoit-Wolf needs the squared design centred by the RUNNING mean of the minibatches seen so far;
+  only the sum of all entries of its Gram is used, and that comes from two kernels over the implicit
+  lagged design (td_lagged_column_sums_f64, td_lagged_lw_stat_f64).
   """
   if not is_dataset(dataset):
     raise TypeError('dataset input to '

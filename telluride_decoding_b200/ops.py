@@ -186,6 +186,39 @@ def lagged_thin_per_segment(x, v, seg_keep, seg_first=None):
   return xtv, vtv
 
 
+def lagged_column_sums(x, seg_first, seg_keep, seg_slot, n_slots):
+  """(sums float64 [n_slots, Dx], rows float64 [n_slots]): column sums of the implicit design over the
+  row range of every segment, added into the segment's slot -- `np.sum(x, axis=0)` of every minibatch
+  (brain_model.py:438) when the segments are the pieces of the minibatches."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = x.data.device
+  sums = torch.empty((n_slots, x.width), dtype=torch.float64, device=device)
+  rows = torch.empty((n_slots,), dtype=torch.float64, device=device)
+  xs = x.c_struct()
+  with torch.cuda.device(device):
+    _lib.check(lib.td_lagged_column_sums_f64(ctypes.byref(xs), _lib.i64_array(seg_first), _lib.i64_array(seg_keep),
+                                             _lib.i32_array(seg_slot), len(seg_keep), int(n_slots),
+                                             _lib.ptr(sums), _lib.ptr(rows), _lib.current_stream_ptr()))
+  return sums, rows
+
+
+def lagged_lw_stat(x, seg_first, seg_keep, seg_slot, mean):
+  """sum_t (sum_i (X[t, i] - mean[slot(t), i])^2)^2 as a float: the sum of all entries of the
+  reference's `sum_x2tx2` (brain_model.py:440-443), which is all its Ledoit-Wolf estimate uses."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  device = x.data.device
+  mean = mean.to(torch.float32).contiguous()
+  out = torch.zeros((1,), dtype=torch.float64, device=device)
+  xs = x.c_struct()
+  with torch.cuda.device(device):
+    _lib.check(lib.td_lagged_lw_stat_f64(ctypes.byref(xs), _lib.i64_array(seg_first), _lib.i64_array(seg_keep),
+                                         _lib.i32_array(seg_slot), len(seg_keep), int(mean.shape[0]),
+                                         _lib.ptr(mean), _lib.ptr(out), _lib.current_stream_ptr()))
+  return float(out.item())
+
+
 def lagged_predict_per_segment(x, seg_keep, out_row, weights, bias=None, out=None, total_rows=None):
   """out rows of segment s = X_s W[s] + b[s]: weights [n_seg, Dx, Dy], bias [n_seg, Dy] -- every
   held-out trial predicted by the model that never saw it."""

@@ -426,3 +426,36 @@ def test_long_streams_with_small_batches_and_unit_windows():
   vals, _ = ops.windowed_corr(a, b, [0], [n], [1], [1], 'global_all', mu_a=mu, mu_b=mu, power=pw)
   want = (a * b / 2.0).double()
   assert torch.equal(vals, want)
+
+
+def test_ledoit_wolf_shrinkage_on_interleaved_trials():
+  """lamb = -1, use_ridge=False (brain_model.py:440-443, :457-465): the running-mean statistic comes
+  from two kernels over the implicit design; minibatches of the interleaved stream mix the trials."""
+  from telluride_decoding_b200 import brain_data
+  rng = np.random.RandomState(14)
+  lens = [1300, 900, 1111]
+  bd = brain_data.TrialBrainData('eeg', 'intensity', 100.0, pre_context=2, post_context=3,
+                                 final_batch_size=200, shuffle_buffer_size=0)
+  by_name = {}
+  wt = rng.randn(6 * 5, 1).astype(np.float32)
+  for i, n in enumerate(lens):
+    x = (rng.randn(n, 5) * (1 + i) + 0.3).astype(np.float32)
+    y = (ora.add_context(x, 2, 3) @ wt + 0.2 * rng.randn(n, 1)).astype(np.float32)
+    bd.add_trial('t%d' % i, x, y)
+    z = np.zeros((n, 1), np.float32)
+    by_name['t%d' % i] = ora.file_rows(x, z, y, z, 2, 3)
+  ds = bd.create_dataset('test')
+  batches = ora.batches_from_files([by_name[name] for name, _, _ in ds.files], 200)
+  for use_offset in (True, False):
+    w, b, _, _, shrink = brain_model.calculate_linear_regressor_parameters_from_dataset(
+        ds, lamb=-1, use_offset=use_offset, use_ridge=False)
+    w0, b0, _, _, shrink0 = ora.linear_regressor_from_batches(batches, -1, use_offset=use_offset,
+                                                              use_ridge=False)
+    assert abs(shrink - shrink0) < 1e-4 * max(abs(shrink0), 1e-3), (shrink, shrink0)
+    assert gpu_util.rel_fro(w, w0) < W_TOL
+  # pieces of the minibatches: every row of the kept stream exactly once, 200 rows per minibatch
+  pieces = ds.batch_pieces()
+  per_batch = {}
+  for s, lo, hi, batch in pieces:
+    per_batch[batch] = per_batch.get(batch, 0) + hi - lo
+  assert set(per_batch.values()) == {200} and len(per_batch) == ds.num_batches
