@@ -87,12 +87,14 @@ def make_trial(cfg, i, n_taps=25, n_src=8):
   return x, y
 
 
-def fill_trials(cfg, x_out, y_out, trial_ids):
+def fill_rows(cfg, x_out, y_out, row_lo, row_hi):
+  """Rows [row_lo, row_hi) of the recording into x_out / y_out (which hold just those rows)."""
   fpt = cfg['frames_per_trial']
-  for i in trial_ids:
+  for i in range(row_lo // fpt, (row_hi + fpt - 1) // fpt):
     x, y = make_trial(cfg, i)
-    x_out[i * fpt:(i + 1) * fpt] = torch_or_numpy(x, x_out)
-    y_out[i * fpt:(i + 1) * fpt] = torch_or_numpy(y, y_out)
+    a, b = max(row_lo, i * fpt), min(row_hi, (i + 1) * fpt)
+    x_out[a - row_lo:b - row_lo] = torch_or_numpy(x[a - i * fpt:b - i * fpt], x_out)
+    y_out[a - row_lo:b - row_lo] = torch_or_numpy(y[a - i * fpt:b - i * fpt], y_out)
 
 
 def torch_or_numpy(a, like):
@@ -594,10 +596,10 @@ def main():
   my_first, my_keep = sharding.shard_rows(None, lens, rank, world)
   my_rows = sum(k - f for f, k in zip(my_first, my_keep))
   row_lo, row_hi = sharding.needed_row_range(starts, lens, lens, pre, post, rank, world)
-  need_trials = [i for i in range(trials) if my_keep[i] > my_first[i]]
-  x_pin = torch.empty((frames, c), dtype=torch.float32, pin_memory=True)
-  y_pin = torch.empty((frames, 1), dtype=torch.float32, pin_memory=True)
-  fill_trials(cfg, x_pin, y_pin, need_trials)       # rows outside are never read (upload_rows)
+  # pinned host arrays holding just the rows this rank touches (its share + the lag halo)
+  x_pin = torch.empty((row_hi - row_lo, c), dtype=torch.float32, pin_memory=True)
+  y_pin = torch.empty((row_hi - row_lo, 1), dtype=torch.float32, pin_memory=True)
+  fill_rows(cfg, x_pin, y_pin, row_lo, row_hi)
 
   def new_brain_data():
     return brain_data.TrialBrainData('meg', 'envelope', 1000.0, pre_context=pre, post_context=post,

@@ -556,7 +556,8 @@ class TrialBrainData(BrainData):
 
     upload_rows = (row_begin, row_end): time-sharded fits (sharding.needed_row_range) -- only these
     rows of the pinned host arrays are copied, the rest of the device arrays is zero; the host
-    rows outside the range are never read."""
+    rows outside the range are never read.  The host arrays may also hold JUST those rows
+    (row_end - row_begin rows instead of sum(lengths)): a rank then pins only its own share."""
     self._ready = None
     pinned = (isinstance(input_data, torch.Tensor) and isinstance(output_data, torch.Tensor) and
               input_data.device.type == 'cpu' and output_data.device.type == 'cpu' and
@@ -629,22 +630,29 @@ class TrialBrainData(BrainData):
     _lib.require_cuda()
     dev = torch.device('cuda', torch.cuda.current_device())
     alloc = torch.empty if upload_rows is None else torch.zeros
-    x = alloc(x_host.shape, dtype=torch.float32, device=dev)
-    y = alloc(y_host.shape, dtype=torch.float32, device=dev)
+    n = sum(int(l) for l in lengths)
+    # host arrays that hold only rows [row_begin, row_end): host row i is device row row_begin + i
+    host_off = 0
+    if upload_rows is not None and int(x_host.shape[0]) != n:
+      if int(x_host.shape[0]) != int(upload_rows[1]) - int(upload_rows[0]):
+        raise ValueError('host arrays must hold either all %d frames or exactly the %d rows of upload_rows' %
+                         (n, int(upload_rows[1]) - int(upload_rows[0])))
+      host_off = int(upload_rows[0])
+    x = alloc((n, x_host.shape[1]), dtype=torch.float32, device=dev)
+    y = alloc((n, y_host.shape[1]), dtype=torch.float32, device=dev)
     side = TrialBrainData._copy_streams.get(dev.index)
     if side is None:
       side = TrialBrainData._copy_streams[dev.index] = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream())        # the buffers may be recycled memory
     cuts = self.upload_cuts(lengths)
-    n = int(x_host.shape[0])
     lo, hi = (0, n) if upload_rows is None else (max(int(upload_rows[0]), 0), min(int(upload_rows[1]), n))
     ready, r0 = [], lo
     with torch.cuda.stream(side):
       for cut in cuts:
         r1 = min(max(cut, lo), hi) if cut != cuts[-1] else hi
         if r1 > r0:
-          x[r0:r1].copy_(x_host[r0:r1], non_blocking=True)
-          y[r0:r1].copy_(y_host[r0:r1], non_blocking=True)
+          x[r0:r1].copy_(x_host[r0 - host_off:r1 - host_off], non_blocking=True)
+          y[r0:r1].copy_(y_host[r0 - host_off:r1 - host_off], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(side)
         # Rows before `lo` and after `hi` are zeros that no design row of this rank reads: the last

@@ -156,3 +156,40 @@ def test_packed_triangle_roundtrip_and_single_rank_comm():
   _lib.check(lib.td_comm_destroy(comm))
   # too small a packed buffer is reported, not overrun (needs a multi-rank comm to get that far: world 1 returns early)
   assert lib.td_pack_upper_f32(None, ctypes.c_int64(4), ctypes.c_int64(4), None, st) != 0
+
+
+def test_sharded_upload_of_a_rank_local_host_array():
+  """TrialBrainData.set_trials(upload_rows=...) with pinned host arrays that hold ONLY the rows a rank
+  touches (its design rows + lag halo, sharding.needed_row_range): the device arrays carry those rows
+  at their global positions, zeros elsewhere, and the rank's partial Gram equals the one computed from
+  the whole recording."""
+  from telluride_decoding_b200 import brain_data
+  lens = [3000, 2500, 4000]
+  c, pre, post = 16, 3, 12
+  x, _, y, starts = _trials(3, lens, c)
+  names = ['a', 'b', 'c']
+  world = 3
+  whole = None
+  for rank in range(world):
+    lo, hi = sharding.needed_row_range(starts, lens, lens, pre, post, rank, world)
+    xp = torch.from_numpy(x[lo:hi].copy()).pin_memory()
+    yp = torch.from_numpy(y[lo:hi].copy()).pin_memory()
+    bd = brain_data.TrialBrainData('eeg', 'env', 100.0, pre_context=pre, post_context=post,
+                                   final_batch_size=500, shuffle_buffer_size=0)
+    bd.set_trials(names, lens, xp, yp, upload_rows=(lo, hi))
+    ds = bd.create_dataset('train')
+    sx = ds.stream('x')
+    torch.cuda.synchronize()
+    dev = sx.data.cpu().numpy()
+    np.testing.assert_array_equal(dev[lo:hi], x[lo:hi])
+    assert not dev[:lo].any() and not dev[hi:].any()
+    order = sorted(range(len(sx.seg_start)), key=lambda i: sx.seg_start[i])
+    f_sorted, k_sorted = sharding.shard_rows(None, [ds.seg_rows[i] for i in order], rank, world)
+    first, keep = [0] * 3, [0] * 3
+    for pos, i in enumerate(order):
+      first[i], keep[i] = f_sorted[pos], k_sorted[pos]
+    g = ops.lagged_gram([sx], keep, seg_first=first).double()
+    whole = g if whole is None else whole + g
+  design = _oracle_design(x, starts, lens, [n - n % 1 for n in lens], pre, post)
+  # drop_remainder keeps 9500 of 9500 rows (500 | 9500): all rows
+  assert gpu_util.rel_fro(whole.cpu().numpy(), design.T @ design) < 1e-5
