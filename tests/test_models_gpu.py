@@ -459,3 +459,26 @@ def test_ledoit_wolf_shrinkage_on_interleaved_trials():
   for s, lo, hi, batch in pieces:
     per_batch[batch] = per_batch.get(batch, 0) + hi - lo
   assert set(per_batch.values()) == {200} and len(per_batch) == ds.num_batches
+
+
+def test_lambda_sweep_matches_the_reference_at_every_lambda_on_a_bench_like_design():
+  """The bench's sweep (logspace(-6, 3, 20)) on a design like the bench's (z-scored white sensors, an
+  FIR-driven envelope): weights within 1e-4 of the reference at ALL 20 lambdas -- here the design is
+  well conditioned, so the reference's own float32 solve is trustworthy down to lambda = 1e-6."""
+  rng = np.random.RandomState(21)
+  n, c, post = 23040, 16, 15                      # 3 trials' worth of frames, D = 256
+  x = rng.randn(n, c).astype(np.float32)
+  taps = (rng.randn(10, c) / 10).astype(np.float32)
+  y = np.zeros((n, 1), np.float32)
+  for k in range(10):
+    y[:n - k, 0] += x[k:] @ taps[k]
+  y += 0.5 * rng.randn(n, 1).astype(np.float32)
+  bd = gpu_util.make_test_data(x, y, post_context=post, final_batch_size=768)
+  stats = brain_model.RegressionStats.from_dataset(bd.create_dataset('train'))
+  lambdas = np.logspace(-6, 3, 20)
+  sweep = brain_model.solve_regression(stats, lambdas, method=2)
+  batches = gpu_util.oracle_batches(x, y, post=post, batch=768)
+  for lam, (w2, b2) in zip(lambdas, sweep):
+    w, b, _, _, _ = ora.linear_regressor_from_batches(batches, float(lam))
+    assert gpu_util.rel_fro(w2.cpu().numpy(), w) < W_TOL, lam
+    assert abs(float(b2[0]) - float(b[0, 0])) < W_TOL, lam
