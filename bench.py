@@ -651,6 +651,11 @@ def main():
   ms_per_step = float(t_res[0].item()) / args.steps
   allreduce_ms = float(t_res[1].item())
   gram_kernel_ms_max = float(t_res[2].item())
+  # The rank that finishes its Gram last waits for nobody: its figure is the collective itself.
+  t_min = torch.tensor([float(np.mean(ar_ms))], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t_min, op=dist.ReduceOp.MIN)
+  allreduce_ms_min = float(t_min.item())
   n_stat = stats.n
 
   # ---- end-to-end arm: host buffers in, fitted weights out ------------------------------------------
@@ -804,6 +809,9 @@ def main():
       gpu_launches=n_launch * args.steps,
       tflops_alg=float(frames) * d * (d + 1) / (ms_per_step * 1e-3) / 1e12,
       gram_kernel_ms=kernel_ms, allreduce_ms=allreduce_ms if world > 1 else 0.0,
+      allreduce_ms_note='stats_done -> allreduce_done: max over ranks (includes waiting for the slowest rank\'s '
+                        'Gram); min over ranks = %.2f ms = the collectives themselves (packed upper triangle of '
+                        'the Gram + thin sums, pack / unpack / mirror)' % (allreduce_ms_min if world > 1 else 0.0),
       step_wall_ms=wall / args.steps * 1e3, rows_checked=n_stat == frames,
       roofline=roofline, e2e=e2e, clocks=clocks, cpu_baseline=cpu, parity=parity, legs=legs)
   print(json.dumps(line))
