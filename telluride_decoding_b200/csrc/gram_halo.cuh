@@ -25,7 +25,10 @@
 
 namespace hk {
 
-constexpr int STAGES = 4;
+#ifndef TD_HALO_STAGES
+#define TD_HALO_STAGES 4
+#endif
+constexpr int STAGES = TD_HALO_STAGES;
 constexpr int BOX_FRAMES = 48;                          // 32 frames + 15 frames of lag halo + 1
 constexpr int BOX_CH = 8;                               // channels per row group
 constexpr int BOX_BYTES = BOX_FRAMES * BOX_CH * 4;      // 1536
@@ -144,12 +147,13 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
       while (wi.next(P, it)) {
         const int ta = (it.tm * 2 + (int)rank) * RG_PER_CTA;
         const int tb = (it.tn * 2 + (int)rank) * RG_PER_CTA;
-        int rq[2 * RG_PER_CTA], rc[2 * RG_PER_CTA], rd[2 * RG_PER_CTA];
+        // per row group, packed into one register: channel << 17 | (lag shift & 0x7fff) << 2 | issue << 1 | stream
+        uint32_t rg[2 * RG_PER_CTA];
         uint32_t n_issue = 0;
 #pragma unroll
         for (int i = 0; i < 2 * RG_PER_CTA; ++i) {
           const int4 g = __ldg(&P.rgs[(i < RG_PER_CTA ? ta : tb) + (i & (RG_PER_CTA - 1))]);
-          rq[i] = g.x; rc[i] = g.y; rd[i] = g.z;
+          rg[i] = ((uint32_t)g.y << 17) | (((uint32_t)g.z & 0x7fffu) << 2) | ((uint32_t)g.x & 3u);
           n_issue += (uint32_t)(g.x >> 1) & 1u;
         }
         int4 kn = __ldg(&P.ktiles[2 * it.kt_begin]);
@@ -163,10 +167,12 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
             const uint32_t sbase = smem_base + stage * STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < 2 * RG_PER_CTA; ++i) {
-              if (rq[i] & 2) {
+              if (rg[i] & 2u) {
                 const uint32_t dst = sbase + (i < RG_PER_CTA ? OFF_ARAW : OFF_BRAW) + (i & (RG_PER_CTA - 1)) * BOX_BYTES;
-                const int q = rq[i] & 1;
-                tma_load_2d(dst, q ? &tmap1 : &tmap0, fb, rc[i], (q ? kc.y : kc.x) + rd[i]);
+                const int q = (int)(rg[i] & 1u);
+                const int c0 = (int)(rg[i] >> 17);
+                const int d0 = ((int)(rg[i] << 15)) >> 17;          // sign-extended 15-bit lag shift
+                tma_load_2d(dst, q ? &tmap1 : &tmap0, fb, c0, (q ? kc.y : kc.x) + d0);
               }
             }
           }
