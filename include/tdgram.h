@@ -84,11 +84,17 @@ int td_shutdown(void);
  *   3  CTA pairs, A operand in tensor memory, operands fetched as (lag, channel-block) TMA boxes from
  *      four shifted channel-major copies of the recording staged in the workspace (round-1 kernel).
  *   2  both operands from shared memory (the only flavour for cta_group 1, i.e. narrow designs).
+ *   5  (opt-in, one stream) the block-Toeplitz structure of a lagged Gram: only the first block row
+ *      C(d)[c1,c2] = sum_t x[t-pre,c1] x[t-pre+d,c2] is contracted on the tensor cores (the method-4
+ *      kernel in rectangular mode, L/2 times fewer MMAs), every other block follows along the lag
+ *      diagonals from C(d) plus edge sums over the first / last k1 frames of each segment.  Same
+ *      3xTF32 arithmetic and row semantics; the dense flavours stay the default and the reference
+ *      point of the roofline.
  * method 1: fp32 CUDA-core kernel kept as an on-device cross-check.
  * Workspace: td_lagged_gram_workspace_bytes bytes of device memory.
  * ------------------------------------------------------------------------------------- */
 typedef struct td_gram_options {
-  int32_t method;        /* 0 = tcgen05 3xTF32 (default), 1 = fp32 SIMT cross-check, 2 / 3 / 4 = force a tcgen05 flavour */
+  int32_t method;        /* 0 = tcgen05 3xTF32 (default), 1 = fp32 SIMT cross-check, 2 / 3 / 4 = force a dense tcgen05 flavour, 5 = block-Toeplitz */
   int32_t cta_group;     /* 0 = auto, 1 = 128x128 tiles per CTA, 2 = CTA-pair 256x256 tiles */
   int32_t chunk_rows;    /* TMEM flush period in frames (0 = default 128) */
   int32_t superchunk_rows; /* L2 working-set period in frames (0 = auto) */

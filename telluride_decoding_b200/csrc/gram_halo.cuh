@@ -59,6 +59,12 @@ struct HaloParams {
   const int4* rgs;        // [Dpad / 32] {stream | issue << 1, first channel, lag shift k0 - pre, byte offset in the operand's raw region}
   const int4* ktiles;     // [NK][2] {raw row of design row 0: stream 0, stream 1, begin | end << 8 | edge << 16, -t0}, {len0 - t0, len1 - t0, 0, 0}
   const int* out_idx;     // [Dpad] tile-space row -> row/col of G, -1 for padding
+  // Rectangular mode (method 5): the A operand comes from its own row-group table (rect_ta pair tiles
+  // of A rows against all nt pair tiles of B rows), every element (m, n) is written at
+  // G[out_idx[n]][out_idx_a[m]] (no triangle), ntri = rect_ta * nt.
+  int rect_ta;
+  const int4* rgs_a;
+  const int* out_idx_a;
   float* G;
   long long ldg;
   long long batch_stride; // 0: one Gram; else superchunk sc (= one segment) accumulates into G + sc * batch_stride
@@ -69,6 +75,11 @@ struct HaloParams {
   long long total_steps;
   long long* prof;
 };
+
+}  // namespace hk
+template <>
+__device__ __forceinline__ int rect_tiles_of<hk::HaloParams>(const hk::HaloParams& P) { return P.rect_ta; }
+namespace hk {
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -150,9 +161,10 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
         // per row group, packed into one register: channel << 17 | (lag shift & 0x7fff) << 2 | issue << 1 | stream
         uint32_t rg[2 * RG_PER_CTA];
         uint32_t n_issue = 0;
+        const int4* rgs_of_a = P.rect_ta ? P.rgs_a : P.rgs;
 #pragma unroll
         for (int i = 0; i < 2 * RG_PER_CTA; ++i) {
-          const int4 g = __ldg(&P.rgs[(i < RG_PER_CTA ? ta : tb) + (i & (RG_PER_CTA - 1))]);
+          const int4 g = __ldg(i < RG_PER_CTA ? &rgs_of_a[ta + i] : &P.rgs[tb + (i & (RG_PER_CTA - 1))]);
           rg[i] = ((uint32_t)g.y << 17) | (((uint32_t)g.z & 0x7fffu) << 2) | ((uint32_t)g.x & 3u);
           n_issue += (uint32_t)(g.x >> 1) & 1u;
         }
@@ -264,7 +276,7 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
     uint32_t phase = 0;
     uint32_t kcount = 0;
     while (wi.next(P, it)) {
-      const int4 ga = __ldg(&P.rgs[(it.tm * 2 + (int)rank) * RG_PER_CTA + quad]);
+      const int4 ga = __ldg(&(P.rect_ta ? P.rgs_a : P.rgs)[(it.tm * 2 + (int)rank) * RG_PER_CTA + quad]);
       const int4 gb = __ldg(&P.rgs[(it.tn * 2 + (int)rank) * RG_PER_CTA + quad]);
       const uint32_t a_rd = OFF_ARAW + (uint32_t)ga.w + (uint32_t)(kk * BOX_CH + cc) * 4u;
       const uint32_t b_rd = OFF_BRAW + (uint32_t)gb.w + (uint32_t)(kk * BOX_CH + cc) * 4u;
@@ -378,13 +390,14 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
       // rows of one row group (4 lags x 8 channels): 4 runs of 8 consecutive addresses.  Accumulator
       // column i of half h is B row h*64 + i%64 of CTA i/64.
       const int m_row = (it.tm * 2 + (int)rank) * TILE_ROWS + quad * 32 + lane;
-      const int m_out = __ldg(&P.out_idx[m_row]);
+      const int m_out = __ldg(&(P.rect_ta ? P.out_idx_a : P.out_idx)[m_row]);
+      const bool all_pairs = P.rect_ta != 0 || it.tm > it.tn;
       float* Gout = P.G + (it.kt_begin / P.KS) * P.batch_stride;      // batched: one Gram per superchunk
 #pragma unroll
       for (int i = 0; i < NACC; ++i) {
         const int n_row = it.tn * 256 + (i >> 6) * TILE_ROWS + half * 64 + (i & 63);
         const int n_out = __ldg(&P.out_idx[n_row]);
-        if (m_out >= 0 && n_out >= 0 && (it.tm > it.tn || n_row <= m_row))
+        if (m_out >= 0 && n_out >= 0 && (all_pairs || n_row <= m_row))
           atomicAdd(Gout + (long long)n_out * P.ldg + m_out, acc[i]);
       }
     }

@@ -87,6 +87,11 @@ struct WorkItem {
 // same time (its staged frames stay L2 resident while every tile consumes them): inside superchunk
 // sc the ntri * KS k-tile steps are split evenly over the workers (stream-K), then everyone moves
 // on to sc + 1.  Identical decode in every warp role.
+// Number of A-operand tiles of a RECTANGULAR problem (A rows x all B rows; method 5), 0 for the
+// symmetric lower-triangle tile set.
+template <class PT>
+__device__ __forceinline__ int rect_tiles_of(const PT&) { return 0; }
+
 struct WorkIter {
   long long sc, nsc, per_sc, p, hi;
   int worker, n_workers;
@@ -116,11 +121,17 @@ struct WorkIter {
       const long long e = min(b + len, P.NK);
       p += len;
       if (b < e) {
-        int tm = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
-        while ((long long)(tm + 1) * (tm + 2) / 2 <= tile) ++tm;
-        while ((long long)tm * (tm + 1) / 2 > tile) --tm;
-        it.tm = tm;
-        it.tn = tile - tm * (tm + 1) / 2;
+        const int ta = rect_tiles_of(P);
+        if (ta > 0) {                              // rectangular: tile = tn * ta + tm
+          it.tn = tile / ta;
+          it.tm = tile - it.tn * ta;
+        } else {
+          int tm = (int)((sqrtf(8.0f * (float)tile + 1.0f) - 1.0f) * 0.5f);
+          while ((long long)(tm + 1) * (tm + 2) / 2 <= tile) ++tm;
+          while ((long long)tm * (tm + 1) / 2 > tile) --tm;
+          it.tm = tm;
+          it.tn = tile - tm * (tm + 1) / 2;
+        }
         it.kt_begin = b;
         it.kt_end = e;
         return true;
@@ -876,6 +887,9 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
   if (pl.NK > 0) {
     hk::HaloParams P;
     P.batch_stride = batched ? pl.Dz * ldg : 0;
+    P.rect_ta = 0;
+    P.rgs_a = nullptr;
+    P.out_idx_a = nullptr;
     P.rgs = reinterpret_cast<const int4*>(ws + pl.off_rgs);
     P.ktiles = reinterpret_cast<const int4*>(ws + pl.off_ktiles);
     P.out_idx = reinterpret_cast<const int*>(ws + pl.off_outidx);
@@ -948,13 +962,65 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
   return TD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Method 5: the Gram of a lagged design is block-Toeplitz up to edge terms.
+//
+//   G[(k1,c1),(k2,c2)] = sum_{t in rows} x~[t-pre+k1, c1] x~[t-pre+k2, c2]      (x~ = x, zero outside the trial)
+//                      = C(d)[c1,c2] + sum_seg ( T_seg(k1, d) - H_seg(k1, d) ),    d = k2 - k1 >= 0
+//   C(d)[c1,c2] = sum_{t in rows} x~[t-pre, c1] x~[t-pre+d, c2]                  (the k1 = 0 block row)
+//   H(k1, d) = sum_{u = first-pre}^{first-pre+k1-1} x~[u,c1] x~[u+d,c2]           (k1 frames at the head)
+//   T(k1, d) = sum_{u = keep-pre}^{keep-pre+k1-1}  x~[u,c1] x~[u+d,c2]           (k1 frames past the tail)
+//
+// So only the first block row is a real contraction -- C x (C L) outputs instead of (C L)^2 / 2: the
+// tcgen05 kernel runs in rectangular mode (A = the lag-0 rows, B = every row), L / 2 times fewer MMAs
+// -- and toeplitz_expand_kernel fills G along the lag diagonals, carrying the edge sums (k1 more
+// outer products per diagonal step and segment).  Same 3xTF32 arithmetic, same row semantics
+// (seg_first / seg_keep, zero padding at trial edges); one stream only.
+// ---------------------------------------------------------------------------------------------
+struct SegEdge { long long start, len, first, keep; };
+
+// grid: (ceil(C / 32), C, L): thread = (c2, c1, d).  Ct[(d*C + c2)][c1] holds C(d)[c1, c2].
+__global__ void __launch_bounds__(32) toeplitz_expand_kernel(const float* __restrict__ Ct, long long ldc,
+                                                             const float* __restrict__ x, long long ld, int C, int L,
+                                                             int pre, const SegEdge* __restrict__ segs, int n_seg,
+                                                             float* __restrict__ G, long long ldg) {
+  const int c2 = blockIdx.x * 32 + threadIdx.x;
+  const int c1 = blockIdx.y;
+  const int d = blockIdx.z;
+  // Upper triangle only (i <= j in the design's lag-major column order; td_symmetrize_f32 mirrors it):
+  // on the block diagonal (d = 0) that is c1 <= c2, so every entry has exactly one writer.
+  if (c2 >= C || (d == 0 && c2 < c1)) return;
+  const double base = (double)Ct[((long long)d * C + c2) * ldc + c1];
+  double run = 0.0;
+  for (int k1 = 0; k1 + d < L; ++k1) {
+    const float v = (float)(base + run);
+    const long long i = (long long)k1 * C + c1, j = (long long)(k1 + d) * C + c2;
+    G[i * ldg + j] = v;
+    // edge terms of the next diagonal step: one more frame at the tail, one fewer at the head
+    double delta = 0.0;
+    for (int s = 0; s < n_seg; ++s) {
+      const SegEdge e = segs[s];
+      if (e.keep <= e.first) continue;
+      const float* xs = x + e.start * ld;
+      const long long ut = e.keep - pre + k1, uh = e.first - pre + k1;
+      if (ut >= 0 && ut + d < e.len) delta += (double)__ldg(xs + ut * ld + c1) * (double)__ldg(xs + (ut + d) * ld + c2);
+      if (uh >= 0 && uh + d < e.len) delta -= (double)__ldg(xs + uh * ld + c1) * (double)__ldg(xs + (uh + d) * ld + c2);
+    }
+    run += delta;
+  }
+}
+
+int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_first, const int64_t* seg_keep,
+                 int n_seg, float* G, int64_t ldg, const td_gram_options* opt, void* workspace,
+                 size_t workspace_bytes, cudaStream_t st, size_t* bytes_only);
+
 // Does this call run the halo kernel (method 4)?  Explicitly, or automatically (method 0) when the
 // design is wide enough for CTA pairs (>= 512 tile rows) and DEFAULT_PAIR_METHOD says so.
 constexpr int DEFAULT_PAIR_METHOD = 4;
 int use_halo(const td_stream* streams, int n_streams, const td_gram_options* opt, bool* halo) {
   const int m = opt ? opt->method : 0;
   const int cg = opt ? opt->cta_group : 0;
-  TD_REQUIRE(m >= 0 && m <= 4, "td_lagged_gram: unknown method %d", m);
+  TD_REQUIRE(m >= 0 && m <= 5, "td_lagged_gram: unknown method %d", m);
   TD_REQUIRE(cg >= 0 && cg <= 2, "td_lagged_gram: cta_group must be 0, 1 or 2");
   TD_REQUIRE(!(m == 4 && cg == 1), "td_lagged_gram: method 4 (operand built on chip) needs CTA pairs");
   *halo = (m == 4);
@@ -971,6 +1037,183 @@ int use_halo(const td_stream* streams, int n_streams, const td_gram_options* opt
   return TD_OK;
 }
 
+
+// Workspace layout of method 5: [halo plan (tables, optional padded copy)] [A row groups] [A out_idx]
+// [segment edges] [Ct: Dz x ldc floats].  bytes_only != nullptr: just report the size.
+int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_first, const int64_t* seg_keep,
+                 int n_seg, float* G, int64_t ldg, const td_gram_options* opt, void* workspace,
+                 size_t workspace_bytes, cudaStream_t st, size_t* bytes_only) {
+  if (n_streams != 1) {
+    set_error("td_lagged_gram: method 5 (block-Toeplitz structure) handles one stream");
+    return TD_ERR_UNSUPPORTED;
+  }
+  HaloPlan pl;
+  int rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &pl);
+  if (rc) return rc;
+  const int C = pl.C[0], L = pl.L[0], pre = pl.pre[0];
+  const int n_rga = pl.ncg[0];                                        // lag group 0 of every channel group
+  const int n_rga_pad = (int)round_up(n_rga, 2 * hk::RG_PER_CTA);     // whole pair tiles of A rows
+  const int ta = n_rga_pad / (2 * hk::RG_PER_CTA);
+  const int64_t ldc = round_up(C, 4);
+  size_t off = pl.total;
+  const size_t off_rga = off;   off += (size_t)round_up((int64_t)n_rga_pad * (int64_t)sizeof(int4), 1024);
+  const size_t off_oia = off;   off += (size_t)round_up((int64_t)n_rga_pad * hk::RG_ROWS * (int64_t)sizeof(int), 1024);
+  const size_t off_seg = off;   off += (size_t)round_up((int64_t)n_seg * (int64_t)sizeof(SegEdge), 1024);
+  const size_t off_ct = off;    off += (size_t)round_up(pl.Dz * ldc * (int64_t)sizeof(float), 1024);
+  if (bytes_only) { *bytes_only = off; return TD_OK; }
+  TD_REQUIRE(ldg >= pl.Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)pl.Dz);
+  if (workspace_bytes < off || !workspace) {
+    set_error("td_lagged_gram_f32: workspace has %zu bytes, %zu needed", workspace_bytes, off);
+    return TD_ERR_WORKSPACE;
+  }
+  int dev = 0, sms = 0, cc_major = 0;
+  TD_CHECK_CUDA(cudaGetDevice(&dev));
+  TD_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  TD_CHECK_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_major != 10) {
+    set_error("td_lagged_gram_f32: the tcgen05 kernel needs an sm_100 device (found sm_%d)", cc_major * 10);
+    return TD_ERR_UNSUPPORTED;
+  }
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+
+  // ---- B side: every row group, as in run_halo ------------------------------------------------
+  const int n_rg_pad = (int)(pl.Dpad / hk::RG_ROWS);
+  std::vector<int4> rgs(n_rg_pad, make_int4(0, 0, 0, 0));
+  std::vector<int> out_idx(pl.Dpad, -1);
+  {
+    int head = -1, head_lg = 0;
+    int i = 0;
+    for (int cg = 0; cg < pl.ncg[0]; ++cg)
+      for (int lg = 0; lg < pl.nlg[0]; ++lg, ++i) {
+        const int r = i % hk::RG_PER_CTA;
+        const bool follows = r > 0 && head >= 0 && lg > 0 && head_lg + (i - head) == lg;
+        if (!follows) { head = i; head_lg = lg; }
+        const int head_r = head % hk::RG_PER_CTA;
+        rgs[i] = make_int4(0 | ((follows ? 0 : 1) << 1), cg * hk::BOX_CH, lg * hk::RG_LAGS - pre,
+                           head_r * hk::BOX_BYTES + (lg - head_lg) * hk::RG_LAGS * hk::BOX_CH * 4);
+        for (int kk = 0; kk < hk::RG_LAGS; ++kk)
+          for (int cc = 0; cc < hk::BOX_CH; ++cc) {
+            const int lag = lg * hk::RG_LAGS + kk, c = cg * hk::BOX_CH + cc;
+            if (lag < L && c < C) out_idx[(int64_t)i * hk::RG_ROWS + kk * hk::BOX_CH + cc] = lag * C + c;
+          }
+        if (r == hk::RG_PER_CTA - 1) head = -1;
+      }
+  }
+  // ---- A side: lag group 0 of every channel group; only its lag-0 rows are written out ------------
+  std::vector<int4> rga(n_rga_pad, make_int4(0, 0, 0, 0));
+  std::vector<int> oia((size_t)n_rga_pad * hk::RG_ROWS, -1);
+  for (int cg = 0; cg < n_rga; ++cg) {
+    rga[cg] = make_int4(0 | (1 << 1), cg * hk::BOX_CH, -pre, (cg % hk::RG_PER_CTA) * hk::BOX_BYTES);
+    for (int cc = 0; cc < hk::BOX_CH; ++cc)
+      if (cg * hk::BOX_CH + cc < C) oia[(size_t)cg * hk::RG_ROWS + cc] = cg * hk::BOX_CH + cc;      // kk = 0
+  }
+  std::vector<int4> ktiles;
+  ktiles.reserve((size_t)pl.NK * 2);
+  std::vector<SegEdge> edges(n_seg);
+  for (int s = 0; s < n_seg; ++s) {
+    const int64_t f = first_of(seg_first, s);
+    edges[s] = SegEdge{(long long)streams[0].seg_start[s], (long long)streams[0].seg_len[s], (long long)f,
+                       (long long)seg_keep[s]};
+    for (int64_t j = f / BK; j * BK < seg_keep[s] && seg_keep[s] > f; ++j) {
+      const int64_t t0 = j * BK;
+      const int begin = (int)std::max<int64_t>(0, f - t0);
+      const int end = (int)std::min<int64_t>(BK, seg_keep[s] - t0);
+      const int64_t len = streams[0].seg_len[s];
+      const int row0 = (int)(streams[0].seg_start[s] + t0 - pl.row_lo[0]);
+      const int hi = (int)std::max<int64_t>(std::min<int64_t>(len - t0, 1 << 24), -(1 << 24));
+      const int edge = (t0 - pre < 0 || t0 + BK - 1 + pl.post[0] >= len) ? 1 : 0;
+      ktiles.push_back(make_int4(row0, row0, begin | (end << 8) | (edge << 16), (int)std::max<int64_t>(-t0, -(1 << 24))));
+      ktiles.push_back(make_int4(hi, hi, 0, 0));
+    }
+  }
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_rgs, rgs.data(), rgs.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  if (!ktiles.empty())
+    TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_ktiles, ktiles.data(), ktiles.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + pl.off_outidx, out_idx.data(), out_idx.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + off_rga, rga.data(), rga.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + off_oia, oia.data(), oia.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  TD_CHECK_CUDA(cudaMemcpyAsync(ws + off_seg, edges.data(), edges.size() * sizeof(SegEdge), cudaMemcpyHostToDevice, st));
+
+  const float* base = streams[0].data_dev;
+  if (pl.staged[0]) {
+    float* dst = reinterpret_cast<float*>(ws + pl.off_stage[0]);
+    const int64_t total = pl.n_rows[0] * pl.ld_eff[0];
+    if (total > 0) {
+      pad_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(streams[0].data_dev, streams[0].ld, C, pl.row_lo[0],
+                                                                    pl.n_rows[0], dst, (int)pl.ld_eff[0]);
+      TD_CHECK_CUDA(cudaGetLastError());
+    }
+    base = dst;
+  }
+  CUtensorMap tmap;
+  rc = make_tmap_raw(&tmap, base, pl.n_rows[0], C, pl.ld_eff[0]);
+  if (rc) return rc;
+  float* Ct = reinterpret_cast<float*>(ws + off_ct);
+  TD_CHECK_CUDA(cudaMemsetAsync(Ct, 0, (size_t)pl.Dz * ldc * sizeof(float), st));
+  if (pl.NK > 0) {
+    hk::HaloParams P;
+    P.rgs = reinterpret_cast<const int4*>(ws + pl.off_rgs);
+    P.ktiles = reinterpret_cast<const int4*>(ws + pl.off_ktiles);
+    P.out_idx = reinterpret_cast<const int*>(ws + pl.off_outidx);
+    P.rect_ta = ta;
+    P.rgs_a = reinterpret_cast<const int4*>(ws + off_rga);
+    P.out_idx_a = reinterpret_cast<const int*>(ws + off_oia);
+    P.G = Ct;
+    P.ldg = ldc;
+    P.batch_stride = 0;
+    P.ntri = ta * pl.nt;
+    P.NK = pl.NK;
+    const int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 128;
+    P.chunk_kt = std::max(1, chunk_rows / BK);
+    int64_t sc_rows = (opt && opt->superchunk_rows > 0) ? opt->superchunk_rows : 0;
+    if (sc_rows == 0) sc_rows = std::max<int64_t>((48LL << 20) / (pl.ld_eff[0] * 4), 4096);
+    int64_t ks = std::max<int64_t>(P.chunk_kt, round_up(ceil_div(sc_rows, BK), P.chunk_kt));
+    ks = std::min<int64_t>(ks, round_up(pl.NK, P.chunk_kt));
+    int64_t nsc = ceil_div(pl.NK, ks);
+    ks = round_up(ceil_div(pl.NK, nsc), P.chunk_kt);
+    nsc = ceil_div(pl.NK, ks);
+    P.KS = (int)ks;
+    P.total_steps = nsc * P.ntri * ks;
+    int workers = sms / 2;
+    if (opt && opt->max_ctas > 0) workers = std::max(1, std::min(workers, opt->max_ctas / 2));
+    workers = (int)std::max<int64_t>(1, std::min<int64_t>(workers, ceil_div((int64_t)P.ntri * ks, P.chunk_kt)));
+    P.prof = nullptr;
+    const bool timed = opt && opt->reserved[0] == 1;
+    if (timed) {
+      if (!g_ev_start) {
+        TD_CHECK_CUDA(cudaEventCreate(&g_ev_start));
+        TD_CHECK_CUDA(cudaEventCreate(&g_ev_stop));
+      }
+      TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
+    }
+    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::SMEM_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers * 2);
+    cfg.blockDim = dim3(hk::NUM_THREADS);
+    cfg.dynamicSmemBytes = hk::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel, tmap, tmap, P));
+    TD_CHECK_CUDA(cudaGetLastError());
+    if (timed) {
+      TD_CHECK_CUDA(cudaEventRecord(g_ev_stop, st));
+      g_ev_valid = true;
+    }
+    if ((rc = debug_sync(st, "toeplitz block-row kernel"))) return rc;
+  }
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)C, (unsigned)L);
+  toeplitz_expand_kernel<<<grid, 32, 0, st>>>(Ct, ldc, streams[0].data_dev, streams[0].ld, C, L, pre,
+                                              reinterpret_cast<const SegEdge*>(ws + off_seg), n_seg, G, ldg);
+  TD_CHECK_CUDA(cudaGetLastError());
+  return td_symmetrize_f32(G, pl.Dz, ldg, /*from_upper=*/1, st);
+}
+
 }  // namespace
 }  // namespace td
 
@@ -981,6 +1224,8 @@ extern "C" int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_st
                                               int n_seg, const td_gram_options* opt, size_t* bytes) {
   TD_REQUIRE(streams && seg_keep && bytes, "td_lagged_gram_workspace_bytes: null argument");
   if (opt && opt->method == 1) { *bytes = 0; return TD_OK; }
+  if (opt && opt->method == 5)
+    return run_toeplitz(streams, n_streams, seg_first, seg_keep, n_seg, nullptr, 0, opt, nullptr, 0, nullptr, bytes);
   bool halo = false;
   int rc = use_halo(streams, n_streams, opt, &halo);
   if (rc) return rc;
@@ -1040,6 +1285,8 @@ extern "C" int td_lagged_gram_f32(const td_stream* streams, int n_streams, const
     TD_REQUIRE(ldg >= Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)Dz);
     return launch_gram_simt(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, st);
   }
+  if (opt && opt->method == 5)
+    return run_toeplitz(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, opt, workspace, workspace_bytes, st, nullptr);
   bool halo = false;
   int rc = use_halo(streams, n_streams, opt, &halo);
   if (rc) return rc;

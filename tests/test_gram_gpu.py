@@ -262,10 +262,13 @@ def test_argument_errors_surface_as_exceptions():
     dict(lens=[3000, 2500], c=40, pre=5, post=26, keep=[2900, 2500], first=[37, 1024]),
     dict(lens=[64] * 200, c=24, pre=4, post=19),                    # hundreds of tiny trials
 ])
-def test_operand_built_on_chip_masks_and_layouts(case):
+@pytest.mark.parametrize('method', [4, 5])
+def test_operand_built_on_chip_masks_and_layouts(case, method):
   """Method 4 specifics against the ORACLE's lagged design: zero padding at trial edges rebuilt by
   masks (the raw TMA box runs into the neighbouring trial; brain_data.py:448-452), row ranges,
-  channel / lag padding of the 4-lag x 8-channel row groups, unaligned and strided inputs."""
+  channel / lag padding of the 4-lag x 8-channel row groups, unaligned and strided inputs.
+  Method 5 (block-Toeplitz structure: only the first block row is contracted, the rest follows along
+  the lag diagonals with edge sums at the head and tail of every trial) on the same cases."""
   lens, c, pre, post = case['lens'], case['c'], case['pre'], case['post']
   keep = case.get('keep', lens)
   first = case.get('first')
@@ -274,7 +277,7 @@ def test_operand_built_on_chip_masks_and_layouts(case):
   xd = torch.as_tensor(x, device='cuda')[:, :c]
   starts = np.concatenate(([0], np.cumsum(lens)[:-1])).tolist()
   stream = ops.Stream(xd, pre, post, starts, lens)
-  got = ops.lagged_gram([stream], keep, options=ops.gram_options(method=4), seg_first=first)
+  got = ops.lagged_gram([stream], keep, options=ops.gram_options(method=method), seg_first=first)
   parts = []
   for s, n, k, f in zip(starts, lens, keep, first or [0] * len(lens)):
     parts.append(ora.add_context(x[s:s + n, :c], pre, post)[f:k].astype(np.float64))
@@ -293,3 +296,28 @@ def test_operand_built_on_chip_two_streams_with_offset():
                         options=ops.gram_options(method=4)).cpu().numpy()
     z = np.concatenate([gpu_util.design64(batches), gpu_util.design64(batches, 'input_2')], axis=1)
     assert gpu_util.rel_fro(g, z.T @ z) < GRAM_TOL
+
+
+def test_block_toeplitz_gram_on_config2_and_sharded_rows():
+  """Method 5 at the cfg 2 shape (one trial) against the dense kernel, and summed over the row ranges
+  of three ranks (mid-trial cuts: the head / tail edge sums then sit in the middle of a trial)."""
+  from telluride_decoding_b200 import sharding
+  gen = torch.Generator(device='cuda')
+  gen.manual_seed(12)
+  n_trials, n, c, lags = 4, 7680, 64, 32
+  xd = torch.randn((n_trials * n, c), generator=gen, device='cuda')
+  starts = [i * n for i in range(n_trials)]
+  lens = [n] * n_trials
+  keep = [n, n - 128, n, n - 5]
+  s = ops.Stream(xd, 3, lags - 4, starts, lens)
+  dense = ops.lagged_gram([s], keep).double()
+  fast = ops.lagged_gram([s], keep, options=ops.gram_options(method=5))
+  assert torch.equal(fast, fast.t())
+  assert gpu_util.rel_fro(fast.cpu().numpy(), dense.cpu().numpy()) < 5e-6
+  total = torch.zeros_like(dense)
+  for rank in range(3):
+    first, mine = sharding.shard_rows(None, keep, rank, 3)
+    total += ops.lagged_gram([s], mine, seg_first=first, options=ops.gram_options(method=5)).double()
+  assert gpu_util.rel_fro(total.cpu().numpy(), dense.cpu().numpy()) < 5e-6
+  with pytest.raises(Exception, match='one stream'):
+    ops.lagged_gram([s, s], keep, options=ops.gram_options(method=5))

@@ -29,10 +29,11 @@ def run(name, n_trials, frames, c, lags, methods, reps=3, **kw):
           (name, m, k, w, f_alg / k / 1e9, float((blk - ref).abs().max() / ref.abs().max())), flush=True)
 
 which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+METHODS = [int(m) for m in sys.argv[2].split(',')] if len(sys.argv) > 2 else [3, 4]
 if which in ('all', 'cfg2'):
-  run('cfg2 64ch x 32 lags, 460800 frames', 60, 7680, 64, 32, [3, 4], reps=5)
+  run('cfg2 64ch x 32 lags, 460800 frames', 60, 7680, 64, 32, METHODS, reps=5)
 if which in ('all', 'cfg4'):
-  run('cfg4 slice 306ch x 100 lags, 300000 frames', 3, 100000, 306, 100, [3, 4], reps=2)
+  run('cfg4 slice 306ch x 100 lags, 300000 frames', 3, 100000, 306, 100, METHODS, reps=2)
 if which == 'sc':
   for sc in (0, 39200, 78400, 156800):
     print('superchunk_rows', sc)

