@@ -374,8 +374,12 @@ def batch_pearson(dataset, truth, pred):
 class BrainModelLinearRegression(BrainModel):
   """Linear regression computed deterministically from the data (brain_model.py:306-381)."""
 
-  def __init__(self, input_dataset, regularization_lambda=0.0, tensorboard_dir=None, **kwargs):
+  def __init__(self, input_dataset, regularization_lambda=0.0, tensorboard_dir=None,
+               gram_options=None, **kwargs):
+    """gram_options (not in the reference): ops.gram_options(...) for the statistics pass of fit(),
+    e.g. method=5 for the block-Toeplitz path; None = the dense tcgen05 kernel."""
     super(BrainModelLinearRegression, self).__init__(tensorboard_dir=tensorboard_dir, **kwargs)
+    self._gram_options = gram_options
     if not is_dataset(input_dataset):
       raise ValueError('Dataset must be a tf.data.datasert, not a %s' % type(input_dataset))
     self._input_width = input_dataset.element_spec[0]['input_1'].shape[-1]
@@ -413,7 +417,7 @@ class BrainModelLinearRegression(BrainModel):
                       'tf.data.Dataset, not %s.' % type(input_dataset))
     if y is not None:
       raise ValueError('Y value not needed, should be part of dataset.')
-    self.fit_from_stats(RegressionStats.from_dataset(input_dataset))
+    self.fit_from_stats(RegressionStats.from_dataset(input_dataset, gram_options=self._gram_options))
     return {}
 
   @property

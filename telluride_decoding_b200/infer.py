@@ -5,6 +5,8 @@ directories of SavedModels / TFRecords, evaluates every window size in one pass,
 attention decoder and reports the fraction of correct windows exactly as infer.py:399-407.
 """
 
+import re
+
 import numpy as np
 import torch
 
@@ -93,7 +95,6 @@ def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_l
        windows of every size inside each trial (result_store.py:262-271, step W // 2), decision
        (attention_decoder.py:128-173) and accuracy (infer.py:399-407).
   """
-  from telluride_decoding_b200 import brain_model
   window_list = [int(w) for w in (window_list or DEFAULT_WINDOW_LIST)]
   saved = (brain_data_obj.train_file_pattern, brain_data_obj.validate_file_pattern,
            brain_data_obj.test_file_pattern)
@@ -229,5 +230,4 @@ def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_l
 
 
 def _re_escape(name):
-  import re
   return re.escape(name)
