@@ -42,6 +42,17 @@ constexpr int OFF_ARAW = 2 * OPERAND_BYTES;
 constexpr int OFF_BRAW = OFF_ARAW + RAW_BYTES;
 constexpr int STAGE_BYTES = 2 * OPERAND_BYTES + 2 * RAW_BYTES;     // 44 KiB
 static_assert(STAGE_BYTES % 1024 == 0, "stage must keep the 1024-byte alignment of the swizzled tiles");
+// Rectangular flavour (method 5: A = the lag-0 rows only): an A row group is 1 lag x 32 channels, its raw
+// box 32 frames x 32 channels (no halo: one lag), so all 128 A rows of a CTA are real channels.
+constexpr int ABOX_CH = 32;
+constexpr int ABOX_FRAMES = 32;
+constexpr int ABOX_BYTES = ABOX_FRAMES * ABOX_CH * 4;    // 4096
+constexpr int RECT_RAW_A_BYTES = RG_PER_CTA * ABOX_BYTES;                      // 16 KiB
+constexpr int RECT_OFF_BRAW = OFF_ARAW + RECT_RAW_A_BYTES;
+constexpr int RECT_STAGE_BYTES = 2 * OPERAND_BYTES + RECT_RAW_A_BYTES + RAW_BYTES;   // 54 KiB
+static_assert(RECT_STAGE_BYTES % 1024 == 0, "stage must keep the 1024-byte alignment of the swizzled tiles");
+constexpr size_t RECT_SMEM_BYTES = (size_t)STAGES * RECT_STAGE_BYTES + 1024 + 256;
+static_assert(RECT_SMEM_BYTES <= 232448, "rectangular flavour exceeds the 227 KB of shared memory");
 constexpr int NUM_THREADS = 512;
 constexpr int NUM_CONV = 4;                              // warps 4..7
 constexpr int EPI_WARP0 = 8, NUM_EPI = 8;
@@ -95,10 +106,15 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   return v;
 }
 
+// RECT = false: symmetric Gram (lower-triangle tile set, A and B from the same row groups).
+// RECT = true:  rectangular product for method 5; tmap1 is then the A-side map (box 32 ch x 32 frames).
+template <bool RECT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
                         const __grid_constant__ CUtensorMap tmap1, const HaloParams P) {
   constexpr uint32_t IDESC = ptx::umma_idesc_tf32(256, 128);
+  constexpr int STAGE_BYTES = RECT ? RECT_STAGE_BYTES : hk::STAGE_BYTES;
+  constexpr int OFF_BRAW = RECT ? RECT_OFF_BRAW : hk::OFF_BRAW;
   using ts::HalfRing;
   using ts::lo_bits;
 
@@ -160,13 +176,13 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
         const int tb = (it.tn * 2 + (int)rank) * RG_PER_CTA;
         // per row group, packed into one register: channel << 17 | (lag shift & 0x7fff) << 2 | issue << 1 | stream
         uint32_t rg[2 * RG_PER_CTA];
-        uint32_t n_issue = 0;
-        const int4* rgs_of_a = P.rect_ta ? P.rgs_a : P.rgs;
+        const int4* rgs_of_a = RECT ? P.rgs_a : P.rgs;
+        uint32_t tx_bytes = 0;
 #pragma unroll
         for (int i = 0; i < 2 * RG_PER_CTA; ++i) {
           const int4 g = __ldg(i < RG_PER_CTA ? &rgs_of_a[ta + i] : &P.rgs[tb + (i & (RG_PER_CTA - 1))]);
           rg[i] = ((uint32_t)g.y << 17) | (((uint32_t)g.z & 0x7fffu) << 2) | ((uint32_t)g.x & 3u);
-          n_issue += (uint32_t)(g.x >> 1) & 1u;
+          if (g.x & 2) tx_bytes += (RECT && i < RG_PER_CTA) ? ABOX_BYTES : BOX_BYTES;
         }
         int4 kn = __ldg(&P.ktiles[2 * it.kt_begin]);
         for (long long kt = it.kt_begin; kt < it.kt_end; ++kt) {
@@ -175,16 +191,20 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           if (ptx::elect_one()) {
             const uint32_t fb = full_bar(stage);
-            ptx::mbar_expect_tx(fb, n_issue * BOX_BYTES);
+            ptx::mbar_expect_tx(fb, tx_bytes);
             const uint32_t sbase = smem_base + stage * STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < 2 * RG_PER_CTA; ++i) {
               if (rg[i] & 2u) {
-                const uint32_t dst = sbase + (i < RG_PER_CTA ? OFF_ARAW : OFF_BRAW) + (i & (RG_PER_CTA - 1)) * BOX_BYTES;
                 const int q = (int)(rg[i] & 1u);
                 const int c0 = (int)(rg[i] >> 17);
                 const int d0 = ((int)(rg[i] << 15)) >> 17;          // sign-extended 15-bit lag shift
-                tma_load_2d(dst, q ? &tmap1 : &tmap0, fb, c0, (q ? kc.y : kc.x) + d0);
+                if (RECT && i < RG_PER_CTA) {
+                  tma_load_2d(sbase + OFF_ARAW + i * ABOX_BYTES, &tmap1, fb, c0, kc.x + d0);
+                } else {
+                  const uint32_t dst = sbase + (i < RG_PER_CTA ? OFF_ARAW : OFF_BRAW) + (i & (RG_PER_CTA - 1)) * BOX_BYTES;
+                  tma_load_2d(dst, (!RECT && q) ? &tmap1 : &tmap0, fb, c0, (q ? kc.y : kc.x) + d0);
+                }
               }
             }
           }
@@ -276,11 +296,13 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
     uint32_t phase = 0;
     uint32_t kcount = 0;
     while (wi.next(P, it)) {
-      const int4 ga = __ldg(&(P.rect_ta ? P.rgs_a : P.rgs)[(it.tm * 2 + (int)rank) * RG_PER_CTA + quad]);
+      const int4 ga = __ldg(&(RECT ? P.rgs_a : P.rgs)[(it.tm * 2 + (int)rank) * RG_PER_CTA + quad]);
       const int4 gb = __ldg(&P.rgs[(it.tn * 2 + (int)rank) * RG_PER_CTA + quad]);
-      const uint32_t a_rd = OFF_ARAW + (uint32_t)ga.w + (uint32_t)(kk * BOX_CH + cc) * 4u;
+      // RECT: lane = channel of a 32-channel, one-lag row group (32 consecutive words per frame)
+      const uint32_t a_rd = OFF_ARAW + (uint32_t)ga.w + (RECT ? (uint32_t)lane * 4u : (uint32_t)(kk * BOX_CH + cc) * 4u);
       const uint32_t b_rd = OFF_BRAW + (uint32_t)gb.w + (uint32_t)(kk * BOX_CH + cc) * 4u;
-      const int a_d = ga.z + kk, b_d = gb.z + kk;        // lag shift k - pre of this thread's rows
+      constexpr uint32_t A_FRAME_BYTES = RECT ? ABOX_CH * 4 : BOX_CH * 4;
+      const int a_d = ga.z + (RECT ? 0 : kk), b_d = gb.z + kk;        // lag shift k - pre of this thread's rows
       const int a_q = ga.x & 1, b_q = gb.x & 1;
       int4 kn0 = __ldg(&P.ktiles[2 * it.kt_begin]);
       int4 kn1 = __ldg(&P.ktiles[2 * it.kt_begin + 1]);
@@ -307,7 +329,7 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
           uint32_t hi[16], lo[16], bv[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            hi[e] = lds32(sbase + a_rd + (uint32_t)((hh * 16 + e) * BOX_CH * 4));
+            hi[e] = lds32(sbase + a_rd + (uint32_t)(hh * 16 + e) * A_FRAME_BYTES);
             bv[e] = lds32(sbase + b_rd + (uint32_t)((hh * 16 + e) * BOX_CH * 4));
           }
           if (edge) {
@@ -390,8 +412,8 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
       // rows of one row group (4 lags x 8 channels): 4 runs of 8 consecutive addresses.  Accumulator
       // column i of half h is B row h*64 + i%64 of CTA i/64.
       const int m_row = (it.tm * 2 + (int)rank) * TILE_ROWS + quad * 32 + lane;
-      const int m_out = __ldg(&(P.rect_ta ? P.out_idx_a : P.out_idx)[m_row]);
-      const bool all_pairs = P.rect_ta != 0 || it.tm > it.tn;
+      const int m_out = __ldg(&(RECT ? P.out_idx_a : P.out_idx)[m_row]);
+      const bool all_pairs = RECT || it.tm > it.tn;
       float* Gout = P.G + (it.kt_begin / P.KS) * P.batch_stride;      // batched: one Gram per superchunk
 #pragma unroll
       for (int i = 0; i < NACC; ++i) {

@@ -748,13 +748,14 @@ int make_halo_plan(const td_stream* streams, int n_streams, const int64_t* seg_f
   return TD_OK;
 }
 
-int make_tmap_raw(CUtensorMap* m, const float* base, int64_t n_rows, int C, int64_t ld) {
+int make_tmap_raw(CUtensorMap* m, const float* base, int64_t n_rows, int C, int64_t ld,
+                  int box_ch = hk::BOX_CH, int box_frames = hk::BOX_FRAMES) {
   EncodeTiledFn enc;
   int rc = get_encode_fn(&enc);
   if (rc) return rc;
   cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)std::max<int64_t>(n_rows, 1)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)hk::BOX_CH, (cuuint32_t)hk::BOX_FRAMES};
+  cuuint32_t box[2] = {(cuuint32_t)box_ch, (cuuint32_t)box_frames};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -928,7 +929,7 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
       }
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
-    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::SMEM_BYTES));
+    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::SMEM_BYTES));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * 2);
     cfg.blockDim = dim3(hk::NUM_THREADS);
@@ -941,7 +942,7 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel, tmaps[0], tmaps[1], P));
+    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel<false>, tmaps[0], tmaps[1], P));
     TD_CHECK_CUDA(cudaGetLastError());
     if (timed) {
       TD_CHECK_CUDA(cudaEventRecord(g_ev_stop, st));
@@ -1051,7 +1052,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
   int rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &pl);
   if (rc) return rc;
   const int C = pl.C[0], L = pl.L[0], pre = pl.pre[0];
-  const int n_rga = pl.ncg[0];                                        // lag group 0 of every channel group
+  const int n_rga = (int)ceil_div(C, hk::ABOX_CH);                    // A row groups: 32 channels at lag 0
   const int n_rga_pad = (int)round_up(n_rga, 2 * hk::RG_PER_CTA);     // whole pair tiles of A rows
   const int ta = n_rga_pad / (2 * hk::RG_PER_CTA);
   const int64_t ldc = round_up(C, 4);
@@ -1099,13 +1100,13 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
         if (r == hk::RG_PER_CTA - 1) head = -1;
       }
   }
-  // ---- A side: lag group 0 of every channel group; only its lag-0 rows are written out ------------
+  // ---- A side: the lag-0 row of every channel, 32 channels per row group (its own 32 x 32 raw box) ----
   std::vector<int4> rga(n_rga_pad, make_int4(0, 0, 0, 0));
   std::vector<int> oia((size_t)n_rga_pad * hk::RG_ROWS, -1);
   for (int cg = 0; cg < n_rga; ++cg) {
-    rga[cg] = make_int4(0 | (1 << 1), cg * hk::BOX_CH, -pre, (cg % hk::RG_PER_CTA) * hk::BOX_BYTES);
-    for (int cc = 0; cc < hk::BOX_CH; ++cc)
-      if (cg * hk::BOX_CH + cc < C) oia[(size_t)cg * hk::RG_ROWS + cc] = cg * hk::BOX_CH + cc;      // kk = 0
+    rga[cg] = make_int4(0 | (1 << 1), cg * hk::ABOX_CH, -pre, (cg % hk::RG_PER_CTA) * hk::ABOX_BYTES);
+    for (int cc = 0; cc < hk::ABOX_CH; ++cc)
+      if (cg * hk::ABOX_CH + cc < C) oia[(size_t)cg * hk::RG_ROWS + cc] = cg * hk::ABOX_CH + cc;
   }
   std::vector<int4> ktiles;
   ktiles.reserve((size_t)pl.NK * 2);
@@ -1145,8 +1146,10 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     }
     base = dst;
   }
-  CUtensorMap tmap;
+  CUtensorMap tmap, tmap_a;
   rc = make_tmap_raw(&tmap, base, pl.n_rows[0], C, pl.ld_eff[0]);
+  if (rc) return rc;
+  rc = make_tmap_raw(&tmap_a, base, pl.n_rows[0], C, pl.ld_eff[0], hk::ABOX_CH, hk::ABOX_FRAMES);
   if (rc) return rc;
   float* Ct = reinterpret_cast<float*>(ws + off_ct);
   TD_CHECK_CUDA(cudaMemsetAsync(Ct, 0, (size_t)pl.Dz * ldc * sizeof(float), st));
@@ -1186,11 +1189,11 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
       }
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
-    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::SMEM_BYTES));
+    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::RECT_SMEM_BYTES));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * 2);
     cfg.blockDim = dim3(hk::NUM_THREADS);
-    cfg.dynamicSmemBytes = hk::SMEM_BYTES;
+    cfg.dynamicSmemBytes = hk::RECT_SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1199,7 +1202,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel, tmap, tmap, P));
+    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel<true>, tmap, tmap_a, P));
     TD_CHECK_CUDA(cudaGetLastError());
     if (timed) {
       TD_CHECK_CUDA(cudaEventRecord(g_ev_stop, st));
