@@ -79,10 +79,11 @@ struct HalfRing {
   }
 };
 
-// lo = tf32_rna(x - trunc_tf32(x)); the subtraction is exact in fp32.
+// lo = tf32_rna(x - trunc_tf32(x)); the subtraction is exact in fp32.  Round-to-nearest = add half a
+// tf32 ulp to the magnitude bits; the 13 low bits are left as they fall, kind::tf32 does not read them.
 __device__ __forceinline__ uint32_t lo_bits(uint32_t x) {
   const float d = __uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u);
-  return (__float_as_uint(d) + 0x1000u) & 0xFFFFE000u;
+  return __float_as_uint(d) + 0x1000u;
 }
 
 template <int ISSUERS>
