@@ -521,6 +521,7 @@ def leg_cfg5(dev, n_trials=1000):
                                           return_details=True)
   acc, det = run()                                         # warm-up (allocator, handles)
   n_windows = sum(len(det[w]['attention']) for w in widths)
+  solver = det['solver']
   del det
   torch.cuda.synchronize()
   t0 = time.perf_counter()
@@ -533,9 +534,9 @@ def leg_cfg5(dev, n_trials=1000):
                        '1/2/5/10/20/30 s (step W/2), reduction first, winner-take-all' % (n_trials, n_trials),
               loo_wall_s=wall, frames_per_s=n / wall, folds_per_s=n_trials / wall,
               windows_per_s=2 * n_windows / wall, decisions=n_windows,
-              accuracy={str(w): acc[w] for w in widths},
-              note='wall clock of infer.leave_one_trial_out_test (per-trial Grams from one launch, batched '
-                   'fold Cholesky, held-out predictions, correlator, windows, decisions; data resident); the '
+              accuracy={str(w): acc[w] for w in widths}, fold_solver=solver,
+              note='wall clock of infer.leave_one_trial_out_test (per-trial Grams from one launch, all folds from one '
+                   'factorisation + fixed-point steps, held-out predictions, correlator, windows, decisions; data resident); the '
                    'reference runs one complete fit per held-out trial (regression.py:197-214)')
 
 

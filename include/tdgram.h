@@ -212,6 +212,22 @@ int td_ridge_solve_batched(const double* G_aug_dev, const double* C_aug_dev, int
                            const double* n, const double* lambdas, int n_batch, float* W_out_dev,
                            void* cuda_stream);
 
+/* td_ridge_loo_solve: every leave-one-trial-out fold from ONE factorisation.  Fold f solves
+ * (G_tot - G_f + lambda n_f I) w = C_tot - C_f; with S = G_tot + lambda n_ref I that is (S - E_f) w = c_f,
+ * E_f = G_f + lambda (n_ref - n_f) I small (one trial of F), and w <- S^-1 (c_f + E_f w) contracts by
+ * ~1/F per step.  Inputs: G_aug_total_dev [D+1][D+1], C_aug_total_dev [D+1][Dy] double (ones column
+ * last), the held-out trials' statistics gram_fold_dev [F][D][D] float32 (td_lagged_gram_batched_f32),
+ * xtv_fold_dev [F][D][Dy+1], vtv_fold_dev [F][Dy+1][Dy+1] double (td_lagged_thin_per_segment_f64),
+ * n_fold HOST [F] rows per trial, n_total.  W_out_dev [F][D+1][Dy] float32.  *iterations and
+ * *worst_rel (HOST, may be NULL) report the steps taken and the largest relative change of the last
+ * one; the status is TD_OK even when that is above tol -- the caller may then fall back to
+ * td_ridge_solve_batched.  Dy <= 4.  Synchronises the stream. */
+int td_ridge_loo_solve(const double* G_aug_total_dev, const double* C_aug_total_dev,
+                       const float* gram_fold_dev, const double* xtv_fold_dev,
+                       const double* vtv_fold_dev, const double* n_fold, int D, int Dy, int F,
+                       double n_total, double lambda, int max_iter, double tol, float* W_out_dev,
+                       int* iterations, double* worst_rel, void* cuda_stream);
+
 /* td_cca_solve: cca.py:337-367.  Inputs are raw sums (double): Gxx [D1,D1], Gyy [D2,D2],
  * Gxy [D1,D2], sum_x [D1], sum_y [D2]; n_frames = total rows, n_norm = n_batches*n_row - 1.
  * Outputs float32: rot_x [D1,dim], rot_y [D2,dim], mean_x [D1], mean_y [D2], e [dim].

@@ -678,6 +678,107 @@ int td_ridge_solve_scaled(Handles* h, Scratch& sc, cudaStream_t st, const double
   return TD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Leave-one-trial-out with ONE factorisation.
+//
+// Fold f solves (G_tot - G_f + lambda n_f I) w = C_tot - C_f  (brain_model.py:447-454 on the fold's
+// sums, n_f = n_tot - rows of trial f).  With S = G_tot + lambda n_ref I (n_ref = mean n_f) this is
+// (S - E_f) w = c_f, E_f = G_f + lambda (n_ref - n_f) I -- a small perturbation of ONE matrix shared
+// by every fold (a trial holds ~1/F of the energy), so after one Cholesky of S the fixed point
+//     w <- S^-1 (c_f + E_f w)
+// contracts by ~1/F per step: 3 - 5 steps to float64 accuracy, each one pass over the per-trial Grams
+// (a memory-bound matrix-vector kernel) and one triangular solve with F*Dy right-hand sides, instead
+// of F factorisations.  The caller falls back to the batched Cholesky when a fold does not converge
+// (one trial dominating the recording).
+// ---------------------------------------------------------------------------------------------
+// R[:, f*Dy + q] = C_tot[:, q] - C_f[:, q]   (column-major Da x F*Dy);  C_f = [xtv_f[:, :Dy]; vtv_f[Dy, :Dy]]
+__global__ void loo_build_rhs(const double* __restrict__ C_tot, const double* __restrict__ xtv, const double* __restrict__ vtv,
+                              int D, int Dy, int F, double* __restrict__ R) {
+  const int Da = D + 1, Q = Dy + 1;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Da * F * Dy) return;
+  const long long col = i / Da;
+  const int r = (int)(i - col * Da);
+  const int f = (int)(col / Dy), q = (int)(col - (long long)f * Dy);
+  const double cf = (r < D) ? xtv[((size_t)f * D + r) * Q + q] : vtv[(size_t)f * Q * Q + (size_t)Dy * Q + q];
+  R[i] = C_tot[(size_t)r * Dy + q] - cf;
+}
+
+// T[:, f*Dy + q] = R[:, f*Dy + q] + E_f W[:, f*Dy + q]: one warp per (row, fold); gram [F][D][D] float32
+// (symmetric), the ones column / row of the augmented Gram from xtv[:, :, Dy] and vtv[:, Dy, Dy].
+template <int DY>
+__global__ void __launch_bounds__(256) loo_apply(const float* __restrict__ gram, const double* __restrict__ xtv,
+                                                 const double* __restrict__ vtv, const double* __restrict__ shift,
+                                                 const double* __restrict__ W, const double* __restrict__ R,
+                                                 int D, int F, double* __restrict__ T) {
+  const int Da = D + 1, Q = DY + 1;
+  const int f = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= Da) return;
+  const double* w = W + (size_t)f * DY * Da;
+  double acc[DY];
+#pragma unroll
+  for (int q = 0; q < DY; ++q) acc[q] = 0.0;
+  if (row < D) {
+    const float* g = gram + ((size_t)f * D + row) * D;
+    for (int j = lane; j < D; j += 32) {
+      const double gv = (double)__ldg(g + j);
+#pragma unroll
+      for (int q = 0; q < DY; ++q) acc[q] += gv * w[(size_t)q * Da + j];
+    }
+  } else {
+    const double* sf = xtv + (size_t)f * D * Q + DY;               // ones column: xtv[f][j][Dy]
+    for (int j = lane; j < D; j += 32) {
+      const double gv = sf[(size_t)j * Q];
+#pragma unroll
+      for (int q = 0; q < DY; ++q) acc[q] += gv * w[(size_t)q * Da + j];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < DY; ++q)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+  if (lane == 0) {
+    const double last = (row < D) ? xtv[((size_t)f * D + row) * Q + DY] : vtv[(size_t)f * Q * Q + (size_t)DY * Q + DY];
+#pragma unroll
+    for (int q = 0; q < DY; ++q) {
+      const size_t o = ((size_t)f * DY + q) * Da + row;
+      T[o] = R[o] + acc[q] + last * w[(size_t)q * Da + D] + shift[f] * w[(size_t)q * Da + row];
+    }
+  }
+}
+
+// per fold: max |Wn - W| and max |Wn| over its Da x Dy block (column-major, contiguous)
+__global__ void loo_diff(const double* __restrict__ Wn, const double* __restrict__ W, long long per_fold, double* out) {
+  __shared__ double sd[256], sm[256];
+  const double* a = Wn + (size_t)blockIdx.x * per_fold;
+  const double* b = W + (size_t)blockIdx.x * per_fold;
+  double d = 0.0, m = 0.0;
+  for (long long i = threadIdx.x; i < per_fold; i += blockDim.x) {
+    d = fmax(d, fabs(a[i] - b[i]));
+    m = fmax(m, fabs(a[i]));
+  }
+  sd[threadIdx.x] = d; sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sd[threadIdx.x] = fmax(sd[threadIdx.x], sd[threadIdx.x + o]); sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + o]); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[2 * blockIdx.x] = sd[0]; out[2 * blockIdx.x + 1] = sm[0]; }
+}
+
+// column-major [Da, F*Dy] double -> W_out [F][Da][Dy] float
+__global__ void loo_store(const double* __restrict__ W, int Da, int Dy, int F, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)F * Da * Dy) return;
+  const int q = (int)(i % Dy);
+  const long long t = i / Dy;
+  const int r = (int)(t % Da);
+  const int f = (int)(t / Da);
+  out[i] = (float)W[((size_t)f * Dy + q) * Da + r];
+}
+
 }  // namespace
 }  // namespace td
 
@@ -744,6 +845,85 @@ extern "C" int td_ridge_solve(const double* G_aug, const double* C_aug, int Da, 
   rc = td_ridge_solve_scaled(h, sc, st, A0, B0, Da, Dy, lambdas, n_lambda, W_out);
   if (rc) return rc;
   TD_CHECK_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
+// Leave-one-trial-out through one shared factorisation (see loo_* above).  G_aug_total [Da][Da] and
+// C_aug_total [Da][Dy] double (Da = D + 1, ones column last), per-fold statistics of the held-out
+// trials: gram_fold [F][D][D] float32, xtv_fold [F][D][Dy+1], vtv_fold [F][Dy+1][Dy+1] double,
+// n_fold (HOST, rows of each held-out trial).  W_out [F][Da][Dy] float32.  worst_rel (HOST) receives
+// the largest relative change of the last iteration over the folds; status TD_OK even if it is above
+// tol -- the caller decides (fallback to td_ridge_solve_batched).  Synchronises the stream.
+extern "C" int td_ridge_loo_solve(const double* G_aug_total, const double* C_aug_total, const float* gram_fold,
+                                  const double* xtv_fold, const double* vtv_fold, const double* n_fold, int D,
+                                  int Dy, int F, double n_total, double lambda, int max_iter, double tol,
+                                  float* W_out, int* iterations, double* worst_rel, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_REQUIRE(G_aug_total && C_aug_total && gram_fold && xtv_fold && vtv_fold && n_fold && W_out,
+             "td_ridge_loo_solve: null argument");
+  TD_REQUIRE(D >= 1 && F >= 1 && Dy >= 1 && Dy <= 4, "td_ridge_loo_solve: D=%d F=%d Dy=%d (Dy must be 1..4)", D, F, Dy);
+  TD_REQUIRE(n_total > 0 && max_iter >= 1, "td_ridge_loo_solve: n_total=%g max_iter=%d", n_total, max_iter);
+  Handles* h;
+  int rc = get_handles(&h);
+  if (rc) return rc;
+  TD_CHECK_SOLVER(cusolverDnSetStream(h->solver, st));
+  Scratch sc(st);
+  const int Da = D + 1;
+  const long long nn = (long long)Da * Da, ncol = (long long)F * Dy, nb = (long long)Da * ncol;
+  double n_ref = 0.0;
+  std::vector<double> shift(F);
+  for (int f = 0; f < F; ++f) {
+    TD_REQUIRE(n_fold[f] > 0 && n_fold[f] < n_total, "td_ridge_loo_solve: trial %d has %g of %g rows", f, n_fold[f], n_total);
+    n_ref += (n_total - n_fold[f]) / F;
+  }
+  for (int f = 0; f < F; ++f) shift[f] = lambda * (n_ref - (n_total - n_fold[f]));     // E_f = G_f + shift_f I
+  double *S, *R, *W, *T, *work, *shift_dev, *diff_dev;
+  int* info;
+  int lwork = 0;
+  if ((rc = sc.get(nn, &S)) || (rc = sc.get(nb, &R)) || (rc = sc.get(nb, &W)) || (rc = sc.get(nb, &T)) ||
+      (rc = sc.get(F, &shift_dev)) || (rc = sc.get(2 * F, &diff_dev)) || (rc = sc.get(2, &info)))
+    return rc;
+  TD_CHECK_CUDA(cudaMemcpyAsync(shift_dev, shift.data(), F * sizeof(double), cudaMemcpyHostToDevice, st));
+  scale_add_diag<<<blocks_for(nn), 256, 0, st>>>(G_aug_total, S, Da, 1.0, lambda * n_ref);
+  TD_CHECK_SOLVER(cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, Da, S, Da, &lwork));
+  if ((rc = sc.get((size_t)lwork, &work))) return rc;
+  TD_CHECK_SOLVER(cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, Da, S, Da, work, lwork, info));
+  loo_build_rhs<<<blocks_for(nb), 256, 0, st>>>(C_aug_total, xtv_fold, vtv_fold, D, Dy, F, R);
+  TD_CHECK_CUDA(cudaMemcpyAsync(W, R, nb * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  TD_CHECK_SOLVER(cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, Da, (int)ncol, S, Da, W, Da, info + 1));
+  int hinfo[2] = {0, 0};
+  TD_CHECK_CUDA(cudaMemcpyAsync(hinfo, info, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TD_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (hinfo[0] != 0 || hinfo[1] != 0) {
+    set_error("td_ridge_loo_solve: the total system is not positive definite (potrf info %d)", hinfo[0]);
+    return TD_ERR_SOLVER;
+  }
+  std::vector<double> hd(2 * F);
+  double worst = 0.0;
+  int it = 0;
+  for (it = 1; it <= max_iter; ++it) {
+    dim3 grid((unsigned)((Da + 7) / 8), (unsigned)F);
+    switch (Dy) {
+      case 1: loo_apply<1><<<grid, 256, 0, st>>>(gram_fold, xtv_fold, vtv_fold, shift_dev, W, R, D, F, T); break;
+      case 2: loo_apply<2><<<grid, 256, 0, st>>>(gram_fold, xtv_fold, vtv_fold, shift_dev, W, R, D, F, T); break;
+      case 3: loo_apply<3><<<grid, 256, 0, st>>>(gram_fold, xtv_fold, vtv_fold, shift_dev, W, R, D, F, T); break;
+      default: loo_apply<4><<<grid, 256, 0, st>>>(gram_fold, xtv_fold, vtv_fold, shift_dev, W, R, D, F, T); break;
+    }
+    TD_CHECK_CUDA(cudaGetLastError());
+    TD_CHECK_SOLVER(cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, Da, (int)ncol, S, Da, T, Da, info + 1));
+    loo_diff<<<F, 256, 0, st>>>(T, W, (long long)Da * Dy, diff_dev);
+    TD_CHECK_CUDA(cudaMemcpyAsync(hd.data(), diff_dev, 2 * F * sizeof(double), cudaMemcpyDeviceToHost, st));
+    std::swap(W, T);
+    TD_CHECK_CUDA(cudaStreamSynchronize(st));
+    worst = 0.0;
+    for (int f = 0; f < F; ++f) worst = std::max(worst, hd[2 * f] / std::max(hd[2 * f + 1], 1e-300));
+    if (worst < tol) break;
+  }
+  loo_store<<<blocks_for((long long)F * Da * Dy), 256, 0, st>>>(W, Da, Dy, F, W_out);
+  TD_CHECK_CUDA(cudaGetLastError());
+  TD_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (iterations) *iterations = std::min(it, max_iter);
+  if (worst_rel) *worst_rel = worst;
   return TD_OK;
 }
 

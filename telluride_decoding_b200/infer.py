@@ -88,7 +88,9 @@ def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_l
     1. per-trial sufficient statistics from one launch of the tcgen05 Gram kernel (+ one of the
        thin-product kernel); fold f = total - trial f (- the rows drop_remainder removes from that
        fold's interleaved stream, brain_data.py:369-370);
-    2. all fold systems solved by the batched blocked Cholesky (groups of `fold_group` folds);
+    2. all fold systems from ONE Cholesky of the total system + a few fixed-point steps over the
+       per-trial Grams (a held-out trial is a small perturbation of the total); the batched blocked
+       Cholesky (groups of `fold_group` folds) when rows are dropped or a fold does not converge;
     3. every trial predicted by the model that never saw it (per-segment weights);
     4. correlator statistics (infer_decoder.py:288-310) pooled over both speakers' (truth,
        prediction) pairs of those held-out predictions; per-frame correlation signal, reduction,
@@ -135,11 +137,31 @@ def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_l
   all_rows = sum(file_rows)
   b = ds.final_batch_size
 
-  # ---- 2. fold systems, solved in groups ----------------------------------------------------------
+  # ---- 2. fold systems ------------------------------------------------------------------------------
   weights = torch.empty((n_files, d, dy), dtype=torch.float32, device=device)
   biases = torch.empty((n_files, dy), dtype=torch.float32, device=device)
   names = [f[0] for f in ds.files]
-  for g0 in range(0, n_files, fold_group):
+  solver = 'batched cholesky'
+  drops = [(all_rows - file_rows[f]) % b != 0 for f in range(n_files)]
+  done = False
+  if not any(drops) and dy <= 4 and isinstance(gram_f, torch.Tensor) and gram_f.dtype == torch.float32:
+    # ONE factorisation of the total system, then a few fixed-point steps over the per-trial Grams:
+    # (S - E_f) w = c_f with E_f (one trial of n_files) small against S (ops.ridge_loo_solve).
+    g_tot = torch.empty((d + 1, d + 1), dtype=torch.float64, device=device)
+    g_tot[:d, :d] = total_g
+    g_tot[:d, d] = total_t[:, dy]
+    g_tot[d, :d] = total_t[:, dy]
+    g_tot[d, d] = total_v[dy, dy]
+    c_tot = torch.cat([total_t[:, :dy], total_v[dy:dy + 1, :dy]], dim=0)
+    # lambda multiplies n_f * I in the un-normalised fold system (brain_model.py:447-452 divides by n_f)
+    sol, iters, worst = ops.ridge_loo_solve(g_tot, c_tot, gram_f, xtv_f, vtv_f, regularization_lambda)
+    if worst < 1e-8:
+      weights.copy_(sol[:, :d, :])
+      biases.copy_(sol[:, d, :])
+      solver = 'one factorisation + %d fixed-point steps' % iters
+      done = True
+    del g_tot, sol
+  for g0 in range(0, 0 if done else n_files, fold_group):
     g1 = min(n_files, g0 + fold_group)
     ng = g1 - g0
     g_aug = torch.empty((ng, d + 1, d + 1), dtype=torch.float64, device=device)
@@ -153,7 +175,7 @@ def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_l
     c_aug[:, d, :] = total_v[dy, :dy].unsqueeze(0) - vtv_f[g0:g1, dy, :dy]
     for j in range(ng):
       f = g0 + j
-      if (all_rows - file_rows[f]) % b:
+      if drops[f]:
         # this fold's interleaved training stream loses its last rows to drop_remainder
         brain_data_obj.set_file_patterns('allbut', '^%s$' % _re_escape(names[f]), '^%s$' % _re_escape(names[f]))
         try:
@@ -225,6 +247,7 @@ def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_l
     details['biases'] = biases
     details['prediction'] = pred
     details['correlator'] = dec.correlation_params
+    details['solver'] = solver
     return out, details
   return out
 

@@ -315,6 +315,34 @@ def ridge_solve_batched(g_aug, c_aug, n, lambdas):
   return out
 
 
+def ridge_loo_solve(g_aug_total, c_aug_total, gram_fold, xtv_fold, vtv_fold, lamb, max_iter=40, tol=1e-10):
+  """Every leave-one-trial-out fold from ONE Cholesky of the total system + a few fixed-point steps
+  over the per-trial Grams (td_ridge_loo_solve).  Returns (W float32 [F, D+1, Dy], iterations,
+  worst relative change of the last step); the caller falls back to ridge_solve_batched when that
+  is not below its tolerance."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  g_aug_total = g_aug_total.to(torch.float64).contiguous()
+  c_aug_total = c_aug_total.to(torch.float64).contiguous()
+  gram_fold = gram_fold.to(torch.float32).contiguous()
+  xtv_fold = xtv_fold.to(torch.float64).contiguous()
+  vtv_fold = vtv_fold.to(torch.float64).contiguous()
+  f, d = int(gram_fold.shape[0]), int(gram_fold.shape[1])
+  dy = int(c_aug_total.shape[1])
+  n_fold = [float(v) for v in vtv_fold[:, dy, dy].cpu().tolist()]
+  n_total = float(g_aug_total[d, d].item())
+  out = torch.empty((f, d + 1, dy), dtype=torch.float32, device=g_aug_total.device)
+  iters = ctypes.c_int(0)
+  worst = ctypes.c_double(0.0)
+  with torch.cuda.device(g_aug_total.device):
+    _lib.check(lib.td_ridge_loo_solve(_lib.ptr(g_aug_total), _lib.ptr(c_aug_total), _lib.ptr(gram_fold),
+                                      _lib.ptr(xtv_fold), _lib.ptr(vtv_fold), _lib.f64_array(n_fold), d, dy, f,
+                                      ctypes.c_double(n_total), ctypes.c_double(float(lamb)), int(max_iter),
+                                      ctypes.c_double(float(tol)), _lib.ptr(out), ctypes.byref(iters),
+                                      ctypes.byref(worst), _lib.current_stream_ptr()))
+  return out, int(iters.value), float(worst.value)
+
+
 def cca_solve(gxx, gyy, gxy, sum_x, sum_y, n_frames, n_norm, reg, eps_eig, dim):
   """(rot_x, rot_y, mean_x, mean_y, e) float32  (cca.py:337-367)."""
   _lib.require_cuda()

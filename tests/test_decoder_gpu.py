@@ -302,3 +302,5 @@ def test_leave_one_trial_out_aad_matches_the_reference_loop(lens, batch):
     np.testing.assert_array_equal(det[w_]['attention'], want[w_]['attention'])      # bit-identical decisions
     assert acc[w_] == want[w_]['accuracy']
   assert acc[200] > 0.8                                # the attended speaker is decodable
+  # equal trials and no dropped rows: one factorisation + fixed-point steps; otherwise the batched Cholesky
+  assert det['solver'].startswith('one factorisation') == (batch == 100), det['solver']
