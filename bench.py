@@ -515,10 +515,10 @@ def leg_cfg5(dev, n_trials=1000):
   bd.set_trials(['trial_%04d' % i for i in range(n_trials)], [frames] * n_trials, eeg, att,
                 input2_data=torch.cat([s1, s2], dim=1), attention_data=label)
   widths = [128, 256, 640, 1280, 2560, 3840]              # 1, 2, 5, 10, 20, 30 s windows, step W/2
-  def run():
+  def run(gram_options=None):
     return infer.leave_one_trial_out_test(bd, regularization_lambda=0.1, window_list=widths,
                                           reduction='first', decoder_type='wta', frame_rate=128.0,
-                                          return_details=True)
+                                          return_details=True, gram_options=gram_options)
   acc, det = run()                                         # warm-up (allocator, handles)
   n_windows = sum(len(det[w]['attention']) for w in widths)
   solver = det['solver']
@@ -529,12 +529,24 @@ def leg_cfg5(dev, n_trials=1000):
   torch.cuda.synchronize()
   wall = time.perf_counter() - t0
   del det
+  # the same with the per-trial Grams through their block-Toeplitz structure (method 5, opt-in)
+  from telluride_decoding_b200 import ops
+  acc5, det5 = run(ops.gram_options(method=5))
+  del det5
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  acc5, det5 = run(ops.gram_options(method=5))
+  torch.cuda.synchronize()
+  wall5 = time.perf_counter() - t0
+  del det5
   return dict(workload='cfg5: %d trials x 7680 frames (60 s @128 Hz), 64 ch x 32 lags, leave-one-trial-out '
                        'ridge (lambda 0.1, %d folds of a 2049 x 2049 system), 2 speakers, windows '
                        '1/2/5/10/20/30 s (step W/2), reduction first, winner-take-all' % (n_trials, n_trials),
               loo_wall_s=wall, frames_per_s=n / wall, folds_per_s=n_trials / wall,
               windows_per_s=2 * n_windows / wall, decisions=n_windows,
               accuracy={str(w): acc[w] for w in widths}, fold_solver=solver,
+              structured=dict(loo_wall_s=wall5, accuracy={str(w): acc5[w] for w in widths},
+                              what='per-trial Grams through the block-Toeplitz structure (gram_options(method=5))'),
               note='wall clock of infer.leave_one_trial_out_test (per-trial Grams from one launch, all folds from one '
                    'factorisation + fixed-point steps, held-out predictions, correlator, windows, decisions; data resident); the '
                    'reference runs one complete fit per held-out trial (regression.py:197-214)')

@@ -105,6 +105,10 @@ typedef struct td_gram_options {
 int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_streams,
                                    const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
                                    const td_gram_options* opt, size_t* bytes);
+/* The same for td_lagged_gram_batched_f32 (method 5 keeps one block row per segment in the workspace). */
+int td_lagged_gram_batched_workspace_bytes(const td_stream* streams, int n_streams,
+                                           const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
+                                           const td_gram_options* opt, size_t* bytes);
 /* Design rows [seg_first[s], seg_keep[s]) of every segment are accumulated (seg_first NULL = 0):
  * a prefix for drop_remainder, a sub-range when a trial's frames are shared between GPUs (the
  * lag halo is read from the neighbouring frames of the same segment, not zero padded). */

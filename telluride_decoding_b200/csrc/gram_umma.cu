@@ -446,10 +446,12 @@ __global__ void stage_kernel(StreamView s, const int64_t* __restrict__ seg_off, 
   }
 }
 
-__global__ void symmetrize_kernel(float* __restrict__ G, int64_t n, int64_t ldg, int from_upper) {
+__global__ void symmetrize_kernel(float* __restrict__ G, int64_t n, int64_t ldg, int from_upper,
+                                  int64_t batch_stride) {
   __shared__ float tile[32][33];
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bj < bi) return;                        // handle block pairs (bi <= bj) once
+  G += (int64_t)blockIdx.z * batch_stride;
   // Source block: the computed triangle's (bi, bj) if from_upper, else (bj, bi).
   const int sr = from_upper ? bi : bj, sc = from_upper ? bj : bi;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -980,14 +982,23 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
 // ---------------------------------------------------------------------------------------------
 struct SegEdge { long long start, len, first, keep; };
 
-// grid: (ceil(C / 32), C, L): thread = (c2, c1, d).  Ct[(d*C + c2)][c1] holds C(d)[c1, c2].
+// grid: (n_batch * ceil(C / 32), C, L): thread = (c2, c1, d).  Ct[(d*C + c2)][c1] holds C(d)[c1, c2].
+// Batched (one Gram per segment): batch b reads Ct + b*ct_stride, segment b only, writes G + b*g_stride.
 __global__ void __launch_bounds__(32) toeplitz_expand_kernel(const float* __restrict__ Ct, long long ldc,
                                                              const float* __restrict__ x, long long ld, int C, int L,
                                                              int pre, const SegEdge* __restrict__ segs, int n_seg,
-                                                             float* __restrict__ G, long long ldg) {
-  const int c2 = blockIdx.x * 32 + threadIdx.x;
+                                                             float* __restrict__ G, long long ldg, int cblocks,
+                                                             long long ct_stride, long long g_stride) {
+  const int batch = blockIdx.x / cblocks;
+  const int c2 = (blockIdx.x - batch * cblocks) * 32 + threadIdx.x;
   const int c1 = blockIdx.y;
   const int d = blockIdx.z;
+  if (g_stride) {                              // one segment per output
+    Ct += (long long)batch * ct_stride;
+    G += (long long)batch * g_stride;
+    segs += batch;
+    n_seg = 1;
+  }
   // Upper triangle only (i <= j in the design's lag-major column order; td_symmetrize_f32 mirrors it):
   // on the block diagonal (d = 0) that is c1 <= c2, so every entry has exactly one writer.
   if (c2 >= C || (d == 0 && c2 < c1)) return;
@@ -1013,7 +1024,7 @@ __global__ void __launch_bounds__(32) toeplitz_expand_kernel(const float* __rest
 
 int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_first, const int64_t* seg_keep,
                  int n_seg, float* G, int64_t ldg, const td_gram_options* opt, void* workspace,
-                 size_t workspace_bytes, cudaStream_t st, size_t* bytes_only);
+                 size_t workspace_bytes, cudaStream_t st, size_t* bytes_only, bool batched = false);
 
 // Does this call run the halo kernel (method 4)?  Explicitly, or automatically (method 0) when the
 // design is wide enough for CTA pairs (>= 512 tile rows) and DEFAULT_PAIR_METHOD says so.
@@ -1043,7 +1054,7 @@ int use_halo(const td_stream* streams, int n_streams, const td_gram_options* opt
 // [segment edges] [Ct: Dz x ldc floats].  bytes_only != nullptr: just report the size.
 int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_first, const int64_t* seg_keep,
                  int n_seg, float* G, int64_t ldg, const td_gram_options* opt, void* workspace,
-                 size_t workspace_bytes, cudaStream_t st, size_t* bytes_only) {
+                 size_t workspace_bytes, cudaStream_t st, size_t* bytes_only, bool batched) {
   if (n_streams != 1) {
     set_error("td_lagged_gram: method 5 (block-Toeplitz structure) handles one stream");
     return TD_ERR_UNSUPPORTED;
@@ -1060,8 +1071,22 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
   const size_t off_rga = off;   off += (size_t)round_up((int64_t)n_rga_pad * (int64_t)sizeof(int4), 1024);
   const size_t off_oia = off;   off += (size_t)round_up((int64_t)n_rga_pad * hk::RG_ROWS * (int64_t)sizeof(int), 1024);
   const size_t off_seg = off;   off += (size_t)round_up((int64_t)n_seg * (int64_t)sizeof(SegEdge), 1024);
-  const size_t off_ct = off;    off += (size_t)round_up(pl.Dz * ldc * (int64_t)sizeof(float), 1024);
+  const int64_t n_out = batched ? n_seg : 1;
+  const size_t off_ct = off;    off += (size_t)round_up(n_out * pl.Dz * ldc * (int64_t)sizeof(float), 1024);
   if (bytes_only) { *bytes_only = off; return TD_OK; }
+  int64_t kt_per_seg = 0;
+  if (batched) {
+    for (int s = 0; s < n_seg; ++s) {
+      const int64_t f = first_of(seg_first, s);
+      const int64_t k = seg_keep[s] > f ? ceil_div(seg_keep[s], BK) - f / BK : 0;
+      if (s == 0) kt_per_seg = k;
+      if (k != kt_per_seg || k == 0) {
+        set_error("td_lagged_gram_batched_f32: segment %d spans %lld k-tiles, segment 0 spans %lld (one launch needs equal, non-empty segments)",
+                  s, (long long)k, (long long)kt_per_seg);
+        return TD_ERR_UNSUPPORTED;
+      }
+    }
+  }
   TD_REQUIRE(ldg >= pl.Dz, "td_lagged_gram_f32: ldg (%lld) < Dz (%lld)", (long long)ldg, (long long)pl.Dz);
   if (workspace_bytes < off || !workspace) {
     set_error("td_lagged_gram_f32: workspace has %zu bytes, %zu needed", workspace_bytes, off);
@@ -1152,7 +1177,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
   rc = make_tmap_raw(&tmap_a, base, pl.n_rows[0], C, pl.ld_eff[0], hk::ABOX_CH, hk::ABOX_FRAMES);
   if (rc) return rc;
   float* Ct = reinterpret_cast<float*>(ws + off_ct);
-  TD_CHECK_CUDA(cudaMemsetAsync(Ct, 0, (size_t)pl.Dz * ldc * sizeof(float), st));
+  TD_CHECK_CUDA(cudaMemsetAsync(Ct, 0, (size_t)n_out * pl.Dz * ldc * sizeof(float), st));
   if (pl.NK > 0) {
     hk::HaloParams P;
     P.rgs = reinterpret_cast<const int4*>(ws + pl.off_rgs);
@@ -1163,7 +1188,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     P.out_idx_a = reinterpret_cast<const int*>(ws + off_oia);
     P.G = Ct;
     P.ldg = ldc;
-    P.batch_stride = 0;
+    P.batch_stride = batched ? pl.Dz * ldc : 0;
     P.ntri = ta * pl.nt;
     P.NK = pl.NK;
     const int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 128;
@@ -1175,6 +1200,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     int64_t nsc = ceil_div(pl.NK, ks);
     ks = round_up(ceil_div(pl.NK, nsc), P.chunk_kt);
     nsc = ceil_div(pl.NK, ks);
+    if (batched) { ks = kt_per_seg; nsc = n_seg; }
     P.KS = (int)ks;
     P.total_steps = nsc * P.ntri * ks;
     int workers = sms / 2;
@@ -1210,11 +1236,22 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     }
     if ((rc = debug_sync(st, "toeplitz block-row kernel"))) return rc;
   }
-  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)C, (unsigned)L);
-  toeplitz_expand_kernel<<<grid, 32, 0, st>>>(Ct, ldc, streams[0].data_dev, streams[0].ld, C, L, pre,
-                                              reinterpret_cast<const SegEdge*>(ws + off_seg), n_seg, G, ldg);
-  TD_CHECK_CUDA(cudaGetLastError());
-  return td_symmetrize_f32(G, pl.Dz, ldg, /*from_upper=*/1, st);
+  const int cblocks = (int)ceil_div(C, 32);
+  const int nb = (int)ceil_div(pl.Dz, 32);
+  // (batched: chunks of segments keep gridDim.x and gridDim.z inside their limits)
+  for (int64_t o0 = 0; o0 < n_out; o0 += 16384) {
+    const int64_t nz = std::min<int64_t>(16384, n_out - o0);
+    dim3 grid((unsigned)(cblocks * nz), (unsigned)C, (unsigned)L);
+    toeplitz_expand_kernel<<<grid, 32, 0, st>>>(Ct + o0 * pl.Dz * ldc, ldc, streams[0].data_dev, streams[0].ld, C, L, pre,
+                                                reinterpret_cast<const SegEdge*>(ws + off_seg) + (batched ? o0 : 0), n_seg,
+                                                G + (batched ? o0 * pl.Dz * ldg : 0), ldg, cblocks,
+                                                batched ? pl.Dz * ldc : 0, batched ? pl.Dz * ldg : 0);
+    TD_CHECK_CUDA(cudaGetLastError());
+    symmetrize_kernel<<<dim3(nb, nb, (unsigned)nz), dim3(32, 8), 0, st>>>(G + (batched ? o0 * pl.Dz * ldg : 0), pl.Dz, ldg, 1,
+                                                                          batched ? pl.Dz * ldg : 0);
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
+  return TD_OK;
 }
 
 }  // namespace
@@ -1267,7 +1304,7 @@ extern "C" int td_symmetrize_f32(float* G, int64_t n, int64_t ldg, int from_uppe
   TD_REQUIRE(G && n >= 0 && ldg >= n, "td_symmetrize_f32: bad arguments");
   if (n == 0) return TD_OK;
   const int nb = (int)ceil_div(n, 32);
-  symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, (cudaStream_t)stream>>>(G, n, ldg, from_upper);
+  symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, (cudaStream_t)stream>>>(G, n, ldg, from_upper, 0);
   TD_CHECK_CUDA(cudaGetLastError());
   return TD_OK;
 }
@@ -1519,9 +1556,26 @@ extern "C" int td_lagged_gram_batched_f32(const td_stream* streams, int n_stream
                                           void* stream) {
   TD_REQUIRE(streams && seg_keep && G, "td_lagged_gram_batched_f32: null argument");
   td_gram_options o = opt ? *opt : td_gram_options{};
-  TD_REQUIRE(o.method == 0 || o.method == 4, "td_lagged_gram_batched_f32: only method 4 (0 = default) writes per-segment Grams");
+  TD_REQUIRE(o.method == 0 || o.method == 4 || o.method == 5,
+             "td_lagged_gram_batched_f32: methods 4 (0 = default) and 5 write per-segment Grams");
+  if (o.method == 5)
+    return run_toeplitz(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, &o, workspace, workspace_bytes,
+                        (cudaStream_t)stream, nullptr, /*batched=*/true);
   o.method = 4;
   o.cta_group = 2;
   return run_halo(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, &o, workspace, workspace_bytes,
                   (cudaStream_t)stream, /*batched=*/true);
+}
+
+extern "C" int td_lagged_gram_batched_workspace_bytes(const td_stream* streams, int n_streams,
+                                                      const int64_t* seg_first, const int64_t* seg_keep,
+                                                      int n_seg, const td_gram_options* opt, size_t* bytes) {
+  TD_REQUIRE(streams && seg_keep && bytes, "td_lagged_gram_batched_workspace_bytes: null argument");
+  if (opt && opt->method == 5)
+    return run_toeplitz(streams, n_streams, seg_first, seg_keep, n_seg, nullptr, 0, opt, nullptr, 0, nullptr, bytes,
+                        /*batched=*/true);
+  td_gram_options o = opt ? *opt : td_gram_options{};
+  o.method = 4;
+  o.cta_group = 2;
+  return td_lagged_gram_workspace_bytes(streams, n_streams, seg_first, seg_keep, n_seg, &o, bytes);
 }

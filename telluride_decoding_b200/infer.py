@@ -73,7 +73,7 @@ def run_reduction_test(model_object, bd1_test, bd2_test, decoder_type='wta',
 
 def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_list=None,
                              reduction='first', decoder_type='wta', frame_rate=100.0,
-                             fold_group=64, return_details=False):
+                             fold_group=64, return_details=False, gram_options=None):
   """Two-speaker attention decoding with a leave-one-trial-out linear decoder
   (BASELINE.json configs[4]): {window size: fraction of correctly decoded windows}.
 
@@ -96,6 +96,7 @@ def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_l
        prediction) pairs of those held-out predictions; per-frame correlation signal, reduction,
        windows of every size inside each trial (result_store.py:262-271, step W // 2), decision
        (attention_decoder.py:128-173) and accuracy (infer.py:399-407).
+  gram_options: ops.gram_options(...) for step 1 (method=5: the block-Toeplitz structure per trial).
   """
   window_list = [int(w) for w in (window_list or DEFAULT_WINDOW_LIST)]
   saved = (brain_data_obj.train_file_pattern, brain_data_obj.validate_file_pattern,
@@ -120,7 +121,7 @@ def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_l
   device = x.data.device
 
   # ---- 1. per-trial statistics from one pass ----------------------------------------------------
-  gram_s = ops.lagged_gram_per_segment([x], rows)                    # [n_seg, D, D] float32
+  gram_s = ops.lagged_gram_per_segment([x], rows, options=gram_options)   # [n_seg, D, D] float32
   xtv_s, vtv_s = ops.lagged_thin_per_segment(x, y, rows)             # float64
   if n_files != len(rows):                                           # several chunks per file: add them up
     idx = torch.as_tensor(seg_file, device=device)

@@ -119,11 +119,13 @@ def lagged_gram_per_segment(streams, seg_keep, options=None, workspace=None, seg
   carr = _streams_array(streams)
   keep = _lib.i64_array(seg_keep)
   first = _lib.i64_array(seg_first) if seg_first is not None else None
-  opt4 = _lib.TdGramOptions(4, 2, options.chunk_rows, 0, options.max_ctas)
+  # method 5 (block-Toeplitz structure, one stream) if asked for, else the dense kernel (method 4)
+  method = 5 if (options.method == 5 and len(streams) == 1) else 4
+  opt4 = _lib.TdGramOptions(method, 2, options.chunk_rows, 0, options.max_ctas)
   opt4.reserved[0] = options.reserved[0]
   nbytes = ctypes.c_size_t(0)
-  _lib.check(lib.td_lagged_gram_workspace_bytes(carr, len(streams), first, keep, n_seg,
-                                                ctypes.byref(opt4), ctypes.byref(nbytes)))
+  _lib.check(lib.td_lagged_gram_batched_workspace_bytes(carr, len(streams), first, keep, n_seg,
+                                                        ctypes.byref(opt4), ctypes.byref(nbytes)))
   ws = (workspace or _default_workspace_for(device)).get(nbytes.value, device)
   with torch.cuda.device(device):
     _lib.check(lib.td_lagged_gram_batched_f32(carr, len(streams), first, keep, n_seg, _lib.ptr(out),

@@ -321,3 +321,22 @@ def test_block_toeplitz_gram_on_config2_and_sharded_rows():
   assert gpu_util.rel_fro(total.cpu().numpy(), dense.cpu().numpy()) < 5e-6
   with pytest.raises(Exception, match='one stream'):
     ops.lagged_gram([s, s], keep, options=ops.gram_options(method=5))
+
+
+def test_per_segment_grams_dense_and_block_toeplitz():
+  """One Gram per trial from one launch (leave-one-trial-out statistics): dense kernel and method 5
+  against per-trial calls of the dense kernel."""
+  gen = torch.Generator(device='cuda')
+  gen.manual_seed(3)
+  n_trials, n, c, lags = 7, 2048, 24, 12
+  xd = torch.randn((n_trials * n, c), generator=gen, device='cuda')
+  starts = [i * n for i in range(n_trials)]
+  lens = [n] * n_trials
+  s = ops.Stream(xd, 2, lags - 3, starts, lens)
+  want = torch.stack([ops.lagged_gram([ops.Stream(xd, 2, lags - 3, [starts[i]], [n])], [n]) for i in range(n_trials)])
+  for method in (0, 5):
+    got = ops.lagged_gram_per_segment([s], lens, options=ops.gram_options(method=method))
+    assert got.shape == (n_trials, c * lags, c * lags)
+    for i in range(n_trials):
+      assert gpu_util.rel_fro(got[i].cpu().numpy(), want[i].cpu().numpy()) < 5e-6, (method, i)
+      assert torch.equal(got[i], got[i].t())
