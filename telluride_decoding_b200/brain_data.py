@@ -240,13 +240,14 @@ class LaggedDataset(object):
     return out
 
   def stream_permutation(self, kept_total=None):
-    """int64 CUDA index: position in file-major row order of each stream element (one epoch)."""
-    fi, ri = interleave_order(self.file_rows)
-    file_base = np.concatenate(([0], np.cumsum(self.file_rows)[:-1])).astype(np.int64)
-    idx = file_base[fi] + ri
-    if kept_total is not None:
-      idx = idx[:kept_total]
-    return torch.from_numpy(idx).to(self.x.device)
+    """int64 CUDA index: position in file-major row order of each stream element (one epoch).
+    Built once per dataset (evaluate / predict ask for it on every call)."""
+    full = getattr(self, '_stream_perm', None)
+    if full is None:
+      fi, ri = interleave_order(self.file_rows)
+      file_base = np.concatenate(([0], np.cumsum(self.file_rows)[:-1])).astype(np.int64)
+      full = self._stream_perm = torch.from_numpy(file_base[fi] + ri).to(self.x.device)
+    return full if kept_total is None else full[:kept_total]
 
   def unlagged_rows(self, which):
     """Rows of an un-lagged stream ('y', 'a', or 'x2' when it has no context) in file-major order,

@@ -258,8 +258,10 @@ __global__ void thin_reduce_kernel(const double* __restrict__ slices, double* __
 
 // ---------------------------------------------------------------------------------------------
 constexpr int PR_ROWS = 4;     // rows per warp
-constexpr int PR_QC = 8;       // output columns per pass
 
+// PR_QC = output columns per pass (1, 2, 4 or 8: the smallest that covers Dy, so that a single-target
+// decoder does not multiply seven columns of zeros)
+template <int PR_QC>
 __global__ void __launch_bounds__(256) predict_kernel(StreamView x, const int64_t* seg_keep,
                                                       const int64_t* out_row, const int* blk_seg,
                                                       const int64_t* blk_t0, int rows_per_block,
@@ -627,7 +629,14 @@ int predict_impl(const td_stream* x, const int64_t* seg_keep, const int64_t* out
   rc = make_blocks(seg_keep, n_seg, rows_per_block, tabs, &blk_seg, &blk_t0, &nblk);
   if (rc) return rc;
   if (nblk > 0) {
-    predict_kernel<<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, W, bias, mean, Dy, out, ldo, w_seg_stride, b_seg_stride);
+    if (Dy == 1)
+      predict_kernel<1><<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, W, bias, mean, Dy, out, ldo, w_seg_stride, b_seg_stride);
+    else if (Dy == 2)
+      predict_kernel<2><<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, W, bias, mean, Dy, out, ldo, w_seg_stride, b_seg_stride);
+    else if (Dy <= 4)
+      predict_kernel<4><<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, W, bias, mean, Dy, out, ldo, w_seg_stride, b_seg_stride);
+    else
+      predict_kernel<8><<<(unsigned)nblk, 256, 0, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, rows_per_block, W, bias, mean, Dy, out, ldo, w_seg_stride, b_seg_stride);
     TD_CHECK_CUDA(cudaGetLastError());
   }
   return TD_OK;
