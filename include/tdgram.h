@@ -123,6 +123,10 @@ int td_lagged_gram_batched_f32(const td_stream* streams, int n_streams,
                                const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
                                float* G_dev, int64_t ldg, const td_gram_options* opt,
                                void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
+/* out_dev[i] (double) = sum over b < batches of in_dev[b * stride + i]: the total Gram from the
+ * per-segment Grams. */
+int td_sum_batches_f32(const float* in_dev, int64_t n, int64_t stride, int batches, double* out_dev,
+                       void* cuda_stream);
 /* Device time (ms) of the most recent tcgen05 Gram kernel launched by this thread with
  * opt->reserved[0] = 1 (CUDA events on the caller's stream; synchronises on the stop event).
  * Negative if none was recorded.  For the bench's roofline line. */

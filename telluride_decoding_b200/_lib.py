@@ -47,7 +47,7 @@ EXPORTS = (
     'td_comm_destroy', 'td_comm_nccl_version', 'td_allreduce_sum_f32', 'td_allreduce_sum_f64',
     'td_allreduce_sym_f32', 'td_pack_upper_f32', 'td_unpack_upper_f32', 'td_lagged_gram_batched_f32',
     'td_lagged_thin_per_segment_f64', 'td_lagged_predict_per_segment_f32', 'td_ridge_solve_batched',
-    'td_lagged_column_sums_f64', 'td_lagged_lw_stat_f64', 'td_ridge_loo_solve', 'td_lagged_gram_batched_workspace_bytes')
+    'td_lagged_column_sums_f64', 'td_lagged_lw_stat_f64', 'td_ridge_loo_solve', 'td_lagged_gram_batched_workspace_bytes', 'td_sum_batches_f32')
 
 _lib = None
 

@@ -698,3 +698,30 @@ extern "C" int td_lagged_lw_stat_f64(const td_stream* x, const int64_t* seg_firs
   }
   return TD_OK;
 }
+
+// out[i] = sum_b in[b * stride + i] in float64 (the total Gram from the per-trial Grams: one coalesced
+// pass over the batch instead of a strided library reduction).
+namespace td { namespace {
+__global__ void sum_batches_kernel(const float* __restrict__ in, long long n, long long stride, int batches,
+                                   double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s0 = 0.0, s1 = 0.0;
+  int b = 0;
+  for (; b + 1 < batches; b += 2) {
+    s0 += (double)__ldg(in + (long long)b * stride + i);
+    s1 += (double)__ldg(in + (long long)(b + 1) * stride + i);
+  }
+  if (b < batches) s0 += (double)__ldg(in + (long long)b * stride + i);
+  out[i] = s0 + s1;
+}
+} }
+
+extern "C" int td_sum_batches_f32(const float* in_dev, int64_t n, int64_t stride, int batches, double* out_dev,
+                                  void* stream) {
+  TD_REQUIRE(in_dev && out_dev && n >= 0 && batches >= 1 && stride >= n, "td_sum_batches_f32: bad arguments");
+  if (n == 0) return TD_OK;
+  td::sum_batches_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(in_dev, n, stride, batches, out_dev);
+  TD_CHECK_CUDA(cudaGetLastError());
+  return TD_OK;
+}

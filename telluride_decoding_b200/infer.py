@@ -132,7 +132,7 @@ def leave_one_trial_out_test(brain_data_obj, regularization_lambda=0.1, window_l
   else:
     gram_f, xtv_f, vtv_f = gram_s, xtv_s, vtv_s
   del gram_s
-  total_g = gram_f.sum(dim=0, dtype=torch.float64)
+  total_g = ops.sum_batches(gram_f)
   total_t, total_v = xtv_f.sum(dim=0), vtv_f.sum(dim=0)
   file_rows = list(ds.file_rows)
   all_rows = sum(file_rows)

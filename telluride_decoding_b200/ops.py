@@ -134,6 +134,22 @@ def lagged_gram_per_segment(streams, seg_keep, options=None, workspace=None, seg
   return out
 
 
+def sum_batches(t):
+  """float64 sum over the first axis of a contiguous float32 CUDA tensor [batches, ...] in one
+  coalesced pass (the total Gram from the per-trial Grams)."""
+  _lib.require_cuda()
+  lib = _lib.load()
+  t = t.contiguous()
+  if t.dtype != torch.float32:
+    return t.sum(dim=0, dtype=torch.float64)
+  n = int(t[0].numel())
+  out = torch.empty(t.shape[1:], dtype=torch.float64, device=t.device)
+  with torch.cuda.device(t.device):
+    _lib.check(lib.td_sum_batches_f32(_lib.ptr(t), ctypes.c_int64(n), ctypes.c_int64(n), int(t.shape[0]),
+                                      _lib.ptr(out), _lib.current_stream_ptr()))
+  return out
+
+
 def lagged_gram_range(streams, seg_first, seg_keep, out=None):
   """Gram over design rows [seg_first, seg_keep) of each segment (CUDA cores; small corrections)."""
   _lib.require_cuda()
