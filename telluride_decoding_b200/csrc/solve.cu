@@ -525,11 +525,11 @@ int batched_cholesky_sweep(Handles* h, Scratch& sc, cudaStream_t st, const doubl
       chol_build<<<dim3(blocks_for(Nt * Da), nbat), 256, 0, st>>>(A0, B0, Da, Dy, lam_dev, l0, M);
     if (dbg) cudaEventRecord(ev[1], st);
     // Four 64-column panels form a 256-column block (measured 2 / 4 / 8 panels: 4.67 / 4.43 / 4.74 ms for the
-    // factorisation of 20 systems of n = 2049).  The serial chain -- potf2, panel solve, the
-    // rank-64 update of the block's second panel, potf2, panel solve, then the rank-128 update of
-    // the NEXT block's columns -- runs on the caller's stream; the wide rank-128 trailing update of
-    // block b (everything right of the next block) runs on a side stream and overlaps the chain of
-    // block b + 1 (look-ahead).  Rank-128 updates halve the passes over the trailing matrix.
+    // factorisation of 20 systems of n = 2049).  The serial chain -- per panel
+    // potf2, panel solve and the rank-64 update of the block's remaining columns, then the rank-256
+    // update of the NEXT block's columns -- runs on the caller's stream; the wide rank-256 trailing
+    // update of block b (everything right of the next block) runs on a side stream and overlaps the
+    // chain of block b + 1 (look-ahead).
     cudaStream_t side = h->lane_stream[0];
     auto panel_factor = [&](int j0, int jb) -> int {
       chol_potf2<<<nbat, 256, potf2_smem, st>>>(M, L, Nt, j0, jb, info + l0, Linv, linv_stride);
