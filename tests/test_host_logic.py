@@ -330,3 +330,34 @@ def test_state_space_decoder_like_the_reference_tests():
                     attention_decoder.StateSpaceAttentionDecoder)
   with pytest.raises(ValueError, match='Unknown type'):
     attention_decoder.create_attention_decoder('bad type name')
+
+
+def test_batch_pieces_are_the_minibatches_of_the_interleaved_stream():
+  """LaggedDataset.batch_pieces (the row plan of the Ledoit-Wolf kernels): minibatch b of the
+  interleaved stream is a contiguous row range of every file, as ora.batches_from_files lays it out
+  (brain_data.py:725-728, :369-370)."""
+  lens = [530, 210, 377]
+  c = 2
+  rng = np.random.RandomState(1)
+  xs = [rng.randn(n, c).astype(np.float32) for n in lens]
+  files, cur = [], 0
+  for i, n in enumerate(lens):
+    files.append(('f%d' % i, cur, n))
+    cur += n
+  x = torch.from_numpy(np.concatenate(xs))
+  z = torch.zeros((cur, 1))
+  batch = 100
+  ds = brain_data.LaggedDataset(x, z, z, z, files, 0, 0, 0, 0, 0, 1000000, batch, 1, 0, 'test',
+                                temporal_context=False)
+  pieces = ds.batch_pieces()
+  # the oracle's stream: tag every row with (file, row) and batch the interleaved stream
+  tagged = [(np.stack([np.full(n, i), np.arange(n)], axis=1).astype(np.float32),) * 4 for i, n in enumerate(lens)]
+  batches = ora.batches_from_files(tagged, batch)
+  assert len(batches) == ds.num_batches == sum(lens) // batch
+  for b, (xd, _) in enumerate(batches):
+    tags = np.asarray(xd['input_1']).astype(int)
+    mine = [(s, lo, hi) for s, lo, hi, bb in pieces if bb == b]
+    assert sum(hi - lo for _, lo, hi in mine) == batch
+    for s, lo, hi in mine:
+      rows = np.sort(tags[tags[:, 0] == s][:, 1])
+      np.testing.assert_array_equal(rows, np.arange(lo, hi))
