@@ -316,6 +316,121 @@ __global__ void __launch_bounds__(256) predict_kernel(StreamView x, const int64_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tiled forward: a block takes PT_ROWS consecutive design rows of one segment.  Per 32-channel block it
+// stages the raw frames the rows need (rows + lag halo, zero outside the trial) and the weights of
+// those channels in shared memory; thread r then owns rows r, r+128, r+256, r+384: every weight is
+// read once for four rows, every x from shared memory (row stride 33 words: conflict free), so the
+// kernel is bound by the one pass over the raw frames instead of L1 traffic per (row, column).
+// (x - mean) W = x W - mean W: the constant is computed once per block.
+constexpr int PT_THREADS = 128;
+constexpr int PT_RPT = 4;                       // rows per thread
+constexpr int PT_ROWS = PT_THREADS * PT_RPT;    // 512
+constexpr int PT_CB = 32;                       // channels per pass
+
+template <int QC>
+__global__ void __launch_bounds__(PT_THREADS) predict_tiled_kernel(StreamView x, const int64_t* seg_keep,
+                                                                   const int64_t* out_row, const int* blk_seg,
+                                                                   const int64_t* blk_t0,
+                                                                   const float* __restrict__ W,
+                                                                   const float* __restrict__ bias,
+                                                                   const float* __restrict__ mean, int Dy,
+                                                                   float* out, int64_t ldo, int64_t w_seg_stride,
+                                                                   int64_t b_seg_stride) {
+  extern __shared__ float pt_sm[];
+  const int seg = blk_seg[blockIdx.x];
+  const int64_t t0 = blk_t0[blockIdx.x];
+  const int64_t keep = seg_keep[seg];
+  const int64_t len = x.seg_len[seg];
+  const int L = x.lags, C = x.channels;
+  const int rows = (int)min((int64_t)PT_ROWS, keep - t0);
+  const int nf = rows + L - 1;                                  // raw frames t0 - pre .. t0 - pre + nf
+  float* xs = pt_sm;                                            // [PT_ROWS + L - 1][33]
+  float* ws = pt_sm + (size_t)(PT_ROWS + L - 1) * (PT_CB + 1);  // [L][PT_CB][QC]
+  __shared__ float s_off[QC];
+  __shared__ float s_red[PT_THREADS / 32][QC];
+  const float* base = x.data + x.seg_start[seg] * x.ld;
+  W += (int64_t)seg * w_seg_stride;
+  if (bias) bias += (int64_t)seg * b_seg_stride;
+  const int64_t Dx = (int64_t)C * L;
+  const int r = threadIdx.x;
+  for (int q0 = 0; q0 < Dy; q0 += QC) {
+    // constant -mean W of these output columns
+    if (mean) {
+      float part[QC];
+#pragma unroll
+      for (int q = 0; q < QC; ++q) part[q] = 0.0f;
+      for (int64_t j = r; j < Dx; j += PT_THREADS) {
+        const float mu = __ldg(mean + j);
+#pragma unroll
+        for (int q = 0; q < QC; ++q)
+          if (q0 + q < Dy) part[q] = fmaf(mu, __ldg(W + j * Dy + q0 + q), part[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < QC; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part[q] += __shfl_xor_sync(0xffffffffu, part[q], o);
+        if ((r & 31) == 0) s_red[r >> 5][q] = part[q];
+      }
+      __syncthreads();
+      if (r < QC) {
+        float t = 0.0f;
+        for (int w = 0; w < PT_THREADS / 32; ++w) t += s_red[w][r];
+        s_off[r] = t;
+      }
+      __syncthreads();
+    }
+    float acc[PT_RPT][QC];
+#pragma unroll
+    for (int j = 0; j < PT_RPT; ++j)
+#pragma unroll
+      for (int q = 0; q < QC; ++q) acc[j][q] = 0.0f;
+    for (int c0 = 0; c0 < C; c0 += PT_CB) {
+      for (int e = r; e < nf * PT_CB; e += PT_THREADS) {
+        const int f = e / PT_CB, cc = e % PT_CB;
+        const int64_t u = t0 - x.pre + f;
+        xs[f * (PT_CB + 1) + cc] = (u >= 0 && u < len && c0 + cc < C) ? __ldg(base + u * x.ld + c0 + cc) : 0.0f;
+      }
+      for (int e = r; e < L * PT_CB * QC; e += PT_THREADS) {
+        const int q = e % QC, cc = (e / QC) % PT_CB, k = e / (QC * PT_CB);
+        ws[e] = (c0 + cc < C && q0 + q < Dy) ? __ldg(W + ((int64_t)k * C + c0 + cc) * Dy + q0 + q) : 0.0f;
+      }
+      __syncthreads();
+      for (int k = 0; k < L; ++k) {
+        const float* xr = xs + (size_t)(r + k) * (PT_CB + 1);
+        const float* wk = ws + (size_t)k * PT_CB * QC;
+#pragma unroll 8
+        for (int cc = 0; cc < PT_CB; ++cc) {
+          float w[QC];
+#pragma unroll
+          for (int q = 0; q < QC; ++q) w[q] = wk[cc * QC + q];
+#pragma unroll
+          for (int j = 0; j < PT_RPT; ++j) {
+            // rows beyond `rows` read frames of the tile that were never staged: they are not written out
+            const float xv = (r + PT_THREADS * j < rows) ? xr[(size_t)PT_THREADS * j * (PT_CB + 1) + cc] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < QC; ++q) acc[j][q] = fmaf(xv, w[q], acc[j][q]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < PT_RPT; ++j) {
+      const int row = r + PT_THREADS * j;
+      if (row < rows) {
+#pragma unroll
+        for (int q = 0; q < QC; ++q)
+          if (q0 + q < Dy)
+            out[(out_row[seg] + t0 + row) * ldo + q0 + q] =
+                acc[j][q] + (bias ? bias[q0 + q] : 0.0f) - (mean ? s_off[q] : 0.0f);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void rows_kernel(StreamView x, const int64_t* seg_keep, const int64_t* out_row,
                             const int* blk_seg, const int64_t* blk_t0, int rows_per_block,
                             float* out, int64_t ldo) {
@@ -624,6 +739,29 @@ int predict_impl(const td_stream* x, const int64_t* seg_keep, const int64_t* out
   const int64_t *keep_dev, *orow_dev;
   rc = tabs.put(seg_keep, n_seg, &keep_dev); if (rc) return rc;
   rc = tabs.put(out_row, n_seg, &orow_dev); if (rc) return rc;
+  // Tiled kernel whenever its tile (raw rows + halo, weights of 32 channels) fits shared memory.
+  const int L = lags_of(*x);
+  const int qc = (Dy == 1) ? 1 : (Dy == 2 ? 2 : 4);
+  const size_t tiled_smem = ((size_t)(PT_ROWS + L - 1) * (PT_CB + 1) + (size_t)L * PT_CB * qc) * sizeof(float);
+  if (tiled_smem <= 200 * 1024) {
+    const int* blk_seg; const int64_t* blk_t0; int64_t nblk;
+    rc = make_blocks(seg_keep, n_seg, PT_ROWS, tabs, &blk_seg, &blk_t0, &nblk);
+    if (rc) return rc;
+    if (nblk > 0) {
+      if (qc == 1) {
+        TD_CHECK_CUDA(cudaFuncSetAttribute(predict_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
+        predict_tiled_kernel<1><<<(unsigned)nblk, PT_THREADS, tiled_smem, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, W, bias, mean, Dy, out, ldo, w_seg_stride, b_seg_stride);
+      } else if (qc == 2) {
+        TD_CHECK_CUDA(cudaFuncSetAttribute(predict_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
+        predict_tiled_kernel<2><<<(unsigned)nblk, PT_THREADS, tiled_smem, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, W, bias, mean, Dy, out, ldo, w_seg_stride, b_seg_stride);
+      } else {
+        TD_CHECK_CUDA(cudaFuncSetAttribute(predict_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
+        predict_tiled_kernel<4><<<(unsigned)nblk, PT_THREADS, tiled_smem, st>>>(xv, keep_dev, orow_dev, blk_seg, blk_t0, W, bias, mean, Dy, out, ldo, w_seg_stride, b_seg_stride);
+      }
+      TD_CHECK_CUDA(cudaGetLastError());
+    }
+    return TD_OK;
+  }
   const int rows_per_block = 8 * PR_ROWS;
   const int* blk_seg; const int64_t* blk_t0; int64_t nblk;
   rc = make_blocks(seg_keep, n_seg, rows_per_block, tabs, &blk_seg, &blk_t0, &nblk);
