@@ -54,8 +54,9 @@ static_assert(RECT_STAGE_BYTES % 1024 == 0, "stage must keep the 1024-byte align
 constexpr size_t RECT_SMEM_BYTES = (size_t)STAGES * RECT_STAGE_BYTES + 1024 + 256;
 static_assert(RECT_SMEM_BYTES <= 232448, "rectangular flavour exceeds the 227 KB of shared memory");
 constexpr int NUM_THREADS = 512;
-constexpr int NUM_CONV = 4;                              // warps 4..7
-constexpr int EPI_WARP0 = 8, NUM_EPI = 8;
+constexpr int NUM_THREADS_F16 = 640;                     // fp16 x 3: one more warpgroup (B converters)
+constexpr int NUM_CONV = 4;                              // warps 4..7 (fp16 x 3: 4..7 build A, 8..11 build B)
+constexpr int NUM_EPI = 8;                               // the last two warpgroups
 constexpr uint32_t ACC_COLS = 128;
 constexpr uint32_t A_COL0 = 3 * ACC_COLS;
 constexpr uint32_t A_SLOT_COLS = 32;
@@ -85,6 +86,11 @@ struct HaloParams {
   int chunk_kt;
   long long total_steps;
   long long* prof;
+  // fp16 x 3 flavour (F16 = true): the tensor maps cover the pre-split copy of the recording (one
+  // 32-bit word per sample: fp16 hi | fp16 lo << 16 of the sample times its channel's power-of-two
+  // scale); the epilogue multiplies element (m, n) by inv_scale_a[m] * inv_scale[n] (tile-space rows).
+  const float* inv_scale;
+  const float* inv_scale_a;
 };
 
 }  // namespace hk
@@ -108,13 +114,24 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 
 // RECT = false: symmetric Gram (lower-triangle tile set, A and B from the same row groups).
 // RECT = true:  rectangular product for method 5; tmap1 is then the A-side map (box 32 ch x 32 frames).
-template <bool RECT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// F16 = false:  3xTF32 -- fp32 samples, hi = the raw bits (the tensor core ignores the low 13 mantissa
+//               bits), lo = x - trunc(x), K = 8 per MMA.
+// F16 = true:   3xFP16 -- the same 11 + 11 bit split (hi = fp16(x'), lo = fp16(x' - hi), x' = x times a
+//               per-channel power of two that puts the channel's largest sample in [2^14, 2^15), so
+//               that neither half leaves the fp16 range) done ONCE by split_rows_kernel; a converter
+//               thread only packs two frames per register.  K = 16 per MMA: half the tensor-pipe
+//               cycles of 3xTF32 for the same products hi*hi + hi*lo + lo*hi in fp32 accumulators.
+template <bool RECT, bool F16>
+__global__ void __launch_bounds__(F16 ? NUM_THREADS_F16 : NUM_THREADS, 1)
 lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
                         const __grid_constant__ CUtensorMap tmap1, const HaloParams P) {
-  constexpr uint32_t IDESC = ptx::umma_idesc_tf32(256, 128);
+  constexpr uint32_t IDESC = F16 ? ptx::umma_idesc_f16(256, 128) : ptx::umma_idesc_tf32(256, 128);
   constexpr int STAGE_BYTES = RECT ? RECT_STAGE_BYTES : hk::STAGE_BYTES;
   constexpr int OFF_BRAW = RECT ? RECT_OFF_BRAW : hk::OFF_BRAW;
+  constexpr int EPI_WARP0 = F16 ? 12 : 8;
+  // Register budget per warpgroup (regs per thread; the launch allocates 128 x 512 resp. 96 x 640):
+  //   3xTF32:  72 + 104 + 168 + 168 = 512        3xFP16:  40 + 72 + 72 + 144 + 144 = 472 <= 480
+  constexpr int REGS_WG0 = F16 ? 56 : 72, REGS_CONV = F16 ? 64 : 104, REGS_EPI = F16 ? 144 : 168;
   using ts::HalfRing;
   using ts::lo_bits;
 
@@ -145,7 +162,7 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
       ptx::mbar_init(empty_bar(s), 2);
     }
     for (int j = 0; j < A_SLOTS; ++j) {
-      ptx::mbar_init(ready_bar(j), 2 * NUM_CONV);
+      ptx::mbar_init(ready_bar(j), 2 * NUM_CONV * (F16 ? 2 : 1));
       ptx::mbar_init(aempty_bar(j), 2);
     }
     for (int h = 0; h < 2; ++h)
@@ -161,10 +178,9 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // Register budget per warpgroup: 128 x (72 + 104 + 168 + 168) = 65536.
   const int wg = warp >> 2;
   if (wg == 0) {
-    ptx::setmaxnreg_dec<72>();
+    ptx::setmaxnreg_dec<REGS_WG0>();
     if (warp == 0) {
       // ===================== TMA producer: raw boxes of this CTA's A and B row groups =============
       WorkIter wi(P, worker, n_workers);
@@ -237,6 +253,28 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
             if (kt == c0) ptx::mbar_wait(tempty_bar(1 - h, r), ring.drained_parity(h));
             const uint64_t b_hi = ptx::umma_desc_k_sw128(sbase + OFF_BHI + h * (OPERAND_BYTES / 2));
             const uint64_t b_lo = ptx::umma_desc_k_sw128(sbase + OFF_BLO + h * (OPERAND_BYTES / 2));
+            if constexpr (F16) {
+              // One A slot = one k-tile (32 frames = two K = 16 steps: hi columns [8s, 8s + 8), lo columns
+              // [16 + 8s, ...); 32 bytes of a B row per step).  Frames outside the call's row range are
+              // zero in A, so partial k-tiles need no skipping.
+              const uint32_t slot = kcount & (A_SLOTS - 1);
+              ptx::mbar_wait_lean(ready_bar(slot), (kcount >> 2) & 1u);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                const uint32_t a_base = tmem_base + A_COL0 + slot * A_SLOT_COLS;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t adv = (uint64_t)(ks * 2);
+                  ptx::mma_f16_ts_pair(d, a_base + 8 * ks, b_hi + adv, IDESC, ks ? 1u : first_acc);
+                  ptx::mma_f16_ts_pair(d, a_base + 8 * ks, b_lo + adv, IDESC, 1u);
+                  ptx::mma_f16_ts_pair(d, a_base + 16 + 8 * ks, b_hi + adv, IDESC, 1u);
+                }
+                ptx::mma_commit<2>(aempty_bar(slot));
+                ptx::mma_commit<2>(empty_bar(stage));
+                if (kt == c1 - 1) ptx::mma_commit<2>(tfull_bar(h, r));
+              }
+              __syncwarp();
+            } else {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               const uint32_t use = 2u * kcount + hh;
@@ -275,14 +313,15 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
               }
               __syncwarp();
             }
+            }
             if (++stage == STAGES) stage = 0;
           }
         }
       }
     }
-  } else if (wg == 1) {
+  } else if (!F16 && wg == 1) {
     // ===================== converters: raw boxes -> A in TMEM (hi | lo), B hi / lo tiles ==========
-    ptx::setmaxnreg_dec<104>();
+    ptx::setmaxnreg_dec<REGS_CONV>();
     const int quad = warp & 3;
     const int row = quad * 32 + lane;                    // A row (= TMEM lane) and B row of this thread
     const int kk = lane >> 3, cc = lane & 7;             // lag and channel of the row inside its row group
@@ -375,9 +414,113 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
+  } else if (F16 && wg <= 2) {
+    // ===================== fp16 x 3 converters: warpgroup 1 builds A (TMEM), warpgroup 2 builds B (smem) ====
+    // Every raw word is (hi | lo << 16) of one sample (split_rows_kernel); converting means packing
+    // two frames per 32-bit register, one k-tile (32 frames of this thread's row) per step.
+    //   A: hi halves = TMEM columns [0, 16) of the slot, lo halves = columns [16, 32);
+    //   B: frame t of a row sits in 16-byte chunk (t/8) ^ (row%8) of the hi tile and of the lo tile.
+    // Two warpgroups, because a k-tile is only 768 tensor-pipe clocks now: each group's chain (wait,
+    // 32 loads, pack, store, fence, arrive) has to fit into that with room to spare.
+    ptx::setmaxnreg_dec<REGS_CONV>();
+    const bool is_a = (wg == 1);
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int kk = lane >> 3, cc = lane & 7;
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t ready_leader0 = ptx::mapa(ready_bar(0), 0);
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + A_COL0;
+    WorkIter wi(P, worker, n_workers);
+    WorkItem it;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t kcount = 0;
+    while (wi.next(P, it)) {
+      const int4 g = is_a ? __ldg(&(RECT ? P.rgs_a : P.rgs)[(it.tm * 2 + (int)rank) * RG_PER_CTA + quad])
+                          : __ldg(&P.rgs[(it.tn * 2 + (int)rank) * RG_PER_CTA + quad]);
+      const bool rect_a = RECT && is_a;                  // lane = channel of a 32-channel, one-lag row group
+      const uint32_t rd = (is_a ? OFF_ARAW : OFF_BRAW) + (uint32_t)g.w +
+                          (rect_a ? (uint32_t)lane * 4u : (uint32_t)(kk * BOX_CH + cc) * 4u);
+      const uint32_t frame_bytes = rect_a ? ABOX_CH * 4 : BOX_CH * 4;
+      const int d = g.z + (rect_a ? 0 : kk);             // lag shift k - pre of this thread's row
+      const int q = g.x & 1;
+      int4 kn0 = __ldg(&P.ktiles[2 * it.kt_begin]);
+      int4 kn1 = __ldg(&P.ktiles[2 * it.kt_begin + 1]);
+      for (long long kt = it.kt_begin; kt < it.kt_end; ++kt, ++kcount) {
+        const int4 k0 = kn0, k1 = kn1;
+        if (kt + 1 < it.kt_end) {
+          kn0 = __ldg(&P.ktiles[2 * (kt + 1)]);
+          kn1 = __ldg(&P.ktiles[2 * (kt + 1) + 1]);
+        }
+        const uint32_t slot = kcount & (A_SLOTS - 1);
+        const uint32_t sbase = smem_base + stage * STAGE_BYTES;
+        const bool special = k0.z != (BK << 8);           // anything but a whole k-tile in the middle of a trial
+        const int begin = k0.z & 0xff, end = (k0.z >> 8) & 0xff;
+        const bool edge = (k0.z >> 16) != 0;
+        const bool partial = is_a && (begin > 0 || end < BK);        // the row range is cut on the A side only
+        const int lo_e = k0.w - d, hi_e = (q ? k1.y : k1.x) - d;     // inside the trial iff lo_e <= e < hi_e
+        const uint32_t bhi = sbase + OFF_BHI + row_off, blo = sbase + OFF_BLO + row_off;
+        ptx::mbar_wait_lean(full_bar(stage), phase);
+        if (is_a) {
+          ptx::mbar_wait_lean(aempty_bar(slot), ((kcount >> 2) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {                  // 16 frames at a time keeps the register footprint at ~32
+          uint32_t w[16], hi2[8], lo2[8];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) w[e] = lds32(sbase + rd + (uint32_t)(hh * 16 + e) * frame_bytes);
+          if (special) {
+            if (edge) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (hh * 16 + e < lo_e || hh * 16 + e >= hi_e) w[e] = 0u;
+            }
+            if (partial) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (hh * 16 + e < begin || hh * 16 + e >= end) w[e] = 0u;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            hi2[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x5410);     // hi halves of frames 2j, 2j + 1
+            lo2[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x7632);     // lo halves
+          }
+          if (is_a) {
+            ptx::tmem_st8(tlane + slot * A_SLOT_COLS + 8 * hh, hi2);
+            ptx::tmem_st8(tlane + slot * A_SLOT_COLS + 16 + 8 * hh, lo2);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const uint32_t off = ((uint32_t)(hh * 2 + i) ^ sw) << 4;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bhi + off), "r"(hi2[4 * i]),
+                           "r"(hi2[4 * i + 1]), "r"(hi2[4 * i + 2]), "r"(hi2[4 * i + 3])
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blo + off), "r"(lo2[4 * i]),
+                           "r"(lo2[4 * i + 1]), "r"(lo2[4 * i + 2]), "r"(lo2[4 * i + 3])
+                           : "memory");
+            }
+          }
+        }
+        if (is_a) {
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+        } else {
+          ptx::fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor-core proxy
+          // The ready barrier of a slot counts A and B arrivals of ONE use: B must not arrive for the
+          // slot's next use before the previous one is consumed.
+          ptx::mbar_wait_lean(aempty_bar(slot), ((kcount >> 2) & 1u) ^ 1u);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_remote(ready_leader0 + 8u * slot);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
   } else {
     // ===================== epilogue: TMEM region -> fp32 registers -> red.add =====================
-    ptx::setmaxnreg_inc<168>();
+    ptx::setmaxnreg_inc<REGS_EPI>();
     const int quad = warp & 3;                 // TMEM lanes [32*quad, 32*quad+32)
     const int half = (warp - EPI_WARP0) >> 2;  // which 128-column half of the pair tile
     const uint32_t tempty_leader0 = ptx::mapa(tempty_bar(half, 0), 0);
@@ -394,13 +537,24 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
         ptx::mbar_wait(tfull_bar(half, r), ring.n);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)r * ACC_COLS;
+        if constexpr (F16) {                 // 144 registers: 16 columns at a time
 #pragma unroll
-        for (int j = 0; j < NACC / 32; ++j) {
-          float v[32];
-          ptx::tmem_ld32(taddr + j * 32, v);
-          ptx::tmem_ld_wait();
+          for (int j = 0; j < NACC / 16; ++j) {
+            float v[16];
+            ptx::tmem_ld16(taddr + j * 16, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+            for (int i = 0; i < 16; ++i) acc[j * 16 + i] += v[i];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NACC / 32; ++j) {
+            float v[32];
+            ptx::tmem_ld32(taddr + j * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+          }
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -415,12 +569,17 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
       const int m_out = __ldg(&(RECT ? P.out_idx_a : P.out_idx)[m_row]);
       const bool all_pairs = RECT || it.tm > it.tn;
       float* Gout = P.G + (it.kt_begin / P.KS) * P.batch_stride;      // batched: one Gram per superchunk
+      float inv_m = 1.0f;
+      if constexpr (F16) inv_m = __ldg(&(RECT ? P.inv_scale_a : P.inv_scale)[m_row]);
 #pragma unroll
       for (int i = 0; i < NACC; ++i) {
         const int n_row = it.tn * 256 + (i >> 6) * TILE_ROWS + half * 64 + (i & 63);
         const int n_out = __ldg(&P.out_idx[n_row]);
-        if (m_out >= 0 && n_out >= 0 && (all_pairs || n_row <= m_row))
-          atomicAdd(Gout + (long long)n_out * P.ldg + m_out, acc[i]);
+        if (m_out >= 0 && n_out >= 0 && (all_pairs || n_row <= m_row)) {
+          float v = acc[i];
+          if constexpr (F16) v = (v * inv_m) * __ldg(&P.inv_scale[n_row]);     // exact: powers of two
+          atomicAdd(Gout + (long long)n_out * P.ldg + m_out, v);
+        }
       }
     }
   }

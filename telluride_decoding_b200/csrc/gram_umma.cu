@@ -28,6 +28,7 @@
 //      tiles are combined with fp32 red.add into G.
 //   3. the computed triangle is mirrored by td_symmetrize_f32.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -509,6 +510,79 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, int64_t ld, int C
   dst[i] = (c < C) ? src[(row0 + r) * ld + c] : 0.0f;
 }
 
+// ---- fp16 x 3 flavour of the halo kernel: per-channel scale and the pre-split copy ----------------
+// Largest |sample| per channel over rows [row0, row0 + n_rows) (bit pattern of a non-negative float:
+// unsigned order = numeric order; a NaN ends up on top and switches the scaling off for that channel).
+// block (32 channels, 8 row lanes), grid (row slabs, channel blocks).
+constexpr int SPLIT_ROWS_PER_BLOCK = 256;
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ src, int64_t ld, int C, int64_t row0,
+                                                     int64_t n_rows, unsigned* __restrict__ amax_bits) {
+  __shared__ unsigned red[8][32];
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * SPLIT_ROWS_PER_BLOCK;
+  const int64_t r1 = min(r0 + SPLIT_ROWS_PER_BLOCK, n_rows);
+  unsigned m = 0;
+  if (c < C)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8)
+      m = max(m, __float_as_uint(src[(row0 + r) * ld + c]) & 0x7fffffffu);
+  red[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = max(m, red[i][threadIdx.x]);
+    if (m) atomicMax(&amax_bits[c], m);
+  }
+}
+
+// Power of two that moves a channel's largest sample into [2^14, 2^15) (fp16 tops out at 65504; the lo
+// halves then sit 11 bits lower, far above the fp16 subnormal spacing of 2^-24).
+__device__ __forceinline__ int scale_exponent(unsigned amax_bits) {
+  const float a = __uint_as_float(amax_bits);
+  if (!(a > 0.0f) || !(a < __int_as_float(0x7f800000))) return 0;
+  int e;
+  frexpf(a, &e);                                   // a = m * 2^e, m in [0.5, 1)
+  return max(-120, min(120, 15 - e));
+}
+
+// dst[r][c] = fp16(x') | fp16(x' - fp16(x')) << 16 with x' = src[row0 + r][c] * 2^scale_exponent(c);
+// channels in [C, ldp) are zero.  Same thread layout as absmax_kernel.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ src, int64_t ld, int C, int64_t row0,
+                                                         int64_t n_rows, const unsigned* __restrict__ amax_bits,
+                                                         uint32_t* __restrict__ dst, int ldp) {
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  if (c >= ldp) return;
+  const int64_t r0 = (int64_t)blockIdx.x * SPLIT_ROWS_PER_BLOCK;
+  const int64_t r1 = min(r0 + SPLIT_ROWS_PER_BLOCK, n_rows);
+  const float scale = (c < C) ? ldexpf(1.0f, scale_exponent(amax_bits[c])) : 0.0f;
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+    uint32_t w = 0;
+    if (c < C) {
+      const float xs = src[(row0 + r) * ld + c] * scale;
+      const __half hi = __float2half_rn(xs);
+      const __half lo = __float2half_rn(xs - __half2float(hi));
+      w = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+    }
+    dst[r * ldp + c] = w;
+  }
+}
+
+// inv[r] = 1 / scale of the channel behind tile-space row r (0 for padding rows).  Column j of the
+// design belongs to stream 0 below col1 (channel j % C0), else to stream 1 (channel (j - col1) % C1).
+__global__ void row_inv_scale_kernel(const int* __restrict__ out_idx, int64_t n, int64_t col1, int C0, int C1,
+                                     const unsigned* __restrict__ amax0, const unsigned* __restrict__ amax1,
+                                     float* __restrict__ inv) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int j = out_idx[r];
+  float v = 0.0f;
+  if (j >= 0) {
+    const bool second = C1 > 0 && j >= col1;
+    const unsigned bits = second ? amax1[(j - col1) % C1] : amax0[j % C0];
+    v = ldexpf(1.0f, -scale_exponent(bits));
+  }
+  inv[r] = v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host-side plan.
 // ---------------------------------------------------------------------------------------------
@@ -676,12 +750,15 @@ struct HaloPlan {
   int64_t Dz = 0, Dpad = 0, NK = 0;
   int nt = 0, ntri = 0, n_rg = 0;
   bool staged[2] = {false, false};
+  bool f16 = false;
   int64_t ld_eff[2] = {0, 0}, row_lo[2] = {0, 0}, n_rows[2] = {0, 0};
-  size_t off_stage[2] = {0, 0}, off_rgs = 0, off_ktiles = 0, off_outidx = 0, total = 0;
+  size_t off_stage[2] = {0, 0}, off_rgs = 0, off_ktiles = 0, off_outidx = 0, off_amax[2] = {0, 0}, off_inv = 0,
+         total = 0;
 };
 
 int make_halo_plan(const td_stream* streams, int n_streams, const int64_t* seg_first,
-                   const int64_t* seg_keep, int n_seg, HaloPlan* pl) {
+                   const int64_t* seg_keep, int n_seg, HaloPlan* pl, bool f16 = false) {
+  pl->f16 = f16;
   TD_REQUIRE(n_streams == 1 || n_streams == 2, "td_lagged_gram: n_streams must be 1 or 2, not %d", n_streams);
   TD_REQUIRE(n_seg > 0, "td_lagged_gram: no segments");
   pl->n_streams = n_streams;
@@ -729,8 +806,8 @@ int make_halo_plan(const td_stream* streams, int n_streams, const int64_t* seg_f
     // into a padded buffer (1x the touched part of the recording, not the 4 shifted planes of the
     // earlier kernels).
     const bool aligned = (streams[q].ld % 4 == 0) && (reinterpret_cast<uintptr_t>(streams[q].data_dev) % 16 == 0);
-    pl->staged[q] = !aligned;
-    if (aligned) {
+    pl->staged[q] = !aligned || f16;                 // fp16 x 3 always reads its pre-split copy
+    if (!pl->staged[q]) {
       pl->ld_eff[q] = streams[q].ld;
       pl->row_lo[q] = 0;
       pl->n_rows[q] = extent;
@@ -746,7 +823,42 @@ int make_halo_plan(const td_stream* streams, int n_streams, const int64_t* seg_f
   pl->off_rgs = off;     off += (size_t)round_up((pl->Dpad / hk::RG_ROWS) * (int64_t)sizeof(int4), 1024);
   pl->off_ktiles = off;  off += (size_t)round_up(std::max<int64_t>(nk, 1) * 2 * (int64_t)sizeof(int4), 1024);
   pl->off_outidx = off;  off += (size_t)round_up(pl->Dpad * (int64_t)sizeof(int), 1024);
+  if (f16) {
+    for (int q = 0; q < n_streams; ++q) {
+      pl->off_amax[q] = off;
+      off += (size_t)round_up(pl->C[q] * (int64_t)sizeof(unsigned), 1024);
+    }
+    pl->off_inv = off;   off += (size_t)round_up(pl->Dpad * (int64_t)sizeof(float), 1024);
+  }
   pl->total = off;
+  return TD_OK;
+}
+
+// The staged copy of stream q: a padded fp32 copy (rows TMA cannot address), or, for the fp16 x 3
+// flavour, the pre-split copy (absmax pass + split pass; amax stays in the workspace for the epilogue's
+// inverse scales).
+int stage_stream(const HaloPlan& pl, const td_stream* streams, int q, uint8_t* ws, cudaStream_t st) {
+  float* dst = reinterpret_cast<float*>(ws + pl.off_stage[q]);
+  if (pl.n_rows[q] <= 0) {
+    if (pl.f16) TD_CHECK_CUDA(cudaMemsetAsync(ws + pl.off_amax[q], 0, pl.C[q] * sizeof(unsigned), st));
+    return TD_OK;
+  }
+  if (!pl.f16) {
+    const int64_t total = pl.n_rows[q] * pl.ld_eff[q];
+    pad_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(streams[q].data_dev, streams[q].ld, pl.C[q],
+                                                                  pl.row_lo[q], pl.n_rows[q], dst, (int)pl.ld_eff[q]);
+    TD_CHECK_CUDA(cudaGetLastError());
+    return TD_OK;
+  }
+  unsigned* amax = reinterpret_cast<unsigned*>(ws + pl.off_amax[q]);
+  TD_CHECK_CUDA(cudaMemsetAsync(amax, 0, pl.C[q] * sizeof(unsigned), st));
+  const dim3 block(32, 8);
+  const dim3 grid((unsigned)ceil_div(pl.n_rows[q], SPLIT_ROWS_PER_BLOCK), (unsigned)ceil_div(pl.ld_eff[q], 32));
+  absmax_kernel<<<grid, block, 0, st>>>(streams[q].data_dev, streams[q].ld, pl.C[q], pl.row_lo[q], pl.n_rows[q], amax);
+  TD_CHECK_CUDA(cudaGetLastError());
+  split_rows_kernel<<<grid, block, 0, st>>>(streams[q].data_dev, streams[q].ld, pl.C[q], pl.row_lo[q], pl.n_rows[q], amax,
+                                            reinterpret_cast<uint32_t*>(dst), (int)pl.ld_eff[q]);
+  TD_CHECK_CUDA(cudaGetLastError());
   return TD_OK;
 }
 
@@ -776,7 +888,8 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
              int n_seg, float* G, int64_t ldg, const td_gram_options* opt, void* workspace,
              size_t workspace_bytes, cudaStream_t st, bool batched = false) {
   HaloPlan pl;
-  int rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &pl);
+  const bool f16 = opt && opt->method == 6;
+  int rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &pl, f16);
   if (rc) return rc;
   int64_t kt_per_seg = 0;
   if (batched) {
@@ -870,19 +983,21 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
   for (int q = 0; q < n_streams; ++q) {
     const float* base = streams[q].data_dev;
     if (pl.staged[q]) {
-      float* dst = reinterpret_cast<float*>(ws + pl.off_stage[q]);
-      const int64_t total = pl.n_rows[q] * pl.ld_eff[q];
-      if (total > 0) {
-        pad_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(streams[q].data_dev, streams[q].ld, pl.C[q],
-                                                                      pl.row_lo[q], pl.n_rows[q], dst, (int)pl.ld_eff[q]);
-        TD_CHECK_CUDA(cudaGetLastError());
-      }
-      base = dst;
+      if ((rc = stage_stream(pl, streams, q, ws, st))) return rc;
+      base = reinterpret_cast<const float*>(ws + pl.off_stage[q]);
     }
-    rc = make_tmap_raw(&tmaps[q], base, pl.n_rows[q], pl.C[q], pl.ld_eff[q]);
+    // (the pre-split copy has ld_eff words per row, channels up to ld_eff are real zeros)
+    rc = make_tmap_raw(&tmaps[q], base, pl.n_rows[q], f16 ? (int)pl.ld_eff[q] : pl.C[q], pl.ld_eff[q]);
     if (rc) return rc;
   }
   if (n_streams == 1) tmaps[1] = tmaps[0];
+  if (f16) {
+    row_inv_scale_kernel<<<(unsigned)ceil_div(pl.Dpad, 256), 256, 0, st>>>(
+        reinterpret_cast<const int*>(ws + pl.off_outidx), pl.Dpad, n_streams == 2 ? width_of(streams[0]) : 0, pl.C[0],
+        n_streams == 2 ? pl.C[1] : 0, reinterpret_cast<const unsigned*>(ws + pl.off_amax[0]),
+        reinterpret_cast<const unsigned*>(ws + pl.off_amax[n_streams == 2 ? 1 : 0]), reinterpret_cast<float*>(ws + pl.off_inv));
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
   if ((rc = debug_sync(st, "halo stage"))) return rc;
 
   const int64_t n_out = batched ? n_seg : 1;
@@ -896,6 +1011,8 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
     P.rgs = reinterpret_cast<const int4*>(ws + pl.off_rgs);
     P.ktiles = reinterpret_cast<const int4*>(ws + pl.off_ktiles);
     P.out_idx = reinterpret_cast<const int*>(ws + pl.off_outidx);
+    P.inv_scale = f16 ? reinterpret_cast<const float*>(ws + pl.off_inv) : nullptr;
+    P.inv_scale_a = nullptr;
     P.G = G;
     P.ldg = ldg;
     P.ntri = pl.ntri;
@@ -931,10 +1048,11 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
       }
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
-    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::SMEM_BYTES));
+    auto kernel = f16 ? hk::lagged_gram_halo_kernel<false, true> : hk::lagged_gram_halo_kernel<false, false>;
+    TD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::SMEM_BYTES));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * 2);
-    cfg.blockDim = dim3(hk::NUM_THREADS);
+    cfg.blockDim = dim3(f16 ? hk::NUM_THREADS_F16 : hk::NUM_THREADS);
     cfg.dynamicSmemBytes = hk::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -944,7 +1062,7 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel<false>, tmaps[0], tmaps[1], P));
+    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmaps[0], tmaps[1], P));
     TD_CHECK_CUDA(cudaGetLastError());
     if (timed) {
       TD_CHECK_CUDA(cudaEventRecord(g_ev_stop, st));
@@ -1032,10 +1150,10 @@ constexpr int DEFAULT_PAIR_METHOD = 4;
 int use_halo(const td_stream* streams, int n_streams, const td_gram_options* opt, bool* halo) {
   const int m = opt ? opt->method : 0;
   const int cg = opt ? opt->cta_group : 0;
-  TD_REQUIRE(m >= 0 && m <= 5, "td_lagged_gram: unknown method %d", m);
+  TD_REQUIRE(m >= 0 && m <= 6, "td_lagged_gram: unknown method %d", m);
   TD_REQUIRE(cg >= 0 && cg <= 2, "td_lagged_gram: cta_group must be 0, 1 or 2");
-  TD_REQUIRE(!(m == 4 && cg == 1), "td_lagged_gram: method 4 (operand built on chip) needs CTA pairs");
-  *halo = (m == 4);
+  TD_REQUIRE(!((m == 4 || m == 6) && cg == 1), "td_lagged_gram: methods 4 and 6 (operand built on chip) need CTA pairs");
+  *halo = (m == 4 || m == 6);
   if (m == 0 && DEFAULT_PAIR_METHOD == 4 && cg != 1 && streams) {
     // Row groups are 4 lags x 8 channels: a design with very few lags (or channels) would mostly
     // multiply padding (one lag fills a quarter of its row groups); those go to the staged kernels.
@@ -1162,14 +1280,8 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
 
   const float* base = streams[0].data_dev;
   if (pl.staged[0]) {
-    float* dst = reinterpret_cast<float*>(ws + pl.off_stage[0]);
-    const int64_t total = pl.n_rows[0] * pl.ld_eff[0];
-    if (total > 0) {
-      pad_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(streams[0].data_dev, streams[0].ld, C, pl.row_lo[0],
-                                                                    pl.n_rows[0], dst, (int)pl.ld_eff[0]);
-      TD_CHECK_CUDA(cudaGetLastError());
-    }
-    base = dst;
+    if ((rc = stage_stream(pl, streams, 0, ws, st))) return rc;
+    base = reinterpret_cast<const float*>(ws + pl.off_stage[0]);
   }
   CUtensorMap tmap, tmap_a;
   rc = make_tmap_raw(&tmap, base, pl.n_rows[0], C, pl.ld_eff[0]);
@@ -1184,6 +1296,8 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     P.ktiles = reinterpret_cast<const int4*>(ws + pl.off_ktiles);
     P.out_idx = reinterpret_cast<const int*>(ws + pl.off_outidx);
     P.rect_ta = ta;
+    P.inv_scale = nullptr;
+    P.inv_scale_a = nullptr;
     P.rgs_a = reinterpret_cast<const int4*>(ws + off_rga);
     P.out_idx_a = reinterpret_cast<const int*>(ws + off_oia);
     P.G = Ct;
@@ -1215,7 +1329,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
       }
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
-    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::RECT_SMEM_BYTES));
+    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::RECT_SMEM_BYTES));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * 2);
     cfg.blockDim = dim3(hk::NUM_THREADS);
@@ -1228,7 +1342,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel<true>, tmap, tmap_a, P));
+    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel<true, false>, tmap, tmap_a, P));
     TD_CHECK_CUDA(cudaGetLastError());
     if (timed) {
       TD_CHECK_CUDA(cudaEventRecord(g_ev_stop, st));
@@ -1271,7 +1385,7 @@ extern "C" int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_st
   if (rc) return rc;
   if (halo) {
     HaloPlan hp;
-    rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &hp);
+    rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &hp, opt && opt->method == 6);
     if (rc) return rc;
     *bytes = hp.total;
     return TD_OK;
@@ -1556,12 +1670,12 @@ extern "C" int td_lagged_gram_batched_f32(const td_stream* streams, int n_stream
                                           void* stream) {
   TD_REQUIRE(streams && seg_keep && G, "td_lagged_gram_batched_f32: null argument");
   td_gram_options o = opt ? *opt : td_gram_options{};
-  TD_REQUIRE(o.method == 0 || o.method == 4 || o.method == 5,
-             "td_lagged_gram_batched_f32: methods 4 (0 = default) and 5 write per-segment Grams");
+  TD_REQUIRE(o.method == 0 || o.method == 4 || o.method == 5 || o.method == 6,
+             "td_lagged_gram_batched_f32: methods 4 (0 = default), 5 and 6 write per-segment Grams");
   if (o.method == 5)
     return run_toeplitz(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, &o, workspace, workspace_bytes,
                         (cudaStream_t)stream, nullptr, /*batched=*/true);
-  o.method = 4;
+  if (o.method != 6) o.method = 4;
   o.cta_group = 2;
   return run_halo(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, &o, workspace, workspace_bytes,
                   (cudaStream_t)stream, /*batched=*/true);
@@ -1575,7 +1689,7 @@ extern "C" int td_lagged_gram_batched_workspace_bytes(const td_stream* streams, 
     return run_toeplitz(streams, n_streams, seg_first, seg_keep, n_seg, nullptr, 0, opt, nullptr, 0, nullptr, bytes,
                         /*batched=*/true);
   td_gram_options o = opt ? *opt : td_gram_options{};
-  o.method = 4;
+  if (o.method != 6) o.method = 4;
   o.cta_group = 2;
   return td_lagged_gram_workspace_bytes(streams, n_streams, seg_first, seg_keep, n_seg, &o, bytes);
 }

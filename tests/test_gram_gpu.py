@@ -262,7 +262,7 @@ def test_argument_errors_surface_as_exceptions():
     dict(lens=[3000, 2500], c=40, pre=5, post=26, keep=[2900, 2500], first=[37, 1024]),
     dict(lens=[64] * 200, c=24, pre=4, post=19),                    # hundreds of tiny trials
 ])
-@pytest.mark.parametrize('method', [4, 5])
+@pytest.mark.parametrize('method', [4, 5, 6])
 def test_operand_built_on_chip_masks_and_layouts(case, method):
   """Method 4 specifics against the ORACLE's lagged design: zero padding at trial edges rebuilt by
   masks (the raw TMA box runs into the neighbouring trial; brain_data.py:448-452), row ranges,
@@ -292,10 +292,11 @@ def test_operand_built_on_chip_two_streams_with_offset():
   for offset, chunk in ((3, 1000000), (-2, 700)):
     ds, batches = _dataset(2600, 40, 1, 14, 100, seed=9, c2=5, pre2=2, post2=1, offset=offset, chunk=chunk)
     (w, keep), = ds.passes()
-    g = ops.lagged_gram([ds.stream('x'), ds.stream('x2')], keep,
-                        options=ops.gram_options(method=4)).cpu().numpy()
     z = np.concatenate([gpu_util.design64(batches), gpu_util.design64(batches, 'input_2')], axis=1)
-    assert gpu_util.rel_fro(g, z.T @ z) < GRAM_TOL
+    for method in (4, 6):
+      g = ops.lagged_gram([ds.stream('x'), ds.stream('x2')], keep,
+                          options=ops.gram_options(method=method)).cpu().numpy()
+      assert gpu_util.rel_fro(g, z.T @ z) < GRAM_TOL, method
 
 
 def test_block_toeplitz_gram_on_config2_and_sharded_rows():
@@ -334,9 +335,47 @@ def test_per_segment_grams_dense_and_block_toeplitz():
   lens = [n] * n_trials
   s = ops.Stream(xd, 2, lags - 3, starts, lens)
   want = torch.stack([ops.lagged_gram([ops.Stream(xd, 2, lags - 3, [starts[i]], [n])], [n]) for i in range(n_trials)])
-  for method in (0, 5):
+  for method in (0, 5, 6):
     got = ops.lagged_gram_per_segment([s], lens, options=ops.gram_options(method=method))
     assert got.shape == (n_trials, c * lags, c * lags)
     for i in range(n_trials):
       assert gpu_util.rel_fro(got[i].cpu().numpy(), want[i].cpu().numpy()) < 5e-6, (method, i)
       assert torch.equal(got[i], got[i].t())
+
+
+def test_fp16_split_flavour_over_badly_scaled_channels():
+  """Method 6 multiplies every channel by a power of two before the fp16 hi / lo split and undoes it in
+  the epilogue: channels in volts next to channels in the thousands, a heavy-tailed channel (one
+  artefact 1e4 times the rest), a constant and an all-zero channel -- block by block against float64
+  products, each block normalised by its own size (a global Frobenius norm would only see the largest
+  channels)."""
+  rng = np.random.RandomState(5)
+  n, c, pre, post = 6000, 24, 2, 9
+  x = rng.randn(n, c).astype(np.float32)
+  gains = np.array([1e-6, 3e-5, 1.0, 4096.0, 7e3, 1e-3] * 4, np.float32)
+  x *= gains
+  x[:, 6] = 0.0
+  x[:, 7] = 2.5
+  x[1234, 8] = 1e4
+  xd = torch.as_tensor(x, device='cuda')
+  stream = ops.Stream(xd, pre, post, [0, 2500], [2500, 3500])
+  keep = [2500, 3400]
+  design = np.concatenate([ora.add_context(x[:2500], pre, post), ora.add_context(x[2500:], pre, post)[:3400]]).astype(np.float64)
+  want = design.T @ design
+  lags = pre + post + 1
+  for method in (4, 6):
+    got = ops.lagged_gram([stream], keep, options=ops.gram_options(method=method)).cpu().numpy().astype(np.float64)
+    assert np.array_equal(got, got.T)
+    worst = 0.0
+    for c1 in range(c):
+      for c2 in range(c):
+        w = want[c1::c, c2::c]
+        g = got[c1::c, c2::c]
+        assert w.shape == (lags, lags)
+        scale = np.sqrt(want[c1::c, c1::c].diagonal().mean() * want[c2::c, c2::c].diagonal().mean())
+        if scale > 0:
+          worst = max(worst, np.abs(g - w).max() / scale)
+        else:
+          assert not g.any()
+    print('method %d: worst block error relative to the channels\' energy %.2e' % (method, worst))
+    assert worst < GRAM_TOL, method
