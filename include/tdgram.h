@@ -72,15 +72,24 @@ int td_shutdown(void);
  *
  * The design is Z = [X_0 | X_1 | ...] over n_streams (1 or 2) lagged streams sharing the
  * segment table; G = Z'Z, [Dz, Dz] with Dz = sum_q channels_q * (pre_q+1+post_q), full
- * symmetric, row stride ldg.  method 0: tcgen05 3xTF32 implicit-Hankel kernel (hi/lo split built on
- * chip, TMEM fp32 accumulation flushed every `chunk_rows` frames into fp32 registers); it picks
- * between the flavours that can also be forced:
- *   4  CTA pairs; the lagged operand is built ON CHIP: one raw [32 + halo frames, 8 channels] TMA box
+ * symmetric, row stride ldg.  method 0: tcgen05 implicit-Hankel kernel on split operands (every sample
+ * x = hi + lo with 11 + 11 significant bits, products hi*hi + hi*lo + lo*hi, TMEM fp32 accumulation
+ * flushed every `chunk_rows` frames into fp32 registers: fp32-equivalent, relative Frobenius error
+ * ~1e-6); it picks between the flavours that can also be forced:
+ *   6  CTA pairs, 3xFP16 (kind::f16, K = 16 per MMA): the method-4 kernel on a PRE-SPLIT copy of the
+ *      recording -- one pass finds every channel's largest sample, a second writes one 32-bit word per
+ *      sample, fp16(x') | fp16(x' - fp16(x')) << 16 with x' = x * 2^e_c (the power of two that puts the
+ *      channel's peak in [2^14, 2^15), undone exactly in the epilogue), so neither half leaves the
+ *      fp16 range whatever the unit of the recording.  Same split as 3xTF32 with round-to-nearest hi
+ *      halves (measured 7e-7 against 2.3e-6), half the tensor-pipe cycles; on a power-capped B200
+ *      1.45 - 1.5x the frames per second of method 4.  Default for designs of >= 512 columns.
+ *      Workspace: tables + the pre-split copy (4 bytes per touched sample).
+ *   4  CTA pairs, 3xTF32 (kind::tf32, K = 8); the lagged operand is built ON CHIP: one raw [32 + halo frames, 8 channels] TMA box
  *      per 4-lag x 8-channel row group straight from the caller's time-major array, converter warps
  *      read every row at its own lag offset, rebuild the zero padding of the trial edges with masks and
- *      write A into tensor memory and B into swizzled shared memory.  Default for designs of >= 512
- *      columns.  Workspace: tables only (plus one padded copy of the touched rows when the row stride
- *      or base address is not a multiple of 16 bytes).
+ *      write A into tensor memory and B into swizzled shared memory.  Workspace: tables only (plus
+ *      one padded copy of the touched rows when the row stride or base address is not a multiple of
+ *      16 bytes).
  *   3  CTA pairs, A operand in tensor memory, operands fetched as (lag, channel-block) TMA boxes from
  *      four shifted channel-major copies of the recording staged in the workspace (round-1 kernel).
  *   2  both operands from shared memory (the only flavour for cta_group 1, i.e. narrow designs).
@@ -94,9 +103,9 @@ int td_shutdown(void);
  * Workspace: td_lagged_gram_workspace_bytes bytes of device memory.
  * ------------------------------------------------------------------------------------- */
 typedef struct td_gram_options {
-  int32_t method;        /* 0 = tcgen05 3xTF32 (default), 1 = fp32 SIMT cross-check, 2 / 3 / 4 = force a dense tcgen05 flavour, 5 = block-Toeplitz */
+  int32_t method;        /* 0 = tcgen05 split-operand kernel (default), 1 = fp32 SIMT cross-check, 2 / 3 / 4 / 6 = force a dense tcgen05 flavour, 5 = block-Toeplitz */
   int32_t cta_group;     /* 0 = auto, 1 = 128x128 tiles per CTA, 2 = CTA-pair 256x256 tiles */
-  int32_t chunk_rows;    /* TMEM flush period in frames (0 = default 128) */
+  int32_t chunk_rows;    /* TMEM flush period in frames (0 = default: 256 for method 6, else 128) */
   int32_t superchunk_rows; /* L2 working-set period in frames (0 = auto) */
   int32_t max_ctas;      /* 0 = all SMs */
   int32_t reserved[3];   /* reserved[0] = 1: record CUDA events around the Gram kernel */
@@ -116,7 +125,7 @@ int td_lagged_gram_f32(const td_stream* streams, int n_streams,
                        const int64_t* seg_first, const int64_t* seg_keep, int n_seg,
                        float* G_dev, int64_t ldg, const td_gram_options* opt,
                        void* workspace_dev, size_t workspace_bytes, void* cuda_stream);
-/* One Gram PER SEGMENT from one launch (method 4): G_dev [n_seg][Dz][ldg].  What leave-one-trial-out
+/* One Gram PER SEGMENT from one launch (methods 6 (default), 4 or 5): G_dev [n_seg][Dz][ldg].  What leave-one-trial-out
  * needs (regression.py:197-214, infer.py: each held-out trial's fold = total - trial): every
  * segment must span the same, non-zero number of 32-frame k-tiles. */
 int td_lagged_gram_batched_f32(const td_stream* streams, int n_streams,

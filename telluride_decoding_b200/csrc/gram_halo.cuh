@@ -66,6 +66,23 @@ constexpr int NACC = 128;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_BARRIERS = 2 * STAGES + 2 * A_SLOTS + 12;
 static_assert(8 * NUM_BARRIERS + 8 <= 256, "barrier block too small");
+// fp16 x 3 flavour: a B row holds its 32 hi halves in bytes [0, 64) and its 32 lo halves in bytes
+// [64, 128) of ONE 128-byte swizzled row, so a stage is 16 KiB of B + 12 KiB of raw boxes and eight
+// stages fit.  The raw ring has to be deep: a stage is busy from the TMA issue to the retirement of the
+// MMAs that read it (TMA latency + conversion + MMA + commit, ~4000 clocks), a k-tile lasts 768.
+#ifndef TD_F16_STAGES
+#define TD_F16_STAGES 6
+#endif
+constexpr int F16_STAGES = TD_F16_STAGES;
+constexpr int F16_OFF_BLO = 64;
+constexpr int F16_OFF_ARAW = OPERAND_BYTES;
+constexpr int F16_OFF_BRAW = F16_OFF_ARAW + RAW_BYTES;
+constexpr int F16_STAGE_BYTES = OPERAND_BYTES + 2 * RAW_BYTES;      // 28 KiB
+static_assert(F16_STAGE_BYTES % 1024 == 0, "stage must keep the 1024-byte alignment of the swizzled tiles");
+constexpr int F16_NUM_BARRIERS = 2 * F16_STAGES + 2 * A_SLOTS + 12;
+constexpr size_t F16_SMEM_BYTES = (size_t)F16_STAGES * F16_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+static_assert(8 * F16_NUM_BARRIERS + 8 <= 512, "barrier block too small");
+static_assert(F16_SMEM_BYTES <= 232448, "fp16 flavour exceeds the 227 KB of shared memory");
 
 struct HaloParams {
   const int4* rgs;        // [Dpad / 32] {stream | issue << 1, first channel, lag shift k0 - pre, byte offset in the operand's raw region}
@@ -126,12 +143,17 @@ __global__ void __launch_bounds__(F16 ? NUM_THREADS_F16 : NUM_THREADS, 1)
 lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
                         const __grid_constant__ CUtensorMap tmap1, const HaloParams P) {
   constexpr uint32_t IDESC = F16 ? ptx::umma_idesc_f16(256, 128) : ptx::umma_idesc_tf32(256, 128);
-  constexpr int STAGE_BYTES = RECT ? RECT_STAGE_BYTES : hk::STAGE_BYTES;
-  constexpr int OFF_BRAW = RECT ? RECT_OFF_BRAW : hk::OFF_BRAW;
+  static_assert(!(RECT && F16), "the rectangular flavour is 3xTF32 only");
+  constexpr int STAGES = F16 ? F16_STAGES : hk::STAGES;
+  constexpr int NUM_BARRIERS = F16 ? F16_NUM_BARRIERS : hk::NUM_BARRIERS;
+  constexpr int STAGE_BYTES = F16 ? F16_STAGE_BYTES : (RECT ? RECT_STAGE_BYTES : hk::STAGE_BYTES);
+  constexpr int OFF_ARAW = F16 ? F16_OFF_ARAW : hk::OFF_ARAW;
+  constexpr int OFF_BRAW = F16 ? F16_OFF_BRAW : (RECT ? RECT_OFF_BRAW : hk::OFF_BRAW);
+  constexpr int OFF_BLO = F16 ? F16_OFF_BLO : hk::OFF_BLO;
   constexpr int EPI_WARP0 = F16 ? 12 : 8;
   // Register budget per warpgroup (regs per thread; the launch allocates 128 x 512 resp. 96 x 640):
   //   3xTF32:  72 + 104 + 168 + 168 = 512        3xFP16:  40 + 72 + 72 + 144 + 144 = 472 <= 480
-  constexpr int REGS_WG0 = F16 ? 56 : 72, REGS_CONV = F16 ? 64 : 104, REGS_EPI = F16 ? 144 : 168;
+  constexpr int REGS_WG0 = F16 ? 48 : 72, REGS_CONV = F16 ? 72 : 104, REGS_EPI = F16 ? 144 : 168;
   using ts::HalfRing;
   using ts::lo_bits;
 
@@ -162,7 +184,7 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
       ptx::mbar_init(empty_bar(s), 2);
     }
     for (int j = 0; j < A_SLOTS; ++j) {
-      ptx::mbar_init(ready_bar(j), 2 * NUM_CONV * (F16 ? 2 : 1));
+      ptx::mbar_init(ready_bar(j), 2 * NUM_CONV);
       ptx::mbar_init(aempty_bar(j), 2);
     }
     for (int h = 0; h < 2; ++h)
@@ -252,7 +274,9 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
             const uint32_t d = tmem_base + (uint32_t)r * ACC_COLS;
             if (kt == c0) ptx::mbar_wait(tempty_bar(1 - h, r), ring.drained_parity(h));
             const uint64_t b_hi = ptx::umma_desc_k_sw128(sbase + OFF_BHI + h * (OPERAND_BYTES / 2));
-            const uint64_t b_lo = ptx::umma_desc_k_sw128(sbase + OFF_BLO + h * (OPERAND_BYTES / 2));
+            // (fp16 x 3: the lo halves are bytes [64, 128) of the same rows -- 4 descriptor units further)
+            const uint64_t b_lo = F16 ? b_hi + (uint64_t)(F16_OFF_BLO >> 4)
+                                      : ptx::umma_desc_k_sw128(sbase + OFF_BLO + h * (OPERAND_BYTES / 2));
             if constexpr (F16) {
               // One A slot = one k-tile (32 frames = two K = 16 steps: hi columns [8s, 8s + 8), lo columns
               // [16 + 8s, ...); 32 bytes of a B row per step).  Frames outside the call's row range are
@@ -415,15 +439,18 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
       }
     }
   } else if (F16 && wg <= 2) {
-    // ===================== fp16 x 3 converters: warpgroup 1 builds A (TMEM), warpgroup 2 builds B (smem) ====
+    // ===================== fp16 x 3 converters: two warpgroups, k-tiles alternate between them ==========
     // Every raw word is (hi | lo << 16) of one sample (split_rows_kernel); converting means packing
-    // two frames per 32-bit register, one k-tile (32 frames of this thread's row) per step.
-    //   A: hi halves = TMEM columns [0, 16) of the slot, lo halves = columns [16, 32);
+    // two frames per 32-bit register.  A thread owns row `row` of the A tile (= its TMEM lane) and row
+    // `row` of the B tile, like the 3xTF32 converter, but a k-tile is only 768 tensor-pipe clocks now
+    // and one warp's chain (waits, 64 loads, 64 packs, stores, fences, arrive: ~1000 clocks, latency
+    // bound) does not fit -- so warpgroup 1 converts the even k-tiles and warpgroup 2 the odd ones.
+    //   A: hi halves of frames [16h, 16h + 16) = TMEM columns [8h, 8h + 8) of the slot, lo halves =
+    //      columns [16 + 8h, ...);
     //   B: frame t of a row sits in 16-byte chunk (t/8) ^ (row%8) of the hi tile and of the lo tile.
-    // Two warpgroups, because a k-tile is only 768 tensor-pipe clocks now: each group's chain (wait,
-    // 32 loads, pack, store, fence, arrive) has to fit into that with room to spare.
     ptx::setmaxnreg_dec<REGS_CONV>();
-    const bool is_a = (wg == 1);
+    static_assert(A_SLOTS == 4, "slot / parity below are bit fields of the k-tile count");
+    const int my_par = wg - 1;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int kk = lane >> 3, cc = lane & 7;
@@ -433,89 +460,101 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
     const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + A_COL0;
     WorkIter wi(P, worker, n_workers);
     WorkItem it;
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t kcount = 0;
+    uint32_t kcount = 0;                                 // k-tiles of all earlier work items
     while (wi.next(P, it)) {
-      const int4 g = is_a ? __ldg(&(RECT ? P.rgs_a : P.rgs)[(it.tm * 2 + (int)rank) * RG_PER_CTA + quad])
-                          : __ldg(&P.rgs[(it.tn * 2 + (int)rank) * RG_PER_CTA + quad]);
-      const bool rect_a = RECT && is_a;                  // lane = channel of a 32-channel, one-lag row group
-      const uint32_t rd = (is_a ? OFF_ARAW : OFF_BRAW) + (uint32_t)g.w +
-                          (rect_a ? (uint32_t)lane * 4u : (uint32_t)(kk * BOX_CH + cc) * 4u);
-      const uint32_t frame_bytes = rect_a ? ABOX_CH * 4 : BOX_CH * 4;
-      const int d = g.z + (rect_a ? 0 : kk);             // lag shift k - pre of this thread's row
-      const int q = g.x & 1;
-      int4 kn0 = __ldg(&P.ktiles[2 * it.kt_begin]);
-      int4 kn1 = __ldg(&P.ktiles[2 * it.kt_begin + 1]);
-      for (long long kt = it.kt_begin; kt < it.kt_end; ++kt, ++kcount) {
-        const int4 k0 = kn0, k1 = kn1;
-        if (kt + 1 < it.kt_end) {
-          kn0 = __ldg(&P.ktiles[2 * (kt + 1)]);
-          kn1 = __ldg(&P.ktiles[2 * (kt + 1) + 1]);
-        }
-        const uint32_t slot = kcount & (A_SLOTS - 1);
+      const int4 ga = __ldg(&(RECT ? P.rgs_a : P.rgs)[(it.tm * 2 + (int)rank) * RG_PER_CTA + quad]);
+      const int4 gb = __ldg(&P.rgs[(it.tn * 2 + (int)rank) * RG_PER_CTA + quad]);
+      const uint32_t a_rd = OFF_ARAW + (uint32_t)ga.w + (RECT ? (uint32_t)lane * 4u : (uint32_t)(kk * BOX_CH + cc) * 4u);
+      const uint32_t b_rd = OFF_BRAW + (uint32_t)gb.w + (uint32_t)(kk * BOX_CH + cc) * 4u;
+      constexpr uint32_t A_FRAME_BYTES = RECT ? ABOX_CH * 4 : BOX_CH * 4;
+      const int a_d = ga.z + (RECT ? 0 : kk), b_d = gb.z + kk;        // lag shift k - pre of this thread's rows
+      const int a_q = ga.x & 1, b_q = gb.x & 1;
+      const uint32_t first = (uint32_t)((my_par - (int)kcount) & 1);  // offset of this group's first k-tile
+      long long kt = it.kt_begin + first;
+      uint32_t g = kcount + first;                                    // running k-tile count of kt
+      kcount += (uint32_t)(it.kt_end - it.kt_begin);
+      int kz_next = (kt < it.kt_end) ? __ldg(&P.ktiles[2 * kt].z) : 0;
+      uint32_t stage = g % (uint32_t)STAGES, phase = (g / (uint32_t)STAGES) & 1u;   // raw ring position of kt
+      for (; kt < it.kt_end; kt += 2, g += 2) {
+        const int kz = kz_next;                           // begin | end << 8 | edge << 16 of this k-tile
+        if (kt + 2 < it.kt_end) kz_next = __ldg(&P.ktiles[2 * (kt + 2)].z);
+        const uint32_t slot = g & 3u, par = (g >> 2) & 1u;             // A slot and its parity
         const uint32_t sbase = smem_base + stage * STAGE_BYTES;
-        const bool special = k0.z != (BK << 8);           // anything but a whole k-tile in the middle of a trial
-        const int begin = k0.z & 0xff, end = (k0.z >> 8) & 0xff;
-        const bool edge = (k0.z >> 16) != 0;
-        const bool partial = is_a && (begin > 0 || end < BK);        // the row range is cut on the A side only
-        const int lo_e = k0.w - d, hi_e = (q ? k1.y : k1.x) - d;     // inside the trial iff lo_e <= e < hi_e
-        const uint32_t bhi = sbase + OFF_BHI + row_off, blo = sbase + OFF_BLO + row_off;
-        ptx::mbar_wait_lean(full_bar(stage), phase);
-        if (is_a) {
-          ptx::mbar_wait_lean(aempty_bar(slot), ((kcount >> 2) & 1u) ^ 1u);
-          ptx::tc_fence_after();
+        const bool special = kz != (BK << 8);             // anything but a whole k-tile in the middle of a trial
+        int begin = 0, end = BK, a_lo_e = 0, a_hi_e = BK, b_lo_e = 0, b_hi_e = BK;
+        bool edge = false, partial = false;
+        if (special) {
+          begin = kz & 0xff;
+          end = (kz >> 8) & 0xff;
+          edge = (kz >> 16) != 0;
+          partial = begin > 0 || end < BK;                // the row range is cut on the A side only
+          const int neg_t0 = __ldg(&P.ktiles[2 * kt].w);  // inside the trial iff lo_e <= e < hi_e
+          const int2 len_t0 = *reinterpret_cast<const int2*>(&P.ktiles[2 * kt + 1]);
+          a_lo_e = neg_t0 - a_d;
+          b_lo_e = neg_t0 - b_d;
+          a_hi_e = (a_q ? len_t0.y : len_t0.x) - a_d;
+          b_hi_e = (b_q ? len_t0.y : len_t0.x) - b_d;
         }
+        const uint32_t bhi = sbase + OFF_BHI + row_off;
+        ptx::mbar_wait_lean(full_bar(stage), phase);
+        ptx::mbar_wait_lean(aempty_bar(slot), par ^ 1u);
+        ptx::tc_fence_after();
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {                  // 16 frames at a time keeps the register footprint at ~32
-          uint32_t w[16], hi2[8], lo2[8];
+        for (int hh = 0; hh < 2; ++hh) {                  // 16 frames at a time keeps the register footprint low
+          uint32_t wa[16], wb[16], p2[8], q2[8];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) w[e] = lds32(sbase + rd + (uint32_t)(hh * 16 + e) * frame_bytes);
+          for (int e = 0; e < 16; ++e) {
+            wa[e] = lds32(sbase + a_rd + (uint32_t)(hh * 16 + e) * A_FRAME_BYTES);
+            wb[e] = lds32(sbase + b_rd + (uint32_t)((hh * 16 + e) * BOX_CH * 4));
+          }
           if (special) {
             if (edge) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (hh * 16 + e < lo_e || hh * 16 + e >= hi_e) w[e] = 0u;
+              for (int e = 0; e < 16; ++e) {
+                const int t = hh * 16 + e;
+                if (t < a_lo_e || t >= a_hi_e) wa[e] = 0u;
+                if (t < b_lo_e || t >= b_hi_e) wb[e] = 0u;
+              }
             }
             if (partial) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (hh * 16 + e < begin || hh * 16 + e >= end) w[e] = 0u;
+              for (int e = 0; e < 16; ++e) {
+                const int t = hh * 16 + e;
+                if (t < begin || t >= end) wa[e] = 0u;
+              }
             }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            hi2[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x5410);     // hi halves of frames 2j, 2j + 1
-            lo2[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x7632);     // lo halves
+            p2[j] = __byte_perm(wa[2 * j], wa[2 * j + 1], 0x5410);       // hi halves of frames 2j, 2j + 1
+            q2[j] = __byte_perm(wa[2 * j], wa[2 * j + 1], 0x7632);       // lo halves
           }
-          if (is_a) {
-            ptx::tmem_st8(tlane + slot * A_SLOT_COLS + 8 * hh, hi2);
-            ptx::tmem_st8(tlane + slot * A_SLOT_COLS + 16 + 8 * hh, lo2);
-          } else {
+          ptx::tmem_st8(tlane + slot * A_SLOT_COLS + 8 * hh, p2);
+          ptx::tmem_st8(tlane + slot * A_SLOT_COLS + 16 + 8 * hh, q2);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const uint32_t off = ((uint32_t)(hh * 2 + i) ^ sw) << 4;
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bhi + off), "r"(hi2[4 * i]),
-                           "r"(hi2[4 * i + 1]), "r"(hi2[4 * i + 2]), "r"(hi2[4 * i + 3])
-                           : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blo + off), "r"(lo2[4 * i]),
-                           "r"(lo2[4 * i + 1]), "r"(lo2[4 * i + 2]), "r"(lo2[4 * i + 3])
-                           : "memory");
-            }
+          for (int j = 0; j < 8; ++j) {
+            p2[j] = __byte_perm(wb[2 * j], wb[2 * j + 1], 0x5410);
+            q2[j] = __byte_perm(wb[2 * j], wb[2 * j + 1], 0x7632);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint32_t off = ((uint32_t)(hh * 2 + i) ^ sw) << 4;
+            const uint32_t off_lo = ((uint32_t)(4 + hh * 2 + i) ^ sw) << 4;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bhi + off), "r"(p2[4 * i]),
+                         "r"(p2[4 * i + 1]), "r"(p2[4 * i + 2]), "r"(p2[4 * i + 3])
+                         : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bhi + off_lo), "r"(q2[4 * i]),
+                         "r"(q2[4 * i + 1]), "r"(q2[4 * i + 2]), "r"(q2[4 * i + 3])
+                         : "memory");
           }
         }
-        if (is_a) {
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-        } else {
-          ptx::fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor-core proxy
-          // The ready barrier of a slot counts A and B arrivals of ONE use: B must not arrive for the
-          // slot's next use before the previous one is consumed.
-          ptx::mbar_wait_lean(aempty_bar(slot), ((kcount >> 2) & 1u) ^ 1u);
-        }
+        ptx::fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor-core proxy
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_remote(ready_leader0 + 8u * slot);
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        stage += 2;
+        if (stage >= (uint32_t)STAGES) { stage -= STAGES; phase ^= 1u; }
       }
     }
   } else {

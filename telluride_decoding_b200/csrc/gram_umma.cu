@@ -882,13 +882,17 @@ int make_tmap_raw(CUtensorMap* m, const float* base, int64_t n_rows, int C, int6
   return TD_OK;
 }
 
+// Which flavour of the halo kernel a call gets: fp16 x 3 (method 6) unless 3xTF32 (method 4) is asked
+// for by number.  Same split arithmetic, 1.4 - 1.5x the frames per joule on a power-capped B200.
+inline bool halo_is_f16(const td_gram_options* opt) { return !opt || opt->method != 4; }
+
 // batched: one Gram per segment, G [n_seg][Dz][ldg]; every segment must span the same number of
 // k-tiles (then a superchunk is exactly one segment and the epilogue picks the output by superchunk).
 int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, const int64_t* seg_keep,
              int n_seg, float* G, int64_t ldg, const td_gram_options* opt, void* workspace,
              size_t workspace_bytes, cudaStream_t st, bool batched = false) {
   HaloPlan pl;
-  const bool f16 = opt && opt->method == 6;
+  const bool f16 = halo_is_f16(opt);
   int rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &pl, f16);
   if (rc) return rc;
   int64_t kt_per_seg = 0;
@@ -1017,7 +1021,10 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
     P.ldg = ldg;
     P.ntri = pl.ntri;
     P.NK = pl.NK;
-    const int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 128;
+    // TMEM accumulates chunk_rows frames in fp32 before the epilogue folds them into its registers: the
+    // rounding error grows with the chunk (fp16 x 3: 7e-7 / 1.4e-6 / 2.9e-6 relative Frobenius error at
+    // 128 / 256 / 512 rows, 3xTF32: 2.3e-6 at 128), the drain cost shrinks with it.
+    const int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : (f16 ? 256 : 128);
     P.chunk_kt = std::max(1, chunk_rows / BK);
     // Superchunk: the raw frames all tiles sweep together; sized to stay L2 resident (~48 MB of the
     // 126 MB: measured on the cfg 4 width, 24 / 48 / 96 / 192 MB -> 1077 / 1072 / 1088 / 1103 ms).
@@ -1049,11 +1056,12 @@ int run_halo(const td_stream* streams, int n_streams, const int64_t* seg_first, 
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
     auto kernel = f16 ? hk::lagged_gram_halo_kernel<false, true> : hk::lagged_gram_halo_kernel<false, false>;
-    TD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::SMEM_BYTES));
+    const size_t smem_bytes = f16 ? hk::F16_SMEM_BYTES : hk::SMEM_BYTES;
+    TD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * 2);
     cfg.blockDim = dim3(f16 ? hk::NUM_THREADS_F16 : hk::NUM_THREADS);
-    cfg.dynamicSmemBytes = hk::SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1144,8 +1152,8 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
                  int n_seg, float* G, int64_t ldg, const td_gram_options* opt, void* workspace,
                  size_t workspace_bytes, cudaStream_t st, size_t* bytes_only, bool batched = false);
 
-// Does this call run the halo kernel (method 4)?  Explicitly, or automatically (method 0) when the
-// design is wide enough for CTA pairs (>= 512 tile rows) and DEFAULT_PAIR_METHOD says so.
+// Does this call run the halo kernel (methods 4 / 6)?  Explicitly, or automatically (method 0: the
+// fp16 x 3 flavour, see halo_is_f16) when the design is wide enough for CTA pairs (>= 512 tile rows).
 constexpr int DEFAULT_PAIR_METHOD = 4;
 int use_halo(const td_stream* streams, int n_streams, const td_gram_options* opt, bool* halo) {
   const int m = opt ? opt->method : 0;
@@ -1385,7 +1393,7 @@ extern "C" int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_st
   if (rc) return rc;
   if (halo) {
     HaloPlan hp;
-    rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &hp, opt && opt->method == 6);
+    rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &hp, halo_is_f16(opt));
     if (rc) return rc;
     *bytes = hp.total;
     return TD_OK;
@@ -1675,7 +1683,7 @@ extern "C" int td_lagged_gram_batched_f32(const td_stream* streams, int n_stream
   if (o.method == 5)
     return run_toeplitz(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, &o, workspace, workspace_bytes,
                         (cudaStream_t)stream, nullptr, /*batched=*/true);
-  if (o.method != 6) o.method = 4;
+  if (o.method != 4) o.method = 6;
   o.cta_group = 2;
   return run_halo(streams, n_streams, seg_first, seg_keep, n_seg, G, ldg, &o, workspace, workspace_bytes,
                   (cudaStream_t)stream, /*batched=*/true);
@@ -1689,7 +1697,7 @@ extern "C" int td_lagged_gram_batched_workspace_bytes(const td_stream* streams, 
     return run_toeplitz(streams, n_streams, seg_first, seg_keep, n_seg, nullptr, 0, opt, nullptr, 0, nullptr, bytes,
                         /*batched=*/true);
   td_gram_options o = opt ? *opt : td_gram_options{};
-  if (o.method != 6) o.method = 4;
+  if (o.method != 4) o.method = 6;
   o.cta_group = 2;
   return td_lagged_gram_workspace_bytes(streams, n_streams, seg_first, seg_keep, n_seg, &o, bytes);
 }

@@ -119,8 +119,8 @@ def lagged_gram_per_segment(streams, seg_keep, options=None, workspace=None, seg
   carr = _streams_array(streams)
   keep = _lib.i64_array(seg_keep)
   first = _lib.i64_array(seg_first) if seg_first is not None else None
-  # method 5 (block-Toeplitz structure, one stream) or 6 (fp16 x 3) if asked for, else the dense kernel (method 4)
-  method = 5 if (options.method == 5 and len(streams) == 1) else (6 if options.method == 6 else 4)
+  # method 5 (block-Toeplitz structure, one stream) or 4 (3xTF32) if asked for, else the default dense kernel (6: fp16 x 3)
+  method = 5 if (options.method == 5 and len(streams) == 1) else (4 if options.method == 4 else 6)
   opt4 = _lib.TdGramOptions(method, 2, options.chunk_rows, 0, options.max_ctas)
   opt4.reserved[0] = options.reserved[0]
   nbytes = ctypes.c_size_t(0)

@@ -34,7 +34,7 @@ for case in range(n_cases):
     x2 = torch.as_tensor(rng.randn(sum(lens), c2).astype(np.float32), device='cuda')
     streams.append(ops.Stream(x2, p2, l2 - 1 - p2, starts, lens))
   want = ops.lagged_gram(streams, keep, options=ops.gram_options(method=1), seg_first=first)
-  for method in ((4,) if two else (4, 5)):
+  for method in ((4, 6) if two else (4, 5, 6)):
     kw = {}
     if rng.rand() < 0.3:
       kw = dict(chunk_rows=int(rng.choice([32, 64, 128])), superchunk_rows=int(rng.choice([512, 1024, 4096])))
@@ -50,7 +50,7 @@ for case in range(n_cases):
     xb = torch.as_tensor((rng.randn(n_seg * n, c) + 0.1).astype(np.float32), device='cuda')
     sb = ops.Stream(xb, pre, post, [i * n for i in range(n_seg)], [n] * n_seg)
     ref = torch.stack([ops.lagged_gram([ops.Stream(xb, pre, post, [i * n], [n])], [n], options=ops.gram_options(method=1)) for i in range(n_seg)])
-    for method in (0, 5):
+    for method in (0, 4, 5):
       got = ops.lagged_gram_per_segment([sb], [n] * n_seg, options=ops.gram_options(method=method))
       e = rel(got, ref)
       if not (e < 1e-5):

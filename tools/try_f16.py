@@ -18,7 +18,7 @@ def lagged(x, pre, post):
     out[lo:hi, k * c:(k + 1) * c] = x[lo + sh:hi + sh]
   return out
 
-def check(lens, c, pre, post, methods=(4, 6), reps=3):
+def check(lens, c, pre, post, methods=(4, 6), reps=3, chunk_rows=0):
   rng = np.random.RandomState(1)
   x = (rng.randn(sum(lens), c) + 0.1).astype(np.float32)
   xd = torch.as_tensor(x, device='cuda')
@@ -29,9 +29,9 @@ def check(lens, c, pre, post, methods=(4, 6), reps=3):
   for m in methods:
     errs = []
     for _ in range(reps):
-      got = ops.lagged_gram([s], lens, options=ops.gram_options(method=m)).cpu().numpy()
+      got = ops.lagged_gram([s], lens, options=ops.gram_options(method=m, chunk_rows=chunk_rows)).cpu().numpy()
       errs.append(np.linalg.norm(got - want) / np.linalg.norm(want))
-    print('lens %s c %d lags %d method %d: rel fro %s' % (lens, c, pre + post + 1, m, ' '.join('%.2e' % e for e in errs)), flush=True)
+    print('[chunk_rows %d] ' % chunk_rows + 'lens %s c %d lags %d method %d: rel fro %s' % (lens, c, pre + post + 1, m, ' '.join('%.2e' % e for e in errs)), flush=True)
 
 def timeit(name, n_trials, frames, c, lags, methods=(4, 6), reps=3, chunk_rows=0):
   gen = torch.Generator(device='cuda'); gen.manual_seed(1)
@@ -60,6 +60,40 @@ print('library', _lib.LIB_PATH)
 if what in ('all', 'check'):
   check([2000, 1777], 10, 3, 56)
   check([3000, 2500], 64, 0, 31)
+if what == 'var':
+  check([2000, 1777], 10, 3, 56, methods=(6,), reps=1)
+  for cr in (256, 512):
+    check([30000, 25000], 64, 0, 31, methods=(6,), reps=1, chunk_rows=cr)
+  for cr in (128, 256):
+    timeit('cfg2', 60, 7680, 64, 32, reps=4, chunk_rows=cr, methods=(6,))
+    timeit('cfg4 slice', 3, 100000, 306, 100, reps=1, chunk_rows=cr, methods=(6,))
+if what == 'power':
+  import threading, time, pynvml
+  pynvml.nvmlInit()
+  h = pynvml.nvmlDeviceGetHandleByIndex(0)
+  gen = torch.Generator(device='cuda'); gen.manual_seed(1)
+  x = torch.randn((300000, 306), generator=gen, device='cuda')
+  st = ops.Stream(x, 0, 99, [0, 100000, 200000], [100000] * 3)
+  G = torch.empty((30600, 30600), device='cuda')
+  for m, cr in ((4, 0), (6, 0), (6, 256)):
+    opt = ops.gram_options(method=m, cta_group=2, timed=True, chunk_rows=cr)
+    ops.lagged_gram([st], [100000] * 3, out=G, options=opt); torch.cuda.synchronize()
+    samples = []; stop = [False]
+    def sampler():
+      while not stop[0]:
+        samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                        pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+        time.sleep(0.02)
+    th = threading.Thread(target=sampler); th.start()
+    ts = []
+    for _ in range(8):
+      ops.lagged_gram([st], [100000] * 3, out=G, options=opt); torch.cuda.synchronize(); ts.append(ops.last_gram_kernel_ms())
+    stop[0] = True; th.join()
+    clk = sorted(c for c, _, _ in samples); pw = sorted(p for _, p, _ in samples)
+    reasons = 0
+    for _, _, r in samples: reasons |= r
+    print('method %d chunk %d: kernel ms %s | SM clock median %d (min %d max %d) MHz, power median %.0f W (max %.0f), throttle bits 0x%x, %d samples' %
+          (m, cr, ' '.join('%.0f' % t for t in ts), clk[len(clk) // 2], clk[0], clk[-1], pw[len(pw) // 2], pw[-1], reasons, len(samples)), flush=True)
 if what == 'prof':
   timeit('cfg4 slice', 3, 100000, 306, 100, reps=1, methods=(6,))
 if what == 'prof2':
@@ -72,3 +106,4 @@ if what == 'chunks':
 if what in ('all', 'time'):
   timeit('cfg2', 60, 7680, 64, 32, reps=4)
   timeit('cfg4 slice', 3, 100000, 306, 100, reps=2)
+  timeit('cfg4 slice', 3, 100000, 306, 100, reps=2, chunk_rows=256, methods=(6,))
