@@ -6,7 +6,8 @@ synthetic 306-channel MEG, 1 h at 1 kHz (36 trials x 100 000 frames), 100 lags (
 D = 30 600), one envelope target, minibatch 1000 (no frame is dropped).
 
 A step = one pass of the hot path over the WHOLE recording through the public API
-(`sharding.sharded_regression_stats`): the lagged Gram X'X on tcgen05 tensor cores in 3xTF32, the
+(`sharding.sharded_regression_stats`): the lagged Gram X'X on tcgen05 tensor cores (split operands,
+fp16 x 3 by default, 3xTF32 with --gram-method 4: fp32-equivalent products either way), the
 thin products X'[y|1] in float64 and -- with N > 1 GPUs -- ONE NCCL allreduce of the partial
 statistics.  Strong scaling: the SAME recording is cut into N contiguous frame ranges
 (`sharding.shard_rows`, cuts on 32-frame tiles in the middle of trials, lag halo read from the same
@@ -296,7 +297,8 @@ class ClockSampler(object):
 # 308 GB written.  Algorithmic bytes are 8.15 GB (raw 4.41 + G 3.75): G (3.75 GB) fits no on-chip memory,
 # so every (tile, superchunk) partial goes through L2 into HBM, and ~11 % of the raw boxes miss L2.
 # 137 GB/s, 2 % of the HBM bandwidth of a tensor-bound kernel.
-GRAM_DRAM_TRAFFIC_BYTES_CFG4 = 1788808138547
+# fp16 x 3 (the default flavour): 1821 GB read + 329 GB written per launch, same reading (249 GB/s).
+GRAM_DRAM_TRAFFIC_BYTES_CFG4 = {6: 2149602696704, 4: 1788808138547}      # by Gram method (6 = fp16 x 3, 4 = 3xTF32)
 
 
 def load_peaks():
@@ -376,14 +378,16 @@ def leg_cfg2(dev, peaks, flush, with_cpu):
   d = CFG2['channels'] * (CFG2['pre'] + 1 + CFG2['post'])
   f_alg = float(frames) * d * (d + 1)
   kernel_ms = float(np.mean(gram_ms))
-  peak = peaks['bf16'] / 6.0
+  peak = peaks['bf16'] / 3.0                      # fp16 x 3: three kind::f16 MMAs per product
   leg = dict(workload=CFG2['workload'], ms_per_step=step_ms, frames_per_s=frames / (step_ms * 1e-3),
              e2e_ms_per_step=e2e_ms, e2e_frames_per_s=frames / (e2e_ms * 1e-3),
              h2d_bytes_per_step=int(x_pin.numel() * 4 + y_pin.numel() * 4),
              d2h_bytes_per_step=int(w_host.numel() * 4), gram_kernel_ms=kernel_ms,
              roofline=dict(bound='tensor', achieved=f_alg / (kernel_ms * 1e-3) / 1e12, peak=peak,
                            unit='TFLOP/s', frac=f_alg / (kernel_ms * 1e-3) / 1e12 / peak,
-                           peak_source=peaks['source'] + ' bf16_tflops (burst: a ms-long kernel) / 2 / 3'),
+                           frac_of_3xtf32_peak=f_alg / (kernel_ms * 1e-3) / 1e12 / (peaks['bf16'] / 6.0),
+                           peak_source=peaks['source'] + ' bf16_tflops (burst: a ms-long kernel; = the fp16 rate) / 3 '
+                                       '(fp16 x 3 split); frac_of_3xtf32_peak is against bf16_tflops / 2 / 3'),
              lambdas='logspace(-6,3,20)', l2='256 MB write between timed steps')
 
   # evaluate / predict throughput: the only numbers the reference publishes
@@ -736,19 +740,34 @@ def main():
   kernel_ms = float(np.mean(gram_ms))
   achieved = f_alg / (kernel_ms * 1e-3) / 1e12
   long_step = kernel_ms > 500.0
-  peak = (peaks['bf16_sustained'] if long_step else peaks['bf16']) / 6.0
+  # Three MMAs per product either way: kind::f16 (the bf16 / fp16 dense rate) for the default fp16 x 3
+  # flavour, kind::tf32 (half that rate) for --gram-method 4.
+  f16 = args.gram_method in (0, 6)
+  mma_div = 3.0 if f16 else 6.0
+  peak = (peaks['bf16_sustained'] if long_step else peaks['bf16']) / mma_div
+  traffic = None
+  if world == 1 and args.minutes == 60.0:
+    traffic = GRAM_DRAM_TRAFFIC_BYTES_CFG4.get(6 if f16 else (4 if args.gram_method == 4 else -1))
   roofline = dict(
       bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
-      traffic=GRAM_DRAM_TRAFFIC_BYTES_CFG4 if (world == 1 and args.minutes == 60.0 and args.gram_method in (0, 4)) else None,
+      traffic=traffic,
       traffic_source='profiles/r02_ncu_launches_summary.txt (ncu dram__bytes_read/write.sum of this command, per launch); '
                      'algorithmic bytes per launch %.2f GB' % ((float(rows0) * c * 4 + float(d) * d * 4) / 1e9),
-      kernel='hk::lagged_gram_halo_kernel' if args.gram_method in (0, 4) else 'ts::lagged_gram_ts_kernel', flops_per_launch=f_alg,
+      kernel=('hk::lagged_gram_halo_kernel<false, true> (fp16 x 3)' if f16 else
+              'hk::lagged_gram_halo_kernel<false, false> (3xTF32)' if args.gram_method == 4 else 'ts::lagged_gram_ts_kernel'),
+      flops_per_launch=f_alg,
       frames_per_launch=rows0, kernel_ms=kernel_ms, kernel_ms_max_over_ranks=gram_kernel_ms_max,
-      peak_source='%s bf16_tflops%s / 2 (tf32 rate) / 3 (3xTF32): the %s figure, the kernel runs for '
+      peak_source='%s bf16_tflops%s%s / 3 (three MMAs per product): the %s figure, the kernel runs for '
                   '%.2f s' % (peaks['source'], '_sustained' if long_step else '',
+                              ' (= the fp16 rate)' if f16 else ' / 2 (tf32 rate)',
                               'sustained' if long_step else 'burst', kernel_ms * 1e-3),
-      frac_of_burst_peak=achieved / (peaks['bf16'] / 6.0),
-      frac_of_sustained_peak=achieved / (peaks['bf16_sustained'] / 6.0),
+      frac_of_burst_peak=achieved / (peaks['bf16'] / mma_div),
+      frac_of_sustained_peak=achieved / (peaks['bf16_sustained'] / mma_div),
+      # BASELINE.json's north star quotes the target against the 3xTF32 peak (bf16 / 2 / 3):
+      frac_of_3xtf32_burst_peak=achieved / (peaks['bf16'] / 6.0),
+      frac_of_3xtf32_sustained_peak=achieved / (peaks['bf16_sustained'] / 6.0),
+      limiter='board power: the kernel runs at the 1000 W cap (sw_power_cap, ~1.5 GHz of 1.965) in both flavours; '
+              'fp16 x 3 delivers ~1.45x the split-precision flops per joule of 3xTF32 (profiles/r02_gram_fp16x3.md)',
       share_of_step=kernel_ms / ms_per_step)
 
   # ---- parity of the bench's own numbers against the CPU oracle (untimed) + cpu_baseline ------------
@@ -816,8 +835,8 @@ def main():
       structured = dict(error=repr(exc)[:300])
   stats_gram_check = None
 
-  # stage, gram, symmetrize, thin, thin-reduce (+ memsets / library allreduce, not counted)
-  n_launch = 5
+  # absmax, split, row scales, gram, symmetrize, thin, thin-reduce (+ memsets / library allreduce, not counted)
+  n_launch = 7 if f16 else 5
   legs = {}
   want = ['cfg2', 'wcorr', 'cfg3', 'cfg5'] if args.legs == 'all' else \
          ([] if args.legs == 'none' else args.legs.split(','))
@@ -842,7 +861,8 @@ def main():
   line = dict(
       metric=METRIC, value=frames / (ms_per_step * 1e-3), unit='frames/s', n_gpus=world,
       steps=args.steps, warmup=warmup, ms_per_step=ms_per_step, higher_is_better=True,
-      scaling='strong', vs_baseline=None, dtype='tf32x3 (fp32-equivalent) Gram, f64 thin sums',
+      scaling='strong', vs_baseline=None,
+      dtype='%s (fp32-equivalent) Gram, f64 thin sums' % ('fp16x3 split' if f16 else 'tf32x3'),
       data='synthetic',
       config=dict(cfg, parallelism=par, D=d,
                   l2='inputs (%.1f GB of raw frames per rank) are far larger than the 126 MB L2; '

@@ -513,13 +513,14 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, int64_t ld, int C
 // ---- fp16 x 3 flavour of the halo kernel: per-channel scale and the pre-split copy ----------------
 // Largest |sample| per channel over rows [row0, row0 + n_rows) (bit pattern of a non-negative float:
 // unsigned order = numeric order; a NaN ends up on top and switches the scaling off for that channel).
-// block (32 channels, 8 row lanes), grid (row slabs, channel blocks).
+// block (32 channels, 8 row lanes); 1-D grid of (row slab, channel block) with the channel block fastest,
+// so that the blocks sharing a slab's sectors run back to back (rows are rarely 128-byte aligned).
 constexpr int SPLIT_ROWS_PER_BLOCK = 256;
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ src, int64_t ld, int C, int64_t row0,
-                                                     int64_t n_rows, unsigned* __restrict__ amax_bits) {
+                                                     int64_t n_rows, unsigned* __restrict__ amax_bits, int n_cblocks) {
   __shared__ unsigned red[8][32];
-  const int c = blockIdx.y * 32 + threadIdx.x;
-  const int64_t r0 = (int64_t)blockIdx.x * SPLIT_ROWS_PER_BLOCK;
+  const int c = (int)(blockIdx.x % n_cblocks) * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)(blockIdx.x / n_cblocks) * SPLIT_ROWS_PER_BLOCK;
   const int64_t r1 = min(r0 + SPLIT_ROWS_PER_BLOCK, n_rows);
   unsigned m = 0;
   if (c < C)
@@ -548,10 +549,10 @@ __device__ __forceinline__ int scale_exponent(unsigned amax_bits) {
 // channels in [C, ldp) are zero.  Same thread layout as absmax_kernel.
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ src, int64_t ld, int C, int64_t row0,
                                                          int64_t n_rows, const unsigned* __restrict__ amax_bits,
-                                                         uint32_t* __restrict__ dst, int ldp) {
-  const int c = blockIdx.y * 32 + threadIdx.x;
+                                                         uint32_t* __restrict__ dst, int ldp, int n_cblocks) {
+  const int c = (int)(blockIdx.x % n_cblocks) * 32 + threadIdx.x;
   if (c >= ldp) return;
-  const int64_t r0 = (int64_t)blockIdx.x * SPLIT_ROWS_PER_BLOCK;
+  const int64_t r0 = (int64_t)(blockIdx.x / n_cblocks) * SPLIT_ROWS_PER_BLOCK;
   const int64_t r1 = min(r0 + SPLIT_ROWS_PER_BLOCK, n_rows);
   const float scale = (c < C) ? ldexpf(1.0f, scale_exponent(amax_bits[c])) : 0.0f;
   for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
@@ -853,11 +854,14 @@ int stage_stream(const HaloPlan& pl, const td_stream* streams, int q, uint8_t* w
   unsigned* amax = reinterpret_cast<unsigned*>(ws + pl.off_amax[q]);
   TD_CHECK_CUDA(cudaMemsetAsync(amax, 0, pl.C[q] * sizeof(unsigned), st));
   const dim3 block(32, 8);
-  const dim3 grid((unsigned)ceil_div(pl.n_rows[q], SPLIT_ROWS_PER_BLOCK), (unsigned)ceil_div(pl.ld_eff[q], 32));
-  absmax_kernel<<<grid, block, 0, st>>>(streams[q].data_dev, streams[q].ld, pl.C[q], pl.row_lo[q], pl.n_rows[q], amax);
+  const int n_cblocks = (int)ceil_div(pl.ld_eff[q], 32);
+  const int64_t n_blocks = ceil_div(pl.n_rows[q], SPLIT_ROWS_PER_BLOCK) * n_cblocks;
+  TD_REQUIRE(n_blocks < (1LL << 31), "td_lagged_gram: recording too large for the split pass");
+  absmax_kernel<<<(unsigned)n_blocks, block, 0, st>>>(streams[q].data_dev, streams[q].ld, pl.C[q], pl.row_lo[q], pl.n_rows[q],
+                                                      amax, n_cblocks);
   TD_CHECK_CUDA(cudaGetLastError());
-  split_rows_kernel<<<grid, block, 0, st>>>(streams[q].data_dev, streams[q].ld, pl.C[q], pl.row_lo[q], pl.n_rows[q], amax,
-                                            reinterpret_cast<uint32_t*>(dst), (int)pl.ld_eff[q]);
+  split_rows_kernel<<<(unsigned)n_blocks, block, 0, st>>>(streams[q].data_dev, streams[q].ld, pl.C[q], pl.row_lo[q], pl.n_rows[q],
+                                                          amax, reinterpret_cast<uint32_t*>(dst), (int)pl.ld_eff[q], n_cblocks);
   TD_CHECK_CUDA(cudaGetLastError());
   return TD_OK;
 }

@@ -54,7 +54,12 @@ def test_workspace_plan_and_argument_errors():
   opt = _lib.TdGramOptions(0, 0, 0, 0, 0)
   assert lib.td_lagged_gram_workspace_bytes(arr, 1, None, keep, 60, ctypes.byref(opt),
                                             ctypes.byref(nbytes)) == 0
-  # default (method 4, operand built on chip): tables only, the recording is read where it lies
+  # default (method 6, fp16 x 3 operand built on chip): tables + the pre-split copy, one 32-bit word per sample
+  assert 460800 * 64 * 4 <= nbytes.value < 460800 * 64 * 4 + (1 << 20)
+  opt4 = _lib.TdGramOptions(4, 0, 0, 0, 0)
+  assert lib.td_lagged_gram_workspace_bytes(arr, 1, None, keep, 60, ctypes.byref(opt4),
+                                            ctypes.byref(nbytes)) == 0
+  # method 4 (3xTF32 on the raw array): tables only, the recording is read where it lies
   assert nbytes.value < (1 << 20)
   opt3 = _lib.TdGramOptions(3, 0, 0, 0, 0)
   assert lib.td_lagged_gram_workspace_bytes(arr, 1, None, keep, 60, ctypes.byref(opt3),
@@ -64,9 +69,10 @@ def test_workspace_plan_and_argument_errors():
   # 306 channels: rows of 1224 bytes are not 16-byte aligned -> ONE padded copy (308 floats per row)
   arr306 = (_lib.TdStream * 1)(_stream(306, 0, 99, [100000] * 2))
   keep306 = _lib.i64_array([100000] * 2)
-  assert lib.td_lagged_gram_workspace_bytes(arr306, 1, None, keep306, 2, ctypes.byref(opt),
-                                            ctypes.byref(nbytes)) == 0
-  assert 200000 * 308 * 4 <= nbytes.value < 200000 * 308 * 4 + (1 << 20)
+  for o in (opt, opt4):    # (the pre-split copy of method 6 has the same 308 words per row)
+    assert lib.td_lagged_gram_workspace_bytes(arr306, 1, None, keep306, 2, ctypes.byref(o),
+                                              ctypes.byref(nbytes)) == 0
+    assert 200000 * 308 * 4 <= nbytes.value < 200000 * 308 * 4 + (1 << 20)
   # three streams are rejected with a message
   rc = lib.td_lagged_gram_workspace_bytes(arr, 3, None, keep, 60, ctypes.byref(opt), ctypes.byref(nbytes))
   assert rc == -1 and b'n_streams' in lib.td_last_error()
