@@ -97,8 +97,8 @@ int td_shutdown(void);
  *      C(d)[c1,c2] = sum_t x[t-pre,c1] x[t-pre+d,c2] is contracted on the tensor cores (the method-4
  *      kernel in rectangular mode, L/2 times fewer MMAs), every other block follows along the lag
  *      diagonals from C(d) plus edge sums over the first / last k1 frames of each segment.  Same
- *      3xTF32 arithmetic and row semantics; the dense flavours stay the default and the reference
- *      point of the roofline.
+ *      split arithmetic (the fp16 x 3 flavour; reserved[1] = 1: 3xTF32) and row semantics; the dense
+ *      flavours stay the default and the reference point of the roofline.
  * method 1: fp32 CUDA-core kernel kept as an on-device cross-check.
  * Workspace: td_lagged_gram_workspace_bytes bytes of device memory.
  * ------------------------------------------------------------------------------------- */
@@ -108,7 +108,7 @@ typedef struct td_gram_options {
   int32_t chunk_rows;    /* TMEM flush period in frames (0 = default: 256 for method 6, else 128) */
   int32_t superchunk_rows; /* L2 working-set period in frames (0 = auto) */
   int32_t max_ctas;      /* 0 = all SMs */
-  int32_t reserved[3];   /* reserved[0] = 1: record CUDA events around the Gram kernel */
+  int32_t reserved[3];   /* reserved[0] = 1: record CUDA events around the Gram kernel; reserved[1] = 1: method 5 contracts in 3xTF32 */
 } td_gram_options;
 
 int td_lagged_gram_workspace_bytes(const td_stream* streams, int n_streams,

@@ -83,6 +83,12 @@ constexpr int F16_NUM_BARRIERS = 2 * F16_STAGES + 2 * A_SLOTS + 12;
 constexpr size_t F16_SMEM_BYTES = (size_t)F16_STAGES * F16_STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
 static_assert(8 * F16_NUM_BARRIERS + 8 <= 512, "barrier block too small");
 static_assert(F16_SMEM_BYTES <= 232448, "fp16 flavour exceeds the 227 KB of shared memory");
+// ... and its rectangular form (method 5): 16 KiB of B + 16 KiB of raw A boxes + 6 KiB of raw B boxes, four stages.
+constexpr int F16_RECT_STAGES = 4;
+constexpr int F16_RECT_OFF_BRAW = F16_OFF_ARAW + RECT_RAW_A_BYTES;
+constexpr int F16_RECT_STAGE_BYTES = OPERAND_BYTES + RECT_RAW_A_BYTES + RAW_BYTES;     // 38 KiB
+static_assert(F16_RECT_STAGE_BYTES % 1024 == 0, "stage must keep the 1024-byte alignment of the swizzled tiles");
+constexpr size_t F16_RECT_SMEM_BYTES = (size_t)F16_RECT_STAGES * F16_RECT_STAGE_BYTES + 1024 + 512;
 
 struct HaloParams {
   const int4* rgs;        // [Dpad / 32] {stream | issue << 1, first channel, lag shift k0 - pre, byte offset in the operand's raw region}
@@ -143,12 +149,11 @@ __global__ void __launch_bounds__(F16 ? NUM_THREADS_F16 : NUM_THREADS, 1)
 lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
                         const __grid_constant__ CUtensorMap tmap1, const HaloParams P) {
   constexpr uint32_t IDESC = F16 ? ptx::umma_idesc_f16(256, 128) : ptx::umma_idesc_tf32(256, 128);
-  static_assert(!(RECT && F16), "the rectangular flavour is 3xTF32 only");
-  constexpr int STAGES = F16 ? F16_STAGES : hk::STAGES;
-  constexpr int NUM_BARRIERS = F16 ? F16_NUM_BARRIERS : hk::NUM_BARRIERS;
-  constexpr int STAGE_BYTES = F16 ? F16_STAGE_BYTES : (RECT ? RECT_STAGE_BYTES : hk::STAGE_BYTES);
+  constexpr int STAGES = F16 ? (RECT ? F16_RECT_STAGES : F16_STAGES) : hk::STAGES;
+  constexpr int NUM_BARRIERS = 2 * STAGES + 2 * A_SLOTS + 12;
+  constexpr int STAGE_BYTES = F16 ? (RECT ? F16_RECT_STAGE_BYTES : F16_STAGE_BYTES) : (RECT ? RECT_STAGE_BYTES : hk::STAGE_BYTES);
   constexpr int OFF_ARAW = F16 ? F16_OFF_ARAW : hk::OFF_ARAW;
-  constexpr int OFF_BRAW = F16 ? F16_OFF_BRAW : (RECT ? RECT_OFF_BRAW : hk::OFF_BRAW);
+  constexpr int OFF_BRAW = F16 ? (RECT ? F16_RECT_OFF_BRAW : F16_OFF_BRAW) : (RECT ? RECT_OFF_BRAW : hk::OFF_BRAW);
   constexpr int OFF_BLO = F16 ? F16_OFF_BLO : hk::OFF_BLO;
   constexpr int EPI_WARP0 = F16 ? 12 : 8;
   // Register budget per warpgroup (regs per thread; the launch allocates 128 x 512 resp. 96 x 640):

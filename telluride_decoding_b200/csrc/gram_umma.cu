@@ -1190,7 +1190,10 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     return TD_ERR_UNSUPPORTED;
   }
   HaloPlan pl;
-  int rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &pl);
+  // The block row runs on the default dense flavour (fp16 x 3 on the pre-split copy) unless
+  // reserved[1] = 1 asks for 3xTF32 on the raw array.
+  const bool f16 = !(opt && opt->reserved[1] == 1);
+  int rc = make_halo_plan(streams, n_streams, seg_first, seg_keep, n_seg, &pl, f16);
   if (rc) return rc;
   const int C = pl.C[0], L = pl.L[0], pre = pl.pre[0];
   const int n_rga = (int)ceil_div(C, hk::ABOX_CH);                    // A row groups: 32 channels at lag 0
@@ -1201,6 +1204,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
   const size_t off_rga = off;   off += (size_t)round_up((int64_t)n_rga_pad * (int64_t)sizeof(int4), 1024);
   const size_t off_oia = off;   off += (size_t)round_up((int64_t)n_rga_pad * hk::RG_ROWS * (int64_t)sizeof(int), 1024);
   const size_t off_seg = off;   off += (size_t)round_up((int64_t)n_seg * (int64_t)sizeof(SegEdge), 1024);
+  const size_t off_inva = off;  off += (size_t)round_up((int64_t)n_rga_pad * hk::RG_ROWS * (int64_t)sizeof(float), 1024);
   const int64_t n_out = batched ? n_seg : 1;
   const size_t off_ct = off;    off += (size_t)round_up(n_out * pl.Dz * ldc * (int64_t)sizeof(float), 1024);
   if (bytes_only) { *bytes_only = off; return TD_OK; }
@@ -1296,10 +1300,20 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     base = reinterpret_cast<const float*>(ws + pl.off_stage[0]);
   }
   CUtensorMap tmap, tmap_a;
-  rc = make_tmap_raw(&tmap, base, pl.n_rows[0], C, pl.ld_eff[0]);
+  const int c_map = f16 ? (int)pl.ld_eff[0] : C;      // (the pre-split copy has real zeros up to ld_eff)
+  rc = make_tmap_raw(&tmap, base, pl.n_rows[0], c_map, pl.ld_eff[0]);
   if (rc) return rc;
-  rc = make_tmap_raw(&tmap_a, base, pl.n_rows[0], C, pl.ld_eff[0], hk::ABOX_CH, hk::ABOX_FRAMES);
+  rc = make_tmap_raw(&tmap_a, base, pl.n_rows[0], c_map, pl.ld_eff[0], hk::ABOX_CH, hk::ABOX_FRAMES);
   if (rc) return rc;
+  if (f16) {
+    const unsigned* amax = reinterpret_cast<const unsigned*>(ws + pl.off_amax[0]);
+    row_inv_scale_kernel<<<(unsigned)ceil_div(pl.Dpad, 256), 256, 0, st>>>(
+        reinterpret_cast<const int*>(ws + pl.off_outidx), pl.Dpad, 0, C, 0, amax, amax, reinterpret_cast<float*>(ws + pl.off_inv));
+    const int64_t n_a = (int64_t)n_rga_pad * hk::RG_ROWS;
+    row_inv_scale_kernel<<<(unsigned)ceil_div(n_a, 256), 256, 0, st>>>(
+        reinterpret_cast<const int*>(ws + off_oia), n_a, 0, C, 0, amax, amax, reinterpret_cast<float*>(ws + off_inva));
+    TD_CHECK_CUDA(cudaGetLastError());
+  }
   float* Ct = reinterpret_cast<float*>(ws + off_ct);
   TD_CHECK_CUDA(cudaMemsetAsync(Ct, 0, (size_t)n_out * pl.Dz * ldc * sizeof(float), st));
   if (pl.NK > 0) {
@@ -1308,8 +1322,8 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     P.ktiles = reinterpret_cast<const int4*>(ws + pl.off_ktiles);
     P.out_idx = reinterpret_cast<const int*>(ws + pl.off_outidx);
     P.rect_ta = ta;
-    P.inv_scale = nullptr;
-    P.inv_scale_a = nullptr;
+    P.inv_scale = f16 ? reinterpret_cast<const float*>(ws + pl.off_inv) : nullptr;
+    P.inv_scale_a = f16 ? reinterpret_cast<const float*>(ws + off_inva) : nullptr;
     P.rgs_a = reinterpret_cast<const int4*>(ws + off_rga);
     P.out_idx_a = reinterpret_cast<const int*>(ws + off_oia);
     P.G = Ct;
@@ -1317,7 +1331,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     P.batch_stride = batched ? pl.Dz * ldc : 0;
     P.ntri = ta * pl.nt;
     P.NK = pl.NK;
-    const int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : 128;
+    const int chunk_rows = (opt && opt->chunk_rows > 0) ? opt->chunk_rows : (f16 ? 256 : 128);
     P.chunk_kt = std::max(1, chunk_rows / BK);
     int64_t sc_rows = (opt && opt->superchunk_rows > 0) ? opt->superchunk_rows : 0;
     if (sc_rows == 0) sc_rows = std::max<int64_t>((48LL << 20) / (pl.ld_eff[0] * 4), 4096);
@@ -1341,11 +1355,13 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
       }
       TD_CHECK_CUDA(cudaEventRecord(g_ev_start, st));
     }
-    TD_CHECK_CUDA(cudaFuncSetAttribute(hk::lagged_gram_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::RECT_SMEM_BYTES));
+    auto kernel = f16 ? hk::lagged_gram_halo_kernel<true, true> : hk::lagged_gram_halo_kernel<true, false>;
+    const size_t smem_bytes = f16 ? hk::F16_RECT_SMEM_BYTES : hk::RECT_SMEM_BYTES;
+    TD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * 2);
-    cfg.blockDim = dim3(hk::NUM_THREADS);
-    cfg.dynamicSmemBytes = hk::RECT_SMEM_BYTES;
+    cfg.blockDim = dim3(f16 ? hk::NUM_THREADS_F16 : hk::NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1354,7 +1370,7 @@ int run_toeplitz(const td_stream* streams, int n_streams, const int64_t* seg_fir
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hk::lagged_gram_halo_kernel<true, false>, tmap, tmap_a, P));
+    TD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, tmap_a, P));
     TD_CHECK_CUDA(cudaGetLastError());
     if (timed) {
       TD_CHECK_CUDA(cudaEventRecord(g_ev_stop, st));
