@@ -70,6 +70,17 @@ static_assert(8 * NUM_BARRIERS + 8 <= 256, "barrier block too small");
 // [64, 128) of ONE 128-byte swizzled row, so a stage is 16 KiB of B + 12 KiB of raw boxes and eight
 // stages fit.  The raw ring has to be deep: a stage is busy from the TMA issue to the retirement of the
 // MMAs that read it (TMA latency + conversion + MMA + commit, ~4000 clocks), a k-tile lasts 768.
+// Both flavours run at the board's power limit, so a warp that only waits should not spin: the TMA
+// producer (its ring is normally full), the epilogue warps (idle for most of a chunk) and the MMA
+// issuers (they wait for the converters 9 polls out of 10) sleep between polls.  Measured at the cfg 4
+// width: 703 -> 686 ms with the first two, -> 667 ms with the issuers (any value from 20 to 200 ns);
+// sleeping converter waits change nothing (the converters rarely wait).
+#ifndef TD_F16_SLEEP_NS
+#define TD_F16_SLEEP_NS 100
+#endif
+#ifndef TD_F16_ISSUER_SLEEP_NS
+#define TD_F16_ISSUER_SLEEP_NS 40
+#endif
 #ifndef TD_F16_STAGES
 #define TD_F16_STAGES 6
 #endif
@@ -231,7 +242,8 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
         for (long long kt = it.kt_begin; kt < it.kt_end; ++kt) {
           const int4 kc = kn;
           if (kt + 1 < it.kt_end) kn = __ldg(&P.ktiles[2 * (kt + 1)]);
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          if constexpr (F16) ptx::mbar_wait_relaxed<TD_F16_SLEEP_NS>(empty_bar(stage), phase ^ 1u);   // the ring is normally full: this warp only waits
+          else ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           if (ptx::elect_one()) {
             const uint32_t fb = full_bar(stage);
             ptx::mbar_expect_tx(fb, tx_bytes);
@@ -287,7 +299,8 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
               // [16 + 8s, ...); 32 bytes of a B row per step).  Frames outside the call's row range are
               // zero in A, so partial k-tiles need no skipping.
               const uint32_t slot = kcount & (A_SLOTS - 1);
-              ptx::mbar_wait_lean(ready_bar(slot), (kcount >> 2) & 1u);
+              if constexpr (TD_F16_ISSUER_SLEEP_NS > 0) ptx::mbar_wait_relaxed<TD_F16_ISSUER_SLEEP_NS>(ready_bar(slot), (kcount >> 2) & 1u);
+              else ptx::mbar_wait_lean(ready_bar(slot), (kcount >> 2) & 1u);
               ptx::tc_fence_after();
               if (ptx::elect_one()) {
                 const uint32_t a_base = tmem_base + A_COL0 + slot * A_SLOT_COLS;
@@ -578,7 +591,8 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
       for (long long c0 = it.kt_begin; c0 < it.kt_end; c0 += P.chunk_kt) {
         ring.next_chunk(half);
         const int r = ring.r;
-        ptx::mbar_wait(tfull_bar(half, r), ring.n);
+        if constexpr (F16) ptx::mbar_wait_relaxed<TD_F16_SLEEP_NS>(tfull_bar(half, r), ring.n);     // idle for most of a chunk
+        else ptx::mbar_wait(tfull_bar(half, r), ring.n);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)r * ACC_COLS;
         if constexpr (F16) {                 // 144 registers: 16 columns at a time

@@ -118,6 +118,20 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
   mbar_wait_slow(bar, parity);
 }
 
+// Wait of a warp that has nothing else to do and can afford to wake up late: sleeps between polls
+// instead of spinning (a polling warp costs issue slots and power the tensor pipe could use).
+template <int NS>
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t i = 0; !mbar_try_wait(bar, parity); ++i) {
+    __nanosleep(NS);
+    if (i > (1u << 28)) {
+      printf("tdgram: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

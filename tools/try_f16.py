@@ -94,6 +94,9 @@ if what == 'power':
     for _, _, r in samples: reasons |= r
     print('method %d chunk %d: kernel ms %s | SM clock median %d (min %d max %d) MHz, power median %.0f W (max %.0f), throttle bits 0x%x, %d samples' %
           (m, cr, ' '.join('%.0f' % t for t in ts), clk[len(clk) // 2], clk[0], clk[-1], pw[len(pw) // 2], pw[-1], reasons, len(samples)), flush=True)
+if what == 'quick':
+  timeit('cfg2', 60, 7680, 64, 32, reps=5, methods=(6,))
+  timeit('cfg4 slice', 3, 100000, 306, 100, reps=4, methods=(6,))
 if what == 'prof':
   timeit('cfg4 slice', 3, 100000, 306, 100, reps=1, methods=(6,))
 if what == 'prof2':
