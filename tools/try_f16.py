@@ -33,7 +33,7 @@ def check(lens, c, pre, post, methods=(4, 6), reps=3, chunk_rows=0):
       errs.append(np.linalg.norm(got - want) / np.linalg.norm(want))
     print('[chunk_rows %d] ' % chunk_rows + 'lens %s c %d lags %d method %d: rel fro %s' % (lens, c, pre + post + 1, m, ' '.join('%.2e' % e for e in errs)), flush=True)
 
-def timeit(name, n_trials, frames, c, lags, methods=(4, 6), reps=3, chunk_rows=0):
+def timeit(name, n_trials, frames, c, lags, methods=(4, 6), reps=3, chunk_rows=0, superchunk_rows=0):
   gen = torch.Generator(device='cuda'); gen.manual_seed(1)
   x = torch.randn((n_trials * frames, c), generator=gen, device='cuda')
   starts = [i * frames for i in range(n_trials)]; lens = [frames] * n_trials
@@ -43,7 +43,7 @@ def timeit(name, n_trials, frames, c, lags, methods=(4, 6), reps=3, chunk_rows=0
   f_alg = float(n_trials * frames) * d * (d + 1)
   ref = None
   for m in methods:
-    opt = ops.gram_options(method=m, cta_group=2, timed=True, chunk_rows=chunk_rows)
+    opt = ops.gram_options(method=m, cta_group=2, timed=True, chunk_rows=chunk_rows, superchunk_rows=superchunk_rows)
     ts = []
     for _ in range(reps + 1):
       ops.lagged_gram([s], lens, out=G, options=opt)
@@ -52,7 +52,7 @@ def timeit(name, n_trials, frames, c, lags, methods=(4, 6), reps=3, chunk_rows=0
     k = min(ts[1:])
     blk = G[:c, :c].double().clone()
     if ref is None: ref = blk
-    print('[chunk_rows %d] ' % chunk_rows + '%s method %d: kernel %.3f ms  %.1f TFLOP/s alg  (block diff vs first %.1e)' %
+    print('[chunk_rows %d superchunk_rows %d] ' % (chunk_rows, superchunk_rows) + '%s method %d: kernel %.3f ms  %.1f TFLOP/s alg  (block diff vs first %.1e)' %
           (name, m, k, f_alg / k / 1e9, float((blk - ref).norm() / ref.norm())), flush=True)
 
 what = sys.argv[1] if len(sys.argv) > 1 else 'all'
@@ -94,6 +94,9 @@ if what == 'power':
     for _, _, r in samples: reasons |= r
     print('method %d chunk %d: kernel ms %s | SM clock median %d (min %d max %d) MHz, power median %.0f W (max %.0f), throttle bits 0x%x, %d samples' %
           (m, cr, ' '.join('%.0f' % t for t in ts), clk[len(clk) // 2], clk[0], clk[-1], pw[len(pw) // 2], pw[-1], reasons, len(samples)), flush=True)
+if what == 'sc':
+  for sc in (9984, 19968, 39936, 79872, 159744):
+    timeit('cfg4 slice', 3, 100000, 306, 100, reps=1, methods=(6,), superchunk_rows=sc)
 if what == 'quick':
   timeit('cfg2', 60, 7680, 64, 32, reps=5, methods=(6,))
   timeit('cfg4 slice', 3, 100000, 306, 100, reps=4, methods=(6,))
