@@ -142,10 +142,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
 
 // L2 residency hints.  A superchunk of raw frames (~48 MB) is swept by every tile and should stay in
 // L2; the partial tiles the epilogues red.add into G (ntri x 256 KB per superchunk, gigabytes) stream
-// through it exactly once.  Without hints the stream evicts the raw frames (measured: 15 % of the raw
-// TMA boxes missed L2, 1.8 TB of DRAM reads per cfg 4 hour).
+// through it exactly once.  Measured at the cfg 4 width on one box: no hints 656 ms, raw boxes
+// evict_last only 658, partials evict_first only 651, both 631 ms.  (The DRAM byte counts do not
+// move -- 76 GB read + 28 GB written per 300 000 frames either way, ~6.5 % of the raw boxes miss L2
+// for every superchunk size from 12 to 48 MB -- the gain is in L2 / crossbar time and power.)
 #ifndef TD_HALO_L2_HINTS
 #define TD_HALO_L2_HINTS 1
+#endif
+#ifndef TD_HALO_L2_HINT_TMA
+#define TD_HALO_L2_HINT_TMA TD_HALO_L2_HINTS
+#endif
+#ifndef TD_HALO_L2_HINT_RED
+#define TD_HALO_L2_HINT_RED TD_HALO_L2_HINTS
 #endif
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;
@@ -285,11 +293,11 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
                 const int c0 = (int)(rg[i] >> 17);
                 const int d0 = ((int)(rg[i] << 15)) >> 17;          // sign-extended 15-bit lag shift
                 if (RECT && i < RG_PER_CTA) {
-                  if (TD_HALO_L2_HINTS) tma_load_2d_hint(sbase + OFF_ARAW + i * ABOX_BYTES, &tmap1, fb, c0, kc.x + d0, keep_policy);
+                  if (TD_HALO_L2_HINT_TMA) tma_load_2d_hint(sbase + OFF_ARAW + i * ABOX_BYTES, &tmap1, fb, c0, kc.x + d0, keep_policy);
                   else tma_load_2d(sbase + OFF_ARAW + i * ABOX_BYTES, &tmap1, fb, c0, kc.x + d0);
                 } else {
                   const uint32_t dst = sbase + (i < RG_PER_CTA ? OFF_ARAW : OFF_BRAW) + (i & (RG_PER_CTA - 1)) * BOX_BYTES;
-                  if (TD_HALO_L2_HINTS) tma_load_2d_hint(dst, (!RECT && q) ? &tmap1 : &tmap0, fb, c0, (q ? kc.y : kc.x) + d0, keep_policy);
+                  if (TD_HALO_L2_HINT_TMA) tma_load_2d_hint(dst, (!RECT && q) ? &tmap1 : &tmap0, fb, c0, (q ? kc.y : kc.x) + d0, keep_policy);
                   else tma_load_2d(dst, (!RECT && q) ? &tmap1 : &tmap0, fb, c0, (q ? kc.y : kc.x) + d0);
                 }
               }
@@ -669,7 +677,7 @@ lagged_gram_halo_kernel(const __grid_constant__ CUtensorMap tmap0,
         if (m_out >= 0 && n_out >= 0 && (all_pairs || n_row <= m_row)) {
           float v = acc[i];
           if constexpr (F16) v = (v * inv_m) * __ldg(&P.inv_scale[n_row]);     // exact: powers of two
-          if (TD_HALO_L2_HINTS) red_add_f32_hint(Gout + (long long)n_out * P.ldg + m_out, v, stream_policy);
+          if (TD_HALO_L2_HINT_RED) red_add_f32_hint(Gout + (long long)n_out * P.ldg + m_out, v, stream_policy);
           else atomicAdd(Gout + (long long)n_out * P.ldg + m_out, v);
         }
       }
