@@ -1,5 +1,7 @@
 // CTA-pair Gram kernel that builds the lagged operand ON CHIP from a raw time tile + lag halo
-// (included by gram_umma.cu).  Method 4, the default for CTA pairs.
+// (included by gram_umma.cu).  Two flavours of one template: 3xTF32 on the caller's fp32 array
+// (method 4, described first) and fp16 x 3 on a pre-split copy (method 6, the default for CTA pairs;
+// see the template's comment and DESIGN.md section 3 for what differs).
 //
 // The earlier kernels (gram_ts.cuh, lagged_gram_umma_kernel) fetch every (lag, channel-block) row
 // group of an operand tile as its own TMA box from four shifted channel-major copies of the
@@ -21,7 +23,8 @@
 //   * MMA issue, accumulator regions, epilogue and barriers are those of gram_ts.cuh.
 //
 // The Hankel matrix never exists anywhere: HBM holds the raw recording once (a padded copy only if
-// the caller's row stride is not a multiple of 16 bytes, which TMA requires).
+// the caller's row stride is not a multiple of 16 bytes, which TMA requires; the fp16 x 3 flavour
+// reads its pre-split copy instead -- the same 4 bytes per sample).
 
 namespace hk {
 

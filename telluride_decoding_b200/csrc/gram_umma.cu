@@ -1,4 +1,10 @@
-// Lagged (implicit-Hankel) Gram on tcgen05 tensor cores, 3xTF32, for sm_100a.
+// Lagged (implicit-Hankel) Gram on tcgen05 tensor cores, split operands (fp16 x 3 / 3xTF32), for sm_100a.
+//
+// The default for designs of >= 512 columns is hk::lagged_gram_halo_kernel (gram_halo.cuh, methods 6
+// and 4: the lagged operand is built on chip from a raw TMA tile + lag halo); its host side -- plan,
+// tables, the pre-split copy of the fp16 x 3 flavour, the block-Toeplitz method 5 -- is in this file
+// below the round-1 kernels, which are described first and remain for narrow designs (method 2 with
+// single CTAs) and as selectable flavours (methods 2 and 3):
 //
 // Replaces the reference's minibatch loop `sum_xtx += np.matmul(x.T, x)` over the materialised
 // lagged design (telluride_decoding/brain_model.py:429-444, cca.py:311-332; the design itself is
@@ -16,8 +22,7 @@
 //      hi*hi + hi*lo + lo*hi tcgen05.mma into TMEM; every `chunk` k-tiles the accumulator is drained
 //      into fp32 registers (bounds the tensor-core accumulation length).  Two flavours:
 //        * ts::lagged_gram_ts_kernel (gram_ts.cuh): CTA pairs, A operand written to TENSOR memory by
-//          the converter warps, two MMA issuing warps, three rotating accumulator regions.  Default
-//          for designs of >= 512 columns.
+//          the converter warps, two MMA issuing warps, three rotating accumulator regions (method 3).
 //        * lagged_gram_umma_kernel<CG> (below): both operands from shared memory.
 //            warp 0      TMA producer, 3-stage ring
 //            warps 10-11 converters (lo tile + masking of frames that are not design rows)
